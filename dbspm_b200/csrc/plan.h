@@ -1,0 +1,13 @@
+// plan.h -- host-side FFT plan: radix schedule, twiddle table, frequency->position table.
+#pragma once
+#include <vector>
+#include "fft_core.h"
+
+struct HostPlan {
+    FftPlanDev dev;
+    std::vector<cplx> tw;       // tw[e] = exp(-2 pi i e / n)
+    std::vector<int> pos_of;    // pos_of[K] = in-place position holding frequency K after the DIF stages
+};
+
+// returns false if n has a prime factor > DBSPM_MAX_RADIX or needs too many stages
+bool dbspm_make_plan(int n, HostPlan &out);

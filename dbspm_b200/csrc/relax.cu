@@ -1,0 +1,132 @@
+// relax.cu -- sm_100a kernels + C ABI for the relax step, the static-potential assembly and
+// the two "next" rows (tricubic gather, dE/dz).  Compiled with --fmad=false: the Powell
+// bookkeeping must use separate multiply and add like numpy/scipy; the interpolation stencil
+// asks for fused multiply-adds explicitly (fma()).
+// Replaces dbspm:479-486, dbspm:558-605, pydbspm/interactions.py:49-105, grid.py:325-386.
+#include "capi_common.h"
+#include "relax_body.h"
+
+#define RELAX_THREADS 128
+
+__global__ void __launch_bounds__(RELAX_THREADS) relax_kernel(const __grid_constant__ RelaxParams P, long long ncol)
+{
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < ncol) relax_column_body(P, col);
+}
+
+__global__ void __launch_bounds__(256) accumulate_kernel(double *acc, const double *comp, double scale, size_t n, int init)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double term = comp[i] * scale;             // numpy: temp = comp * scale
+        acc[i] = init ? (0.0 + term) : (acc[i] + term);  //        static += temp
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const double *data, int nx, int ny, int nz,
+                                                     const double *pts, size_t npts, double *out)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += stride)
+        out[i] = tricubic_eval(data, nx, ny, nz, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+}
+
+// np.gradient(E, -dz, axis=2): central differences inside, one-sided first order at the ends
+__global__ void __launch_bounds__(256) gradz_kernel(const double *E, long long ncol, int nz, double h, double *out)
+{
+    const long long total = ncol * nz;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int k = (int)(i % nz);
+        double g;
+        if (nz == 1) g = 0.0;
+        else if (k == 0) g = (E[i + 1] - E[i]) / h;
+        else if (k == nz - 1) g = (E[i] - E[i - 1]) / h;
+        else g = (E[i + 1] - E[i - 1]) / (2.0 * h);
+        out[i] = g;
+    }
+}
+
+static unsigned grid_for(size_t n, int threads)
+{
+    size_t b = (n + threads - 1) / threads;
+    const size_t cap = 148 * 16;                        // a few waves of the 148 SMs
+    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+static bool inv3(const double m[9], double out[9])
+{
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    if (det == 0.0 || !isfinite(det)) return false;
+    out[0] = (e * i - f * h) / det; out[1] = (c * h - b * i) / det; out[2] = (b * f - c * e) / det;
+    out[3] = (f * g - d * i) / det; out[4] = (a * i - c * g) / det; out[5] = (c * d - a * f) / det;
+    out[6] = (d * h - e * g) / det; out[7] = (b * g - a * h) / det; out[8] = (a * e - b * d) / det;
+    return true;
+}
+
+extern "C" int dbspm_static_accumulate_f64(double *acc, const double *comp, double scale, size_t n,
+                                           int init, void *stream)
+{
+    DBSPM_REQUIRE(acc && comp, DBSPM_EINVAL, "null pointer argument");
+    if (n == 0) return DBSPM_OK;
+    accumulate_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(acc, comp, scale, n, init);
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    return DBSPM_OK;
+}
+
+extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
+                                      int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                                      double kappa, double rpivot, const double dr[3], const double *dR,
+                                      double xtol, double ftol, int maxfev,
+                                      double *out_E_theta_phi, double *out_cart, int *out_nfev, void *stream)
+{
+    DBSPM_REQUIRE(static_win && dr && out_E_theta_phi, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nzc >= 1, DBSPM_EINVAL, "bad grid shape (%d,%d,%d)", nx, ny, nzc);
+    DBSPM_REQUIRE(i_lo <= i_hi && j_lo <= j_hi && nz_relax >= 0, DBSPM_EINVAL, "bad tile");
+    DBSPM_REQUIRE(dr[0] > 0 && dr[1] > 0 && dr[2] > 0, DBSPM_EINVAL, "grid spacings must be positive");
+    DBSPM_REQUIRE(maxfev >= 1, DBSPM_EINVAL, "maxfev must be >= 1");
+    RelaxParams P;
+    P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc;
+    P.i_lo = i_lo; P.i_hi = i_hi; P.j_lo = j_lo; P.j_hi = j_hi; P.nz_relax = nz_relax;
+    P.kappa = kappa; P.rpivot = rpivot;
+    P.npivot = rpivot / dr[2];
+    P.rpivot_rt = P.npivot * dr[2];
+    P.dr[0] = dr[0]; P.dr[1] = dr[1]; P.dr[2] = dr[2];
+    P.noortho = dR != nullptr;
+    for (int q = 0; q < 9; ++q) P.Minv[q] = 0.0;
+    if (dR) {
+        const double dRT[9] = {dR[0], dR[3], dR[6], dR[1], dR[4], dR[7], dR[2], dR[5], dR[8]};
+        DBSPM_REQUIRE(inv3(dRT, P.Minv), DBSPM_EINVAL, "dR is singular");
+    }
+    P.xtol = xtol; P.ftol = ftol; P.maxfev = maxfev; P.maxiter = 2000;   // N*1000 (_optimize.py:3514-3516)
+    P.out_etp = out_E_theta_phi; P.out_cart = out_cart; P.out_nfev = out_nfev;
+    const long long ncol = (long long)(i_hi - i_lo) * (j_hi - j_lo);
+    if (ncol == 0 || nz_relax == 0) return DBSPM_OK;
+    const long long blocks = (ncol + RELAX_THREADS - 1) / RELAX_THREADS;
+    DBSPM_REQUIRE(blocks < 2147483647LL, DBSPM_EUNSUPPORTED, "tile too large");
+    relax_kernel<<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    return DBSPM_OK;
+}
+
+extern "C" int dbspm_tricubic_gather_f64(const double *data, int nx, int ny, int nz,
+                                         const double *pts, size_t npts, double *out, void *stream)
+{
+    DBSPM_REQUIRE(data && pts && out, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1, DBSPM_EINVAL, "bad grid shape");
+    if (npts == 0) return DBSPM_OK;
+    gather_kernel<<<grid_for(npts, 256), 256, 0, (cudaStream_t)stream>>>(data, nx, ny, nz, pts, npts, out);
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    return DBSPM_OK;
+}
+
+extern "C" int dbspm_dfz_gradient_f64(const double *E, int nx, int ny, int nz, double dz, double *out, void *stream)
+{
+    DBSPM_REQUIRE(E && out, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1 && dz != 0.0, DBSPM_EINVAL, "bad arguments");
+    const long long ncol = (long long)nx * ny;
+    gradz_kernel<<<grid_for((size_t)ncol * nz, 256), 256, 0, (cudaStream_t)stream>>>(E, ncol, nz, -dz, out);
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    return DBSPM_OK;
+}

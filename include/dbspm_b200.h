@@ -1,0 +1,93 @@
+/*
+ * dbspm_b200.h -- C ABI of libdbspm_b200.so: the B200 (sm_100a) replacement for the
+ * data-parallel hot path of SPMTH/DBSPM (sr / es interaction grids and the relax step).
+ *
+ * The reference is pure Python and has no FFI layer; the "interface each entry point
+ * replaces" is therefore a Python function or a block of the `dbspm` driver script
+ * (paths relative to the reference repository):
+ *
+ *   dbspm_corr3d_f64            pydbspm/interactions.py:9-22  get_density_overlap()
+ *                               + the `**ALPHA` on both densities and the window slice
+ *                               `sr[denscalc.nidx]` at dbspm:329-330 / dbspm:348-349
+ *   dbspm_static_accumulate_f64 dbspm:479-486  static += sr*V ; static += es ; static += vdw
+ *   dbspm_relax_powell_f64      dbspm:558-581 (tricubic(...) + loop over lateral points)
+ *                               -> pydbspm/interactions.py:70-105 relax_tip_z /
+ *                               relax_noortho_tip_z -> scipy.optimize.minimize("Powell")
+ *                               -> tricubic .ip ; plus sph2cart at dbspm:603-605
+ *   dbspm_tricubic_gather_f64   pydbspm/grid.py:325-361 interpolate_data (tricubic .ip at
+ *                               explicit index-space points; also grid.py:122-139)
+ *   dbspm_dfz_gradient_f64      pydbspm/SPMGrid.py:375-379 np.gradient(E, -dz, axis=2)
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer to C-contiguous float64 memory (z fastest),
+ *     owned by the caller for the whole call (e.g. a torch.cuda tensor's data_ptr());
+ *   - no persistent allocation except cached FFT tables (a few KB per distinct length);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default);
+ *     calls return after enqueueing, they do not synchronise;
+ *   - return value 0 = success, negative = DBSPM_E* below; dbspm_last_error() gives a
+ *     thread-local message; no C++ exception crosses this boundary;
+ *   - one host thread per GPU; the library never changes the current device.
+ */
+#ifndef DBSPM_B200_H
+#define DBSPM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBSPM_OK              0
+#define DBSPM_EINVAL         -1   /* bad argument (NULL pointer, non-positive size, bad window) */
+#define DBSPM_EUNSUPPORTED   -2   /* shape not supported (odd nz, prime factor > 31 in a length) */
+#define DBSPM_EWORKSPACE     -3   /* workspace too small or misaligned */
+#define DBSPM_ECUDA          -4   /* a CUDA runtime call / kernel launch failed */
+
+/* flags for dbspm_corr3d_f64 */
+#define DBSPM_CORR_DEFAULT    0
+
+/* library / build identification: "dbspm_b200 <version> sm_100a" */
+const char *dbspm_version(void);
+const char *dbspm_last_error(void);
+
+/* ---- sr / es: periodic 3-D cross-correlation, output restricted to a z-window ------------
+ * E_win[x,y,z-z_lo] = dV * sum_r A[r]^alphaA * B[(r - R) mod N]^alphaB ,  R = (x,y,z), z in [z_lo,z_hi)
+ * A, B: (nx,ny,nz); E_win: (nx,ny,z_hi-z_lo).  alpha == 1.0 skips the power.
+ * Requires nz even, 0 <= z_lo < z_hi <= nz, and nx, ny, nz/2 with prime factors <= 31.
+ * workspace: at least dbspm_corr3d_workspace_bytes(...) bytes, 256-byte aligned.           */
+size_t dbspm_corr3d_workspace_bytes(int nx, int ny, int nz, int z_lo, int z_hi, int flags);
+int dbspm_corr3d_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                     int nx, int ny, int nz, int z_lo, int z_hi, double *E_win,
+                     void *workspace, size_t workspace_bytes, int flags, void *stream);
+
+/* ---- static potential assembly: acc = (init ? 0 : acc) + comp*scale  (separate mul, add) -- */
+int dbspm_static_accumulate_f64(double *acc, const double *comp, double scale, size_t n,
+                                int init, void *stream);
+
+/* ---- relax: Powell minimisation of E(theta,phi) at every tip position of a lateral tile ---
+ * static_win: (nx,ny,nzc) window potential, periodic in all three axes for interpolation.
+ * Lateral tile i in [i_lo,i_hi), j in [j_lo,j_hi); z indices k = 0..nz_relax-1 swept from the
+ * top down with warm start.  rpivot in Angstrom, dr = grid spacings; npivot = rpivot/dr[2] and
+ * the pivot plane index is trunc(k + npivot) exactly as the reference's int64 origin does.
+ * dR: 9 doubles (row-major 3x3 lattice step matrix) selects the non-orthogonal offset
+ * inv(dR^T).(x,y,z); NULL selects the orthogonal path.
+ * out_E_theta_phi: (ni,nj,nz_relax,3) rows [E_min, theta, phi]
+ * out_cart:        (3,ni,nj,nz_relax) tip_x, tip_y, tip_z = sph2cart(theta, phi, rpivot); nullable
+ * out_nfev:        (ni,nj,nz_relax) objective evaluations per position; nullable            */
+int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
+                           int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                           double kappa, double rpivot, const double dr[3], const double *dR,
+                           double xtol, double ftol, int maxfev,
+                           double *out_E_theta_phi, double *out_cart, int *out_nfev, void *stream);
+
+/* ---- tricubic gather: out[p] = interp(data)(pts[p,0], pts[p,1], pts[p,2]), index units ---- */
+int dbspm_tricubic_gather_f64(const double *data, int nx, int ny, int nz,
+                              const double *pts /* (npts,3) */, size_t npts, double *out, void *stream);
+
+/* ---- dE/dz image: out = np.gradient(E, -dz, axis=2) for E of shape (nx,ny,nz) ------------- */
+int dbspm_dfz_gradient_f64(const double *E, int nx, int ny, int nz, double dz, double *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBSPM_B200_H */

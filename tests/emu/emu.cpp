@@ -1,0 +1,144 @@
+// emu.cpp -- CPU emulation of the CUDA kernel bodies (TEST INFRASTRUCTURE ONLY).
+//
+// Compiles dbspm_b200/csrc/{corr_body.h,relax_body.h,plan.cpp} with g++ and runs each
+// CUDA block serially as a single "thread" (tid = 0, nthr = 1; BLOCK_SYNC is a no-op), so
+// the index arithmetic, FFT schedule, untangle/product algebra and the Powell state machine
+// can be checked against the oracle on a machine without a GPU.  It validates the code that
+// ships; it is not a fallback -- dbspm_b200/_lib.py only ever loads libdbspm_b200.so.
+#define DBSPM_EMU_INTERP_HOOK 1
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../dbspm_b200/csrc/corr_body.h"
+#include "../../dbspm_b200/csrc/relax_body.h"
+#include "../../dbspm_b200/csrc/plan.h"
+
+double (*dbspm_emu_interp_hook)(double, double, double) = nullptr;
+extern "C" void emu_set_interp_hook(double (*f)(double, double, double)) { dbspm_emu_interp_hook = f; }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int pick_tshift(int n, long long inner)
+{
+    for (int ts = 3; ts >= 0; --ts) {
+        if ((1LL << ts) > inner && ts > 0) continue;
+        if (axis_smem_bytes(n, ts) <= 100 * 1024) return ts;
+    }
+    return 0;
+}
+
+template <int D>
+static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, int narrays, double a0, double a1,
+                    int use_pow, int n, long long inner, long long outer, int force_tshift)
+{
+    HostPlan hp;
+    if (!dbspm_make_plan(n, hp)) return -2;
+    AxisParams P;
+    P.in[0] = in0; P.in[1] = in1; P.out[0] = out0; P.out[1] = out1;
+    P.alpha[0] = a0; P.alpha[1] = a1; P.use_pow = use_pow; P.narrays = narrays;
+    P.n = n; P.inner = inner; P.outer = outer;
+    P.tshift = force_tshift >= 0 ? force_tshift : pick_tshift(n, inner);
+    P.tiles = (inner + (1LL << P.tshift) - 1) >> P.tshift;
+    P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data();
+    std::vector<unsigned char> smem(axis_smem_bytes(n, P.tshift) + 64);
+    unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
+    for (int w = 0; w < narrays; ++w)
+        for (long long b = 0; b < outer * P.tiles; ++b) axis_pass_body<D>(P, sm, b, w, 0, 1);
+    return 0;
+}
+
+extern "C" size_t emu_corr3d_workspace_bytes(int nx, int ny, int nz, int z_lo, int z_hi)
+{
+    const size_t N = (size_t)nx * ny * nz;
+    const int nzw = z_hi - z_lo, nwh = (nzw + 1) / 2;
+    size_t bytes = 2 * align_up(N * 8, 256);
+    if (nzw & 1) bytes += align_up((size_t)nx * ny * nwh * 16, 256);
+    return bytes;
+}
+
+extern "C" int emu_corr3d_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                              int nx, int ny, int nz, int z_lo, int z_hi, double *E_win, int force_tshift)
+{
+    if (nz & 1) return -2;
+    const int n = nz / 2, nzw = z_hi - z_lo, nwh = (nzw + 1) / 2;
+    const size_t N = (size_t)nx * ny * nz;
+    std::vector<cplx> WA(N / 2), WB(N / 2), Wodd;
+    cplx *W = (cplx *)E_win;
+    if (nzw & 1) { Wodd.resize((size_t)nx * ny * nwh); W = Wodd.data(); }
+    int rc;
+    if ((rc = run_axis<-1>((const cplx *)A, WA.data(), (const cplx *)B, WB.data(), 2, alphaA, alphaB, 1, nx, (long long)ny * n, 1, force_tshift))) return rc;
+    if ((rc = run_axis<-1>(WA.data(), WA.data(), WB.data(), WB.data(), 2, 1.0, 1.0, 0, ny, n, nx, force_tshift))) return rc;
+    {
+        HostPlan hp, hpN;
+        if (!dbspm_make_plan(n, hp) || !dbspm_make_plan(nz, hpN)) return -2;
+        ZFusedParams P;
+        P.ZA = WA.data(); P.ZB = WB.data(); P.W = W;
+        P.nx = nx; P.ny = ny; P.n = n; P.nwh = nwh; P.z_lo = z_lo;
+        P.scale = dV / ((double)nx * (double)ny * (double)nz) * 0.25;
+        P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data(); P.twN = hpN.tw.data();
+        P.npairs = (long long)(nx / 2 + 1) * ny;
+        std::vector<unsigned char> smem(zfused_smem_bytes(n) + 64);
+        unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
+        for (long long b = 0; b < (P.npairs + ZL - 1) / ZL; ++b) zfused_body(P, sm, b, 0, 1);
+    }
+    if ((rc = run_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, force_tshift))) return rc;
+    if ((rc = run_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)ny * nwh, 1, force_tshift))) return rc;
+    if (nzw & 1) compact_body((const double *)W, E_win, (long long)nx * ny, nzw, 2 * nwh, 0, 1);
+    return 0;
+}
+
+// plain 1-D FFT of T interleaved lines through the tile routine (plan / butterfly unit test)
+extern "C" int emu_fft_lines(const double *in, double *out, int n, int tshift, int dir)
+{
+    HostPlan hp;
+    if (!dbspm_make_plan(n, hp)) return -2;
+    const int T = 1 << tshift;
+    std::vector<cplx> s((size_t)n * T);
+    memcpy(s.data(), in, sizeof(cplx) * s.size());
+    if (dir < 0) fft_tile<-1>(s.data(), T, tshift, hp.dev, hp.tw.data(), 0, 1);
+    else fft_tile<1>(s.data(), T, tshift, hp.dev, hp.tw.data(), 0, 1);
+    cplx *o = (cplx *)out;
+    for (int K = 0; K < n; ++K)
+        for (int t = 0; t < T; ++t) o[(size_t)K * T + t] = s[(size_t)hp.pos_of[K] * T + t];
+    return hp.dev.nstages;
+}
+
+static bool inv3(const double m[9], double out[9])
+{
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    if (det == 0.0) return false;
+    out[0] = (e * i - f * h) / det; out[1] = (c * h - b * i) / det; out[2] = (b * f - c * e) / det;
+    out[3] = (f * g - d * i) / det; out[4] = (a * i - c * g) / det; out[5] = (c * d - a * f) / det;
+    out[6] = (d * h - e * g) / det; out[7] = (b * g - a * h) / det; out[8] = (a * e - b * d) / det;
+    return true;
+}
+
+extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
+                                    int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                                    double kappa, double rpivot, const double dr[3], const double *dR,
+                                    double xtol, double ftol, int maxfev,
+                                    double *out_etp, double *out_cart, int *out_nfev)
+{
+    RelaxParams P;
+    P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc;
+    P.i_lo = i_lo; P.i_hi = i_hi; P.j_lo = j_lo; P.j_hi = j_hi; P.nz_relax = nz_relax;
+    P.kappa = kappa; P.rpivot = rpivot; P.npivot = rpivot / dr[2]; P.rpivot_rt = P.npivot * dr[2];
+    P.dr[0] = dr[0]; P.dr[1] = dr[1]; P.dr[2] = dr[2];
+    P.noortho = dR != nullptr;
+    for (int q = 0; q < 9; ++q) P.Minv[q] = 0.0;
+    if (dR) {
+        const double dRT[9] = {dR[0], dR[3], dR[6], dR[1], dR[4], dR[7], dR[2], dR[5], dR[8]};
+        if (!inv3(dRT, P.Minv)) return -1;
+    }
+    P.xtol = xtol; P.ftol = ftol; P.maxfev = maxfev; P.maxiter = 2000;
+    P.out_etp = out_etp; P.out_cart = out_cart; P.out_nfev = out_nfev;
+    const long long ncol = (long long)(i_hi - i_lo) * (j_hi - j_lo);
+    for (long long c = 0; c < ncol; ++c) relax_column_body(P, c);
+    return 0;
+}
+
+extern "C" double emu_tricubic(const double *g, int nx, int ny, int nz, double x, double y, double z)
+{
+    return tricubic_eval(g, nx, ny, nz, x, y, z);
+}
