@@ -136,13 +136,17 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
 
     int rc;
     // forward x (out of place, power fused into the load), then y in place
-    rc = launch_axis<-1>((const cplx *)A, WA, (const cplx *)B, WB, 2, alphaA, alphaB, 1, nx, (long long)ny * n, 1, st);
-    if (rc) return rc;
-    rc = launch_axis<-1>(WA, WA, WB, WB, 2, 1.0, 1.0, 0, ny, n, nx, st);
-    if (rc) return rc;
+    if (!(flags & DBSPM_CORR_SKIP_XFWD)) {
+        rc = launch_axis<-1>((const cplx *)A, WA, (const cplx *)B, WB, 2, alphaA, alphaB, 1, nx, (long long)ny * n, 1, st);
+        if (rc) return rc;
+    }
+    if (!(flags & DBSPM_CORR_SKIP_YFWD)) {
+        rc = launch_axis<-1>(WA, WA, WB, WB, 2, 1.0, 1.0, 0, ny, n, nx, st);
+        if (rc) return rc;
+    }
 
     // fused z: forward, untangle, product, window phase, pruned inverse
-    {
+    if (!(flags & DBSPM_CORR_SKIP_Z)) {
         DevPlan *pl = nullptr, *plN = nullptr;
         rc = get_plan(n, st, &pl);
         if (rc) return rc;
@@ -164,10 +168,14 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
     }
 
     // inverse y, then x on the packed window (in place)
-    rc = launch_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, st);
-    if (rc) return rc;
-    rc = launch_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)ny * nwh, 1, st);
-    if (rc) return rc;
+    if (!(flags & DBSPM_CORR_SKIP_YINV)) {
+        rc = launch_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, st);
+        if (rc) return rc;
+    }
+    if (!(flags & DBSPM_CORR_SKIP_XINV)) {
+        rc = launch_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)ny * nwh, 1, st);
+        if (rc) return rc;
+    }
 
     if (nzw & 1) {
         const long long ncol = (long long)nx * ny;

@@ -1,0 +1,243 @@
+"""GPU versions of the reference's hot-path operators (pydbspm/interactions.py).
+
+Same names, argument meaning and return layout as the reference so callers can switch:
+
+  get_density_overlap(rho0, rho1, dr)                      interactions.py:9-22
+  relax_tip_z(i, j, interpE, kappa, npivot, zi, dr, method) interactions.py:70-86
+  relax_noortho_tip_z(..., dr, dR, method)                  interactions.py:88-105
+
+plus the whole-grid forms the `dbspm` driver needs (one kernel launch instead of a Python
+loop): density_overlap_window(), build_static(), relax_grid(), and TricubicField (the
+object to pass as `interpE`; drop-in for tricubic.tricubic(list(static), list(shape))).
+
+numpy in -> numpy out (host<->device copies inside); torch CUDA tensors in -> torch CUDA
+tensors out (no copies).  All arithmetic is float64 on the GPU through the ctypes C ABI in
+_lib.py; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_WS_CACHE: dict = {}
+
+
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("dbspm_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _to_dev(a, device) -> torch.Tensor:
+    """float64 C-contiguous CUDA tensor from numpy / torch (host tensors go through one H2D copy)."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _WS_CACHE.pop(key, None)
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def release_workspace() -> None:
+    _WS_CACHE.clear()
+
+
+# ------------------------------------------------------------------------------------ sr / es
+def density_overlap_window(rho0, rho1, dr, z_lo=0, z_hi=None, alpha0=1.0, alpha1=1.0, out=None, device=None,
+                           flags=0):
+    """dV * sum_r rho0[r]^alpha0 * rho1[(r-R) mod N]^alpha1 for R on planes z_lo..z_hi-1.
+
+    Fuses what dbspm:329-330 / :348-349 do in three passes (`**ALPHA`, get_density_overlap,
+    `[nidx]`).  Returns (Nx,Ny,z_hi-z_lo): a CUDA tensor if the inputs were CUDA tensors,
+    else a numpy array."""
+    on_device = isinstance(rho0, torch.Tensor) and rho0.is_cuda
+    dev = rho0.device if on_device else _device(device)
+    a = _to_dev(rho0, dev)
+    b = _to_dev(rho1, dev)
+    if a.dim() != 3 or a.shape != b.shape:
+        raise ValueError(f"rho0 {tuple(a.shape)} and rho1 {tuple(b.shape)} must be equal 3-D shapes")
+    nx, ny, nz = (int(s) for s in a.shape)
+    z_hi = nz if z_hi is None else int(z_hi)
+    z_lo = int(z_lo)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        need = L.dbspm_corr3d_workspace_bytes(nx, ny, nz, z_lo, z_hi, 0)
+        if need == 0:
+            raise ValueError(f"bad window [{z_lo},{z_hi}) for shape {(nx, ny, nz)}")
+        ws = _workspace(need, dev)
+        if out is None:
+            out = torch.empty((nx, ny, z_hi - z_lo), dtype=torch.float64, device=dev)
+        elif not (out.is_cuda and out.dtype == torch.float64 and out.is_contiguous()
+                  and tuple(out.shape) == (nx, ny, z_hi - z_lo)):
+            raise ValueError("out must be a contiguous float64 CUDA tensor of the window shape")
+        dV = float(np.prod(np.asarray(dr, dtype=np.float64)))
+        _lib.check(L.dbspm_corr3d_f64(a.data_ptr(), b.data_ptr(), float(alpha0), float(alpha1), dV,
+                                      nx, ny, nz, z_lo, z_hi, out.data_ptr(), ws.data_ptr(), ws.numel(), int(flags),
+                                      _stream_ptr(dev)))
+    return out if on_device else out.cpu().numpy()
+
+
+def get_density_overlap(rho0, rho1, dr):
+    """Drop-in for pydbspm.interactions.get_density_overlap: full (Nx,Ny,Nz) energy grid."""
+    return density_overlap_window(rho0, rho1, dr)
+
+
+# ------------------------------------------------------------------------------------ static
+def build_static(components, device=None):
+    """static = sum_l scale_l * comp_l in the given order (dbspm:479-486: sr is scaled by V,
+    the others by 1).  `components` = iterable of (array, scale).  Returns a CUDA tensor."""
+    comps = list(components)
+    if not comps:
+        raise ValueError("no components")
+    first = comps[0][0]
+    dev = first.device if isinstance(first, torch.Tensor) and first.is_cuda else _device(device)
+    L = _lib.lib()
+    acc = None
+    with torch.cuda.device(dev):
+        for idx, (arr, scale) in enumerate(comps):
+            t = _to_dev(arr, dev)
+            if acc is None:
+                acc = torch.empty_like(t)
+            elif t.shape != acc.shape:
+                raise ValueError("component shapes differ")
+            _lib.check(L.dbspm_static_accumulate_f64(acc.data_ptr(), t.data_ptr(), float(scale), t.numel(),
+                                                     1 if idx == 0 else 0, _stream_ptr(dev)))
+    return acc
+
+
+# ------------------------------------------------------------------------------------ relax
+class TricubicField:
+    """Device-resident periodic tricubic interpolant in index units.
+
+    Drop-in for `tricubic.tricubic(list(data), list(shape))` as used at dbspm:562: `.ip([x,y,z])`
+    evaluates one point (through the gather kernel); pass the object as `interpE` to
+    relax_tip_z, or use relax_grid() for all lateral positions at once."""
+
+    def __init__(self, data, shape=None, device=None):
+        on_device = isinstance(data, torch.Tensor) and data.is_cuda
+        dev = data.device if on_device else _device(device)
+        if not isinstance(data, (torch.Tensor, np.ndarray)):
+            data = np.asarray(data, dtype=np.float64)
+        t = _to_dev(data, dev)
+        if shape is not None:
+            t = t.reshape([int(s) for s in shape])
+        if t.dim() != 3:
+            raise ValueError("tricubic data must be 3-D")
+        self.data = t
+        self.shape = tuple(int(s) for s in t.shape)
+
+    def gather(self, pts):
+        """Interpolate at pts (..., 3) in index units -> (...) values (same kind as pts)."""
+        on_device = isinstance(pts, torch.Tensor) and pts.is_cuda
+        dev = self.data.device
+        p = _to_dev(pts, dev).reshape(-1, 3).contiguous()
+        out = torch.empty(p.shape[0], dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().dbspm_tricubic_gather_f64(self.data.data_ptr(), *self.shape, p.data_ptr(),
+                                                            p.shape[0], out.data_ptr(), _stream_ptr(dev)))
+        lead = tuple(pts.shape[:-1])
+        out = out.reshape(lead)
+        return out if on_device else out.cpu().numpy()
+
+    def ip(self, xyz) -> float:
+        return float(self.gather(np.asarray([xyz], dtype=np.float64))[0])
+
+
+def relax_grid(static, kappa, rpivot, dr, nz_relax, dR=None, tile=None, xtol=1e-4, ftol=1e-4,
+               maxfev=2000, method="Powell", want_nfev=False, device=None):
+    """Relax the probe at every (i, j, k) of a lateral tile (default: the whole window).
+
+    static: (Nx,Ny,Nzc) window potential (numpy, CUDA tensor or TricubicField).
+    Returns dict with E (ni,nj,nz), theta, phi, tip_x, tip_y, tip_z (and nfev) -- CUDA tensors
+    if `static` lives on the GPU, numpy arrays otherwise.  Equivalent to the loop at
+    dbspm:564-581 followed by dbspm:597-605."""
+    if str(method).lower() != "powell":
+        raise NotImplementedError(f"MINMETHOD={method!r}: only scipy's Powell is restated on the GPU")
+    field = static if isinstance(static, TricubicField) else None
+    on_device = field is not None or (isinstance(static, torch.Tensor) and static.is_cuda)
+    if field is None:
+        field = TricubicField(static, device=device)
+    dev = field.data.device
+    nx, ny, nzc = field.shape
+    i_lo, i_hi, j_lo, j_hi = (0, nx, 0, ny) if tile is None else (int(v) for v in tile)
+    ni, nj, nz = i_hi - i_lo, j_hi - j_lo, int(nz_relax)
+    etp = torch.empty((ni, nj, nz, 3), dtype=torch.float64, device=dev)
+    cart = torch.empty((3, ni, nj, nz), dtype=torch.float64, device=dev)
+    nfev = torch.empty((ni, nj, nz), dtype=torch.int32, device=dev) if want_nfev else None
+    dr3 = (C.c_double * 3)(*[float(v) for v in dr])
+    dR9 = None
+    if dR is not None:
+        dR9 = (C.c_double * 9)(*[float(v) for v in np.asarray(dR, dtype=np.float64).reshape(9)])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dbspm_relax_powell_f64(
+            field.data.data_ptr(), nx, ny, nzc, i_lo, i_hi, j_lo, j_hi, nz, float(kappa), float(rpivot),
+            dr3, dR9, float(xtol), float(ftol), int(maxfev), etp.data_ptr(), cart.data_ptr(),
+            nfev.data_ptr() if nfev is not None else None, _stream_ptr(dev)))
+    res = {"E": etp[..., 0], "theta": etp[..., 1], "phi": etp[..., 2],
+           "tip_x": cart[0], "tip_y": cart[1], "tip_z": cart[2]}
+    if want_nfev:
+        res["nfev"] = nfev
+    if not on_device:
+        res = {k: v.cpu().numpy() for k, v in res.items()}
+    return res
+
+
+def _relax_column(i, j, interpE, kappa, npivot, zi, dr, dR, method):
+    if not isinstance(interpE, TricubicField):
+        raise TypeError("interpE must be a dbspm_b200.interactions.TricubicField (device-resident); "
+                        "a host-side interpolator cannot be driven from the GPU and there is no CPU fallback")
+    zi = np.asarray(zi)
+    if zi.size == 0 or not np.array_equal(zi, np.arange(zi.size)):
+        raise ValueError("zi must be arange(nz) (window-relative heights from 0, as built at dbspm:506)")
+    rpivot = float(npivot) * float(dr[2])
+    r = relax_grid(interpE, kappa, rpivot, dr, zi.size, dR=dR, tile=(int(i), int(i) + 1, int(j), int(j) + 1),
+                   method=method)
+    out = torch.stack([r["E"][0, 0], r["theta"][0, 0], r["phi"][0, 0]], dim=-1)
+    return out.cpu().numpy()
+
+
+def relax_tip_z(i, j, interpE, kappa, npivot, zi, dr, method="Powell"):
+    """Drop-in for pydbspm.interactions.relax_tip_z: (len(zi), 3) rows [E_min, theta, phi]."""
+    return _relax_column(i, j, interpE, kappa, npivot, zi, dr, None, method)
+
+
+def relax_noortho_tip_z(i, j, interpE, kappa, npivot, zi, dr, dR, method="Powell"):
+    """Drop-in for pydbspm.interactions.relax_noortho_tip_z."""
+    return _relax_column(i, j, interpE, kappa, npivot, zi, dr, dR, method)
+
+
+# ------------------------------------------------------------------------------------ next rows
+def force_gradient(E, dz):
+    """np.gradient(E, -dz, axis=2) on the GPU (SPMGrid.get_gradient, SPMGrid.py:375-379)."""
+    on_device = isinstance(E, torch.Tensor) and E.is_cuda
+    dev = E.device if on_device else _device()
+    t = _to_dev(E, dev)
+    out = torch.empty_like(t)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dbspm_dfz_gradient_f64(t.data_ptr(), *[int(s) for s in t.shape], float(dz),
+                                                     out.data_ptr(), _stream_ptr(dev)))
+    return out if on_device else out.cpu().numpy()

@@ -1,0 +1,109 @@
+"""Multi-GPU partition + gather for the sr / es / relax steps.
+
+Replaces the mpi4py split of the reference (round-robin lateral points + pickled
+bcast/gather at dbspm:505-515,540-556,585-591; the dead copy in pydbspm/parallel.py:4-64):
+
+  sr / es  ranks own contiguous slabs of the window's z-planes; every rank holds the inputs
+           (broadcast once) and computes its slab; rank 0 gathers and interleaves along z.
+  relax    ranks own contiguous x-tiles of lateral positions; every rank holds the static
+           window; rank 0 gathers (tiles are contiguous in C order: no permutation).
+
+One process per GPU (torchrun); torch.distributed is the plumbing: NCCL on the GPUs,
+gloo in the CPU unit tests.  There is no data-path collective other than the final gather
+(the partitions are independent).  The compute callables are injected so the partition /
+gather logic can be tested on CPU with world_size 2."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def split_range(lo: int, hi: int, parts: int):
+    """Contiguous near-equal split of [lo,hi): part g = [lo + g*n//parts, lo + (g+1)*n//parts)."""
+    n = hi - lo
+    return [(lo + (g * n) // parts, lo + ((g + 1) * n) // parts) for g in range(parts)]
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from the torchrun environment (no-op for one process).
+    Returns (rank, world, device)."""
+    rank, world = env_rank_world()
+    use_cuda = torch.cuda.is_available()
+    if use_cuda:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    device = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"), rank=rank, world_size=world)
+    return rank, world, device
+
+
+def _world():
+    return (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+
+
+def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(t, src)
+    return t
+
+
+def _gather_padded(local: torch.Tensor, sizes, dst: int = 0):
+    """Gather tensors that differ only in their first dimension: pad to the largest, gather, trim."""
+    rank, world = _world()
+    if world == 1:
+        return [local]
+    big = max(sizes)
+    pad = local
+    if local.shape[0] < big:
+        pad = torch.zeros((big,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+    pad = pad.contiguous()
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
+    if rank != dst:
+        return None
+    return [b[:n] for b, n in zip(bufs, sizes)]
+
+
+def corr3d_sharded(compute_slab, nx, ny, z_lo, z_hi, device):
+    """compute_slab(zl, zh) -> (nx,ny,zh-zl) tensor on `device`.  Rank 0 returns the full
+    (nx,ny,z_hi-z_lo) window, other ranks None."""
+    rank, world = _world()
+    slabs = split_range(z_lo, z_hi, world)
+    zl, zh = slabs[rank]
+    if zh > zl:
+        mine = compute_slab(zl, zh)
+    else:
+        mine = torch.empty((nx, ny, 0), dtype=torch.float64, device=device)
+    if world == 1:
+        return mine
+    # z is the fastest axis: ship slab-major (nz_g, nx, ny), interleave on rank 0
+    parts = _gather_padded(mine.permute(2, 0, 1).contiguous(), [b - a for a, b in slabs])
+    if rank != 0:
+        return None
+    return torch.cat(parts, dim=0).permute(1, 2, 0).contiguous()
+
+
+def relax_sharded(compute_tile, nx, device):
+    """compute_tile(i_lo, i_hi) -> dict of tensors whose first axis is the tile's x extent
+    (E, theta, phi, tip_x, tip_y, tip_z: (ni,ny,nz)).  Rank 0 returns the concatenated dict."""
+    rank, world = _world()
+    tiles = split_range(0, nx, world)
+    i_lo, i_hi = tiles[rank]
+    mine = compute_tile(i_lo, i_hi)
+    if world == 1:
+        return mine
+    out = {}
+    for key in sorted(mine):
+        parts = _gather_padded(mine[key].contiguous(), [b - a for a, b in tiles])
+        if rank == 0:
+            out[key] = torch.cat(parts, dim=0)
+    return out if rank == 0 else None

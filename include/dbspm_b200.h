@@ -45,6 +45,12 @@ extern "C" {
 
 /* flags for dbspm_corr3d_f64 */
 #define DBSPM_CORR_DEFAULT    0
+/* profiling aid: skip stages (results are then meaningless); bench.py times each launch alone */
+#define DBSPM_CORR_SKIP_XFWD  (1 << 8)
+#define DBSPM_CORR_SKIP_YFWD  (1 << 9)
+#define DBSPM_CORR_SKIP_Z     (1 << 10)
+#define DBSPM_CORR_SKIP_YINV  (1 << 11)
+#define DBSPM_CORR_SKIP_XINV  (1 << 12)
 
 /* library / build identification: "dbspm_b200 <version> sm_100a" */
 const char *dbspm_version(void);

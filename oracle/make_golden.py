@@ -1,0 +1,113 @@
+"""Generate tests/golden/* by running the REFERENCE's own functions (TEST INFRASTRUCTURE).
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+    python oracle/make_golden.py
+
+The reference package is imported unchanged from /root/reference with import shims for the
+packages missing from this image (oracle/refshim: ase.atoms, ase.geometry, ase.units,
+dftd3.interface -- none of them is reached on the sr/es/relax path).  The third-party
+`tricubic` package is not installed and not vendored; the reference's relax_tip_z is driven
+with oracle.Tricubic (our Lekien-Marsden restatement), so the relax goldens pin the
+reference's control flow + scipy's Powell, and the tricubic boundary stays "parity unpinned".
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+sys.path.insert(0, "/root/reference")
+
+import pydbspm.grid as RG                      # noqa: E402  (the reference)
+import pydbspm.input_parser as RP              # noqa: E402
+import pydbspm.interactions as RI              # noqa: E402
+import scipy                                   # noqa: E402
+
+from oracle import oracle as O                 # noqa: E402
+from dbspm_b200 import synth                   # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+assert RI.__file__.startswith("/root/reference"), RI.__file__
+
+
+def overlap_cases():
+    rng = np.random.default_rng(20260100)
+    data = {}
+    meta = []
+    for idx, (shape, alpha, signed) in enumerate([
+        ((14, 15, 16), 1.0, True), ((14, 15, 16), 1.08, False), ((12, 10, 28), 1.08, False),
+        ((9, 7, 10), 1.0, True), ((28, 30, 32), 1.0, True), ((16, 16, 16), 1.12, False),
+    ]):
+        a = rng.random(shape)
+        b = rng.random(shape)
+        if signed:
+            b -= b.mean()                                 # zero-sum like nrhoT (grid.py:442-447)
+        dr = rng.uniform(0.05, 0.2, 3)
+        ref = RI.get_density_overlap(a ** alpha, b ** alpha, dr) if alpha != 1.0 else RI.get_density_overlap(a, b, dr)
+        data[f"a{idx}"], data[f"b{idx}"], data[f"dr{idx}"], data[f"E{idx}"] = a, b, dr, ref
+        meta.append({"idx": idx, "shape": list(shape), "alpha": alpha, "signed": signed})
+    # a physically shaped case: synthetic 'tiny' config, sr and es on the real window
+    cfg = synth.CONFIGS["tiny"]
+    rhoS, potS, _ = synth.make_sample(cfg)
+    rhoT, nrhoT = synth.make_tip(cfg, variant="noisy")
+    dr = np.array(cfg.cell) / np.array(cfg.shape)
+    sr = RI.get_density_overlap(rhoS.numpy() ** cfg.alpha, rhoT.numpy() ** cfg.alpha, dr)
+    es = RI.get_density_overlap(potS.numpy(), nrhoT.numpy(), dr)
+    data["tiny_sr_win"], data["tiny_es_win"], data["tiny_dr"] = sr[:, :, 20:44], es[:, :, 20:44], dr
+    np.savez_compressed(os.path.join(OUT, "overlap_reference.npz"), **data)
+    return meta
+
+
+def relax_cases():
+    static = synth.make_static_like((24, 20, 54), 11).numpy()
+    dr = np.array([0.0765306, 0.0765306, 0.075])
+    kappa, rp = 0.2, 3.02
+    npivot = rp / dr[2]
+    zi = np.arange(24)
+    interp = O.Tricubic(list(static), list(static.shape))
+    cols = [(0, 0), (5, 7), (12, 10), (11, 9), (23, 19), (7, 13), (17, 3), (2, 18)]
+    ortho = np.array([RI.relax_tip_z(i, j, interp, kappa, npivot, zi, dr, "Powell") for i, j in cols])
+    dR = np.diag(dr)
+    noortho = np.array([RI.relax_noortho_tip_z(i, j, interp, kappa, npivot, zi, dr, dR, "Powell") for i, j in cols[:3]])
+    stiff = np.array([RI.relax_tip_z(i, j, interp, 0.5, 2.0 / dr[2], np.arange(10), dr, "Powell") for i, j in cols[:3]])
+    np.savez_compressed(os.path.join(OUT, "relax_reference.npz"), static=static, dr=dr, cols=np.array(cols),
+                        ortho=ortho, noortho=noortho, stiff=stiff)
+    return {"kappa": kappa, "rpivot": rp, "nz": 24, "stiff": {"kappa": 0.5, "rpivot": 2.0, "nz": 10}}
+
+
+def geometry_cases():
+    out = {}
+    for name, path, shape, cell in [
+        ("pyridine", "/root/reference/example/input.in", (196, 196, 240), (15.0, 15.0, 18.0)),
+        ("triangulene", "/root/reference/brstm_example/input.in", (240, 320, 240), (18.0, 24.0, 18.0)),
+    ]:
+        p = RP.parse_params(path)
+        g = RG.Grid(shape, cell=np.diag(cell), positions=np.zeros((1, 3)), numbers=np.array([1]))
+        win, nidx = RG.get_grid_from_params(p, g, nidx=True, rpivot=p.RPIVOT, zpad=p.ZPAD)
+        rel, ridx, nbox = RG.get_grid_from_params(p, g, nidx=True, nbox=True)
+        out[name] = {
+            "params": {k: (v if not isinstance(v, np.ndarray) else v.tolist()) for k, v in vars(p).items()
+                       if k in ("ALPHA", "V", "Z0", "ZF", "ZREF", "ZPAD", "RPIVOT", "K", "MINMETHOD", "COMPONENTS", "LABEL")},
+            "dr": g.dr.tolist(),
+            "window_shape": [int(v) for v in win.shape], "window_z": [int(nidx[2].start), int(nidx[2].stop)],
+            "window_origin": [float(v) for v in win.origin], "window_span": np.asarray(win.span).tolist(),
+            "relax_shape": [int(v) for v in rel.shape], "relax_z": [int(ridx[2].start), int(ridx[2].stop)],
+            "relax_z_first": float(rel.z[0]), "relax_z_last": float(rel.z[-1]),
+        }
+    return out
+
+
+if __name__ == "__main__":
+    manifest = {
+        "generator": "oracle/make_golden.py", "reference": "/root/reference (SPMTH/DBSPM, unmodified)",
+        "numpy": np.__version__, "scipy": scipy.__version__,
+        "overlap": overlap_cases(), "relax": relax_cases(), "geometry": geometry_cases(),
+    }
+    with open(os.path.join(OUT, "manifest.json"), "w") as fh:
+        json.dump(manifest, fh, indent=1, sort_keys=True)
+    print("wrote", sorted(os.listdir(OUT)))

@@ -1,0 +1,138 @@
+"""The CUDA kernel bodies (dbspm_b200/csrc/*.h), compiled for the CPU by tests/emu, against
+the oracle.  This checks the code that ships -- plan, butterflies, tiling, the packed-real
+untangle / product / pruned inverse algebra, the Powell state machine -- without a GPU."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+LENGTHS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 20, 21, 27, 28, 30, 32, 49, 64, 77, 80, 96, 98, 120,
+           128, 160, 196, 240, 256, 320, 384, 512, 1024, 11, 13, 22, 26, 33, 62, 169]
+
+
+@pytest.mark.parametrize("n", LENGTHS)
+def test_tile_fft_matches_numpy(emu, n):
+    rng = np.random.default_rng(n)
+    for tshift in (0, 2, 3):
+        x = rng.standard_normal((n, 1 << tshift)) + 1j * rng.standard_normal((n, 1 << tshift))
+        fwd = emu.fft_lines(x, -1, tshift)
+        inv = emu.fft_lines(x, +1, tshift)
+        scale = max(1.0, np.abs(np.fft.fft(x, axis=0)).max())
+        assert np.abs(fwd - np.fft.fft(x, axis=0)).max() < 2e-14 * scale * max(1, np.log2(n + 1))
+        assert np.abs(inv - np.fft.ifft(x, axis=0) * n).max() < 2e-14 * scale * max(1, np.log2(n + 1))
+
+
+def test_unsupported_length_is_reported(emu):
+    with pytest.raises(RuntimeError):
+        emu.fft_lines(np.zeros((37, 1), dtype=complex), -1, 0)       # prime > 31
+
+
+def test_corr3d_matches_reference_goldens(emu, overlap_golden, manifest):
+    g = overlap_golden
+    for case in manifest["overlap"]:
+        i, alpha = case["idx"], case["alpha"]
+        a, b, dr, ref = g[f"a{i}"], g[f"b{i}"], g[f"dr{i}"], g[f"E{i}"]
+        nz = a.shape[2]
+        for z_lo, z_hi in [(0, nz), (nz // 4, nz // 4 + nz // 2), (3, 8), (nz - 1, nz)]:
+            got = emu.corr3d(a, b, dr, z_lo, z_hi, alpha, alpha)
+            err = np.abs(got - ref[:, :, z_lo:z_hi]).max() / np.abs(ref).max()
+            assert err <= 1e-12, (case, z_lo, z_hi, err)
+
+
+@pytest.mark.parametrize("shape,window", [
+    ((4, 4, 4), (0, 4)), ((2, 2, 2), (0, 2)), ((1, 1, 2), (0, 2)), ((3, 1, 6), (1, 6)), ((1, 5, 4), (2, 3)),
+    ((6, 5, 8), (3, 7)), ((7, 9, 10), (1, 2)), ((12, 10, 28), (0, 1)), ((14, 15, 16), (5, 12)),
+    ((5, 14, 12), (11, 12)), ((16, 3, 6), (0, 5)),
+])
+def test_corr3d_edge_shapes_all_tile_widths(emu, shape, window):
+    rng = np.random.default_rng(sum(shape))
+    a, b = rng.random(shape), rng.random(shape) - 0.4
+    dr = np.array([0.1, 0.2, 0.3])
+    ref = O.density_overlap_fft(a, b, dr)[:, :, window[0]:window[1]]
+    for tshift in (-1, 0, 1, 2):
+        got = emu.corr3d(a, b, dr, *window, tshift=tshift)
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, window, tshift)
+
+
+def test_corr3d_tiny_config_window(emu, overlap_golden):
+    from dbspm_b200 import synth
+    cfg = synth.CONFIGS["tiny"]
+    rhoS, potS, _ = synth.make_sample(cfg)
+    rhoT, nrhoT = synth.make_tip(cfg, variant="noisy")
+    dr = overlap_golden["tiny_dr"]
+    sr = emu.corr3d(rhoS.numpy(), rhoT.numpy(), dr, 20, 44, cfg.alpha, cfg.alpha)
+    es = emu.corr3d(potS.numpy(), nrhoT.numpy(), dr, 20, 44)
+    for got, ref in ((sr, overlap_golden["tiny_sr_win"]), (es, overlap_golden["tiny_es_win"])):
+        assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max()
+    # zero density stays zero under the fused power (0**alpha = 0), negative -> NaN like numpy
+    z = np.zeros((4, 4, 4)); z[1, 2, 3] = 2.0
+    out = emu.corr3d(z, z, dr, 0, 4, 1.08, 1.08)
+    assert np.isfinite(out).all() and abs(out[0, 0, 0] - np.prod(dr) * (2.0 ** 1.08) ** 2) < 1e-12
+
+
+def test_odd_nz_is_refused(emu):
+    with pytest.raises(RuntimeError):
+        emu.corr3d(np.zeros((4, 4, 5)), np.zeros((4, 4, 5)), np.ones(3))
+
+
+def test_tricubic_stencil_equals_oracle(emu, relax_golden):
+    s = relax_golden["static"]
+    tc = O.Tricubic(s)
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        p = rng.uniform(-60, 120, 3)
+        assert abs(emu.tricubic(s, *p) - tc.ip(list(p))) <= 1e-13 * max(1.0, np.abs(s).max())
+    assert emu.tricubic(s, 3.0, 4.0, 5.0) == s[3, 4, 5]
+
+
+def test_relax_matches_reference_goldens(emu, relax_golden, manifest):
+    g, m = relax_golden, manifest["relax"]
+    static, dr, cols = g["static"], g["dr"], g["cols"]
+    rp = m["rpivot"]
+    dev = []
+    for c, (i, j) in enumerate(cols):
+        etp, cart, nfev = emu.relax(static, (i, i + 1, j, j + 1), m["nz"], m["kappa"], rp, dr)
+        ref = g["ortho"][c]
+        assert np.abs(etp[0, 0, :, 0] - ref[:, 0]).max() <= 1e-6 * np.abs(ref[:, 0]).max()
+        want = np.stack(O.sph2cart(ref[:, 1], ref[:, 2], rp))
+        dev.append(np.abs(cart[:, 0, 0] - want).max(axis=0) / rp)
+    dev = np.concatenate(dev)
+    # the reference stops at xtol = 1e-4 with a 0.01 line-search tolerance, so its answer depends
+    # (chaotically, through the warm start) on last-bit differences of the interpolant: a few
+    # positions leave the 1e-6*rpivot band; none leaves 1e-4*rpivot
+    assert (dev > 1e-6).mean() <= 0.05 and dev.max() <= 1e-4, (dev.max(), (dev > 1e-6).mean())
+    for c, (i, j) in enumerate(cols[:3]):
+        etp, cart, _ = emu.relax(static, (i, i + 1, j, j + 1), m["nz"], m["kappa"], rp, dr, dR=np.diag(dr))
+        assert np.abs(etp[0, 0, :, 0] - g["noortho"][c][:, 0]).max() <= 1e-6 * np.abs(g["noortho"][c][:, 0]).max()
+        s = m["stiff"]
+        etp, cart, _ = emu.relax(static, (i, i + 1, j, j + 1), s["nz"], s["kappa"], s["rpivot"], dr)
+        assert np.abs(etp[0, 0, :, 0] - g["stiff"][c][:, 0]).max() <= 1e-6 * np.abs(g["stiff"][c][:, 0]).max()
+
+
+def test_relax_tile_against_oracle_with_outlier_budget(emu, relax_golden):
+    """Whole tile: E within 1e-6 relative; tip positions within 1e-6*rpivot except for a small
+    fraction of Powell branch flips (ulp-level differences of the interpolant)."""
+    static, dr = relax_golden["static"], relax_golden["dr"]
+    ref, nf_ref = O.relax_tile(static, 0, 24, 0, 20, 24, 0.2, 3.02, dr, want_nfev=True)
+    etp, cart, nfev = emu.relax(static, (0, 24, 0, 20), 24, 0.2, 3.02, dr)
+    assert np.abs(etp[..., 0] - ref[..., 0]).max() <= 1e-6 * np.abs(ref[..., 0]).max()
+    want = np.stack(O.sph2cart(ref[..., 1], ref[..., 2], 3.02))
+    bad = (np.abs(cart - want).max(axis=0) > 1e-6 * 3.02).mean()
+    assert bad < 2e-3, bad
+    assert abs(nfev.mean() - nf_ref.mean()) < 1.0
+    # maxfev exhaustion: same early-exit semantics as scipy's _MaxFuncCallError path
+    r2, n2 = O.relax_tile(static, 2, 6, 2, 6, 24, 0.2, 3.02, dr, maxfev=17, want_nfev=True)
+    e2, _, m2 = emu.relax(static, (2, 6, 2, 6), 24, 0.2, 3.02, dr, maxfev=17)
+    assert np.array_equal(n2, m2) and np.abs(e2[..., 0] - r2[..., 0]).max() < 1e-9
+
+
+def test_relax_empty_tile_and_periodic_wrap(emu, relax_golden):
+    static, dr = relax_golden["static"], relax_golden["dr"]
+    etp, cart, nfev = emu.relax(static, (3, 3, 0, 5), 4, 0.2, 3.02, dr)
+    assert etp.size == 0
+    # columns at the lateral edges use the periodic wrap of the interpolant: shift the grid
+    # by one cell and the same physical column must give the same answer
+    rolled = np.ascontiguousarray(np.roll(static, (1, 1), axis=(0, 1)))
+    a, _, _ = emu.relax(static, (0, 1, 0, 1), 6, 0.2, 3.02, dr)
+    b, _, _ = emu.relax(rolled, (1, 2, 1, 2), 6, 0.2, 3.02, dr)
+    assert np.abs(a[..., 0] - b[..., 0]).max() < 1e-12

@@ -1,0 +1,279 @@
+"""Parity of the CUDA path (through the Python operators -> ctypes C ABI -> sm_100a kernels)
+with the oracle and with the reference's own outputs in tests/golden.  Tolerances are the
+ones north_star states: sr/es <= 1e-9 relative to max|ref|; relax E <= 1e-6 relative, tip
+positions <= 1e-6*rpivot (outlier fraction reported and bounded)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from oracle import oracle as O                            # noqa: E402  (checker only)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dbspm_b200 import interactions
+    return interactions
+
+
+def _rel(got, ref):
+    return float(np.abs(np.asarray(got) - ref).max() / np.abs(ref).max())
+
+
+# ------------------------------------------------------------------------------------ sr / es
+def test_overlap_matches_reference_goldens(ops, overlap_golden, manifest):
+    g = overlap_golden
+    for case in manifest["overlap"]:
+        i, alpha = case["idx"], case["alpha"]
+        a, b, dr, ref = g[f"a{i}"], g[f"b{i}"], g[f"dr{i}"], g[f"E{i}"]
+        nz = a.shape[2]
+        full = ops.get_density_overlap(a ** alpha, b ** alpha, dr) if alpha != 1.0 else ops.get_density_overlap(a, b, dr)
+        assert isinstance(full, np.ndarray) and full.shape == ref.shape and full.dtype == np.float64
+        assert _rel(full, ref) <= 1e-9, case
+        for z_lo, z_hi in [(nz // 4, nz // 4 + nz // 2), (3, 8), (nz - 1, nz), (1, nz)]:
+            win = ops.density_overlap_window(a, b, dr, z_lo, z_hi, alpha, alpha)
+            err = np.abs(win - ref[:, :, z_lo:z_hi]).max() / np.abs(ref).max()
+            assert err <= 1e-9, (case, z_lo, z_hi, err)
+
+
+@pytest.mark.parametrize("shape,window", [
+    ((4, 4, 4), (0, 4)), ((2, 2, 2), (0, 2)), ((1, 1, 2), (0, 2)), ((3, 1, 6), (1, 6)), ((1, 5, 4), (2, 3)),
+    ((6, 5, 8), (3, 7)), ((7, 9, 10), (1, 2)), ((12, 10, 28), (0, 1)), ((5, 14, 12), (11, 12)),
+    ((22, 26, 6), (0, 6)), ((33, 9, 62), (7, 30)),
+])
+def test_overlap_edge_shapes(ops, shape, window):
+    rng = np.random.default_rng(sum(shape))
+    a, b = rng.random(shape), rng.random(shape) - 0.4
+    dr = np.array([0.1, 0.2, 0.3])
+    ref = O.density_overlap_fft(a, b, dr)[:, :, window[0]:window[1]]
+    got = ops.density_overlap_window(a, b, dr, *window)
+    assert _rel(got, ref) <= 1e-9
+
+
+def test_overlap_tiny_config_sr_es(ops, overlap_golden):
+    from dbspm_b200 import synth
+    cfg = synth.CONFIGS["tiny"]
+    dev = torch.device("cuda", 0)
+    rhoS, potS, _ = synth.make_sample(cfg)
+    rhoT, nrhoT = synth.make_tip(cfg, variant="noisy")
+    dr = overlap_golden["tiny_dr"]
+    sr = ops.density_overlap_window(rhoS.to(dev), rhoT.to(dev), dr, 20, 44, cfg.alpha, cfg.alpha)
+    es = ops.density_overlap_window(potS.to(dev), nrhoT.to(dev), dr, 20, 44)
+    assert sr.is_cuda and es.is_cuda                     # device in -> device out, no copies
+    assert _rel(sr.cpu().numpy(), overlap_golden["tiny_sr_win"]) <= 1e-9
+    assert _rel(es.cpu().numpy(), overlap_golden["tiny_es_win"]) <= 1e-9
+
+
+def test_overlap_errors(ops):
+    from dbspm_b200._lib import DbspmError, EUNSUPPORTED
+    with pytest.raises(DbspmError) as e:
+        ops.get_density_overlap(np.ones((4, 4, 5)), np.ones((4, 4, 5)), np.ones(3))    # odd nz
+    assert e.value.code == EUNSUPPORTED
+    with pytest.raises(DbspmError) as e:
+        ops.get_density_overlap(np.ones((37, 4, 4)), np.ones((37, 4, 4)), np.ones(3))  # prime 37 > 31
+    assert e.value.code == EUNSUPPORTED
+    with pytest.raises(ValueError):
+        ops.density_overlap_window(np.ones((4, 4, 4)), np.ones((4, 4, 4)), np.ones(3), 3, 2)
+    with pytest.raises(ValueError):
+        ops.get_density_overlap(np.ones((4, 4, 4)), np.ones((4, 4, 6)), np.ones(3))
+    zero = np.zeros((6, 6, 6)); zero[1, 2, 3] = 2.0
+    out = ops.density_overlap_window(zero, zero, np.ones(3), 0, 6, 1.08, 1.08)          # 0**alpha = 0
+    assert np.isfinite(out).all() and abs(out[0, 0, 0] - (2.0 ** 1.08) ** 2) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["pyridine", "tma_cu111"])
+def test_overlap_full_size_properties(ops, name):
+    """At BASELINE sizes: (1) a delta tip at s reproduces the shifted sample exactly,
+    (2) linearity in the sample, (3) agreement with the numpy oracle on the whole window."""
+    from dbspm_b200 import synth
+    cfg = synth.CONFIGS[name]
+    dev = torch.device("cuda", 0)
+    nx, ny, nz = cfg.shape
+    dr = np.array(cfg.cell) / np.array(cfg.shape)
+    dV = float(np.prod(dr))
+    z_lo, z_hi = 76, 130
+    g = torch.Generator(device="cpu").manual_seed(cfg.seed)
+    A = torch.rand(cfg.shape, dtype=torch.float64, generator=g).to(dev)
+    A2 = torch.rand(cfg.shape, dtype=torch.float64, generator=g).to(dev)
+    delta = torch.zeros(cfg.shape, dtype=torch.float64, device=dev)
+    s = (3, ny - 2, nz - 5)
+    delta[s] = 1.0
+    E = ops.density_overlap_window(A, delta, dr, z_lo, z_hi)
+    # E[R] = dV * A[R + s]
+    want = dV * torch.roll(A, shifts=(-s[0], -s[1], -s[2]), dims=(0, 1, 2))[:, :, z_lo:z_hi]
+    assert float((E - want).abs().max() / want.abs().max()) <= 1e-12
+    B = torch.rand(cfg.shape, dtype=torch.float64, generator=g).to(dev) - 0.5
+    E1 = ops.density_overlap_window(A, B, dr, z_lo, z_hi)
+    E2 = ops.density_overlap_window(A2, B, dr, z_lo, z_hi)
+    E12 = ops.density_overlap_window(A + 2.0 * A2, B, dr, z_lo, z_hi)
+    assert float((E12 - (E1 + 2.0 * E2)).abs().max() / E12.abs().max()) <= 1e-11
+    if name == "pyridine":
+        ref = O.density_overlap_fft(A.cpu().numpy(), B.cpu().numpy(), dr)[:, :, z_lo:z_hi]
+        assert _rel(E1.cpu().numpy(), ref) <= 1e-9
+        # odd number of window planes (a multi-GPU z-slab) goes through the compaction kernel
+        odd = ops.density_overlap_window(A, B, dr, 82, 89)
+        assert _rel(odd.cpu().numpy(), ref[:, :, 6:13]) <= 1e-9
+
+
+# ------------------------------------------------------------------------------------ relax
+def _dev_positions(res, ref, rp):
+    want = np.stack(O.sph2cart(ref[..., 1], ref[..., 2], rp))
+    got = np.stack([np.asarray(res[k].cpu() if hasattr(res[k], "cpu") else res[k]) for k in ("tip_x", "tip_y", "tip_z")])
+    return np.abs(got - want).max(axis=0) / rp
+
+
+def test_relax_matches_reference_goldens(ops, relax_golden, manifest):
+    g, m = relax_golden, manifest["relax"]
+    static, dr, cols = g["static"], g["dr"], g["cols"]
+    rp = m["rpivot"]
+    field = ops.TricubicField(list(static), list(static.shape))      # reference constructor form
+    dev = []
+    for c, (i, j) in enumerate(cols):
+        out = ops.relax_tip_z(int(i), int(j), field, m["kappa"], rp / dr[2], np.arange(m["nz"]), dr, "Powell")
+        ref = g["ortho"][c]
+        assert out.shape == ref.shape
+        assert np.abs(out[:, 0] - ref[:, 0]).max() <= 1e-6 * np.abs(ref[:, 0]).max()
+        want = np.stack(O.sph2cart(ref[:, 1], ref[:, 2], rp))
+        got = np.stack(O.sph2cart(out[:, 1], out[:, 2], rp))
+        dev.append(np.abs(got - want).max(axis=0) / rp)
+    dev = np.concatenate(dev)
+    assert (dev > 1e-6).mean() <= 0.05 and dev.max() <= 1e-4, (dev.max(), (dev > 1e-6).mean())
+    for c, (i, j) in enumerate(cols[:3]):
+        out = ops.relax_noortho_tip_z(int(i), int(j), field, m["kappa"], rp / dr[2], np.arange(m["nz"]), dr, np.diag(dr))
+        assert np.abs(out[:, 0] - g["noortho"][c][:, 0]).max() <= 1e-6 * np.abs(g["noortho"][c][:, 0]).max()
+        s = m["stiff"]
+        out = ops.relax_tip_z(int(i), int(j), field, s["kappa"], s["rpivot"] / dr[2], np.arange(s["nz"]), dr)
+        assert np.abs(out[:, 0] - g["stiff"][c][:, 0]).max() <= 1e-6 * np.abs(g["stiff"][c][:, 0]).max()
+    assert abs(field.ip([3.25, 4.5, 7.75]) - O.Tricubic(static).ip([3.25, 4.5, 7.75])) < 1e-13
+
+
+def test_relax_tile_against_oracle(ops, relax_golden):
+    static, dr = relax_golden["static"], relax_golden["dr"]
+    ref, nf_ref = O.relax_tile(static, 0, 24, 0, 20, 24, 0.2, 3.02, dr, want_nfev=True)
+    res = ops.relax_grid(static, 0.2, 3.02, dr, 24, want_nfev=True)
+    assert res["E"].shape == (24, 20, 24) and isinstance(res["E"], np.ndarray)
+    assert _rel(res["E"], ref[..., 0]) <= 1e-6
+    dev = _dev_positions(res, ref, 3.02)
+    assert (dev > 1e-6).mean() < 2e-3 and dev.max() < 1e-3, ((dev > 1e-6).mean(), dev.max())
+    assert abs(res["nfev"].mean() - nf_ref.mean()) < 1.0
+    # sub-tile == the same columns of the full run (what a multi-GPU rank computes)
+    sub = ops.relax_grid(static, 0.2, 3.02, dr, 24, tile=(5, 11, 3, 17))
+    assert np.array_equal(sub["E"], res["E"][5:11, 3:17]) and np.array_equal(sub["tip_x"], res["tip_x"][5:11, 3:17])
+    # maxfev exhaustion follows scipy's exception path
+    r2, n2 = O.relax_tile(static, 2, 6, 2, 6, 24, 0.2, 3.02, dr, maxfev=17, want_nfev=True)
+    g2 = ops.relax_grid(static, 0.2, 3.02, dr, 24, tile=(2, 6, 2, 6), maxfev=17, want_nfev=True)
+    assert np.array_equal(g2["nfev"], n2) and np.abs(g2["E"] - r2[..., 0]).max() < 1e-9
+    empty = ops.relax_grid(static, 0.2, 3.02, dr, 24, tile=(3, 3, 0, 5))
+    assert empty["E"].size == 0
+
+
+def test_relax_full_size_subsample(ops):
+    """Pyridine-sized window (196,196,54) x 24 heights = 921 984 positions on the GPU; a seeded
+    subsample of columns is checked against the oracle."""
+    from dbspm_b200 import synth
+    dev = torch.device("cuda", 0)
+    static = synth.make_static_like((196, 196, 54), 20260100, dev)
+    dr = np.array([15.0 / 196, 15.0 / 196, 0.075])
+    res = ops.relax_grid(static, 0.2, 3.02, dr, 24, want_nfev=True)
+    assert res["E"].is_cuda and res["E"].shape == (196, 196, 24)
+    host = static.cpu().numpy()
+    rng = np.random.default_rng(1)
+    devs, errs = [], []
+    emax = float(res["E"].abs().max())
+    for i, j in rng.integers(0, 196, size=(160, 2)):
+        ref = O.relax_tile(host, int(i), int(i) + 1, int(j), int(j) + 1, 24, 0.2, 3.02, dr)[0, 0]
+        errs.append(np.abs(res["E"][i, j].cpu().numpy() - ref[:, 0]).max() / emax)
+        want = np.stack(O.sph2cart(ref[:, 1], ref[:, 2], 3.02))
+        got = np.stack([res[k][i, j].cpu().numpy() for k in ("tip_x", "tip_y", "tip_z")])
+        devs.append(np.abs(got - want).max(axis=0) / 3.02)
+    devs = np.concatenate(devs)
+    assert max(errs) <= 1e-6, max(errs)
+    assert (devs > 1e-6).mean() < 5e-3, (devs > 1e-6).mean()
+    assert 15 < float(res["nfev"].float().mean()) < 120
+
+
+# ------------------------------------------------------------------------------------ glue
+def test_build_static_order_and_gradient(ops):
+    rng = np.random.default_rng(9)
+    sr, es, vdw = rng.random((6, 5, 8)), rng.standard_normal((6, 5, 8)), -rng.random((6, 5, 8))
+    V = 42.9071
+    ref = np.zeros((6, 5, 8))
+    ref += sr * V
+    ref += es
+    ref += vdw                                            # dbspm:479-486, COMPONENTS order
+    got = ops.build_static([(sr, V), (es, 1.0), (vdw, 1.0)]).cpu().numpy()
+    assert np.array_equal(got, ref)
+    E = rng.standard_normal((6, 5, 8))
+    assert np.allclose(ops.force_gradient(E, 0.075), np.gradient(E, -0.075, axis=2), rtol=0, atol=1e-13)
+    pts = rng.uniform(-10, 20, (50, 3))
+    f = ops.TricubicField(E)
+    tc = O.Tricubic(E)
+    want = np.array([tc.ip(list(p)) for p in pts])
+    assert np.abs(f.gather(pts) - want).max() < 1e-13
+
+
+def test_cli_sr_es_relax_end_to_end(tmp_path, ops):
+    """`dbspm sr es relax -i input.in` in a scratch directory: file names, .npz keys, shapes and
+    values (against the oracle pipeline: numpy overlap -> static -> C Powell)."""
+    from dbspm_b200 import synth
+    from dbspm_b200.grid import Grid, get_grid_from_params
+    from dbspm_b200.input_parser import parse_params
+    cfg = synth.CONFIGS["tiny"]
+    rhoS, potS, atoms = synth.make_sample(cfg)
+    rhoT, nrhoT = synth.make_tip(cfg, variant="noisy")
+    cell = np.diag(cfg.cell)
+    pos = np.array([[a[1], a[2], a[3]] for a in atoms])
+    num = np.array([a[0] for a in atoms])
+    (tmp_path / "sample").mkdir()
+    (tmp_path / "tip").mkdir()
+    np.savez(tmp_path / "sample" / "sample.npz", rhoS=rhoS.numpy(), potS=potS.numpy(), cell=cell, positions=pos, numbers=num)
+    np.savez(tmp_path / "tip" / "tip.npz", rhoT=rhoT.numpy(), nrhoT=nrhoT.numpy(), cell=cell,
+             positions=np.array([[0, 0, 0.0], [0, 0, 1.153425]]), numbers=np.array([8, 6]))
+    (tmp_path / "input.in").write_text(
+        f"LABEL = tiny\nZ0 = {cfg.z0}\nZF = {cfg.zf}\nZREF = {cfg.zref}\nRPIVOT = {cfg.rpivot}\nZPAD = {cfg.zpad}\n"
+        f"ALPHA = {cfg.alpha}\nV = 0.5\nK = 0.2\n")
+    p = parse_params(str(tmp_path / "input.in"))
+    gS = Grid(cfg.shape, cell=cell, positions=pos, numbers=num)
+    win, nidx = get_grid_from_params(p, gS, nidx=True, rpivot=p.RPIVOT, zpad=p.ZPAD, numbers=num, positions=pos)
+    z_lo, z_hi = nidx[2].start, nidx[2].stop
+    vdw = synth.make_vdw_window(cfg, atoms, tuple(int(v) for v in win.shape), float(win.origin[2])).numpy() * 1e-3
+    win.set_density("vdw", vdw)
+    win.save_density("vdw", filename=str(tmp_path / "tiny_vdw.npz"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "dbspm"), "sr", "es", "relax", "-i", "input.in"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "F_max" in r.stdout and "relax   |" in r.stdout
+    keys = ["shape", "span", "origin", "ortho", "cell", "numbers", "positions", "zref"]
+    sr = np.load(tmp_path / f"tiny_sr_a{cfg.alpha:.2f}.npz")
+    es = np.load(tmp_path / "tiny_es.npz")
+    rl = np.load(tmp_path / f"relax_tiny_k0.2000_a{cfg.alpha:.2f}_V0.50.npz")
+    assert sr.files == ["sr"] + keys and es.files == ["es"] + keys and rl.files == ["E", "tip_x", "tip_y", "tip_z"] + keys
+    dr = gS.dr
+    ref_sr = O.density_overlap_fft(rhoS.numpy() ** cfg.alpha, rhoT.numpy() ** cfg.alpha, dr)[:, :, z_lo:z_hi]
+    ref_es = O.density_overlap_fft(potS.numpy(), nrhoT.numpy(), dr)[:, :, z_lo:z_hi]
+    assert sr["sr"].shape == ref_sr.shape and _rel(sr["sr"], ref_sr) <= 1e-9 and _rel(es["es"], ref_es) <= 1e-9
+    assert np.array_equal(sr["origin"], win.origin) and np.array_equal(sr["span"], win.span)
+    static = np.zeros(ref_sr.shape)
+    static += sr["sr"] * 0.5
+    static += es["es"]
+    static += vdw
+    nzr = rl["E"].shape[2]
+    ref = O.relax_tile(static, 0, cfg.shape[0], 0, cfg.shape[1], nzr, 0.2, cfg.rpivot, dr)
+    assert _rel(rl["E"], ref[..., 0]) <= 1e-6
+    want = np.stack(O.sph2cart(ref[..., 1], ref[..., 2], cfg.rpivot))
+    got = np.stack([rl["tip_x"], rl["tip_y"], rl["tip_z"]])
+    dev = np.abs(got - want).max(axis=0) / cfg.rpivot
+    assert (dev > 1e-6).mean() < 1e-2, (dev > 1e-6).mean()
+    # an out-of-scope step is refused, not silently skipped
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "dbspm"), "vdw", "-i", "input.in"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 2 and "reference" in r.stdout

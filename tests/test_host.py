@@ -1,0 +1,206 @@
+"""Host-side logic: parser, step aliases, window geometry and .npz layout (against values the
+reference produced, tests/golden/manifest.json), the C-ABI library's exports, the no-fallback
+rule, and the multi-process partition / gather with gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from argparse import Namespace
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from dbspm_b200 import _lib, parallel                      # noqa: E402
+from dbspm_b200.grid import Grid, get_grid_from_params, read_grid, save_grid, sph2cart  # noqa: E402
+from dbspm_b200.input_parser import default_params, parse_params  # noqa: E402
+from dbspm_b200.setup_calculation import setup_calc            # noqa: E402
+
+PYRIDINE_IN = """# Example input
+LABEL   = pyridine
+Z0      = 2.7
+ZF      = 4.5
+ZREF   = 3.0   # comment
+SAMPLEGRID = True
+TIPGRID = True 
+ALPHA   = 1.08
+V       = 42.9071
+OPT = False
+&VASP
+$NPAR = 8
+"""
+
+
+def _params(tmp_path, text=PYRIDINE_IN):
+    f = tmp_path / "input.in"
+    f.write_text(text)
+    return parse_params(str(f))
+
+
+def test_parser_types_defaults_and_quirks(tmp_path, manifest):
+    p = _params(tmp_path)
+    want = manifest["geometry"]["pyridine"]["params"]
+    for k in ("ALPHA", "V", "Z0", "ZF", "ZREF", "ZPAD", "RPIVOT", "K", "MINMETHOD"):
+        assert getattr(p, k) == want[k], k
+    assert p.LABEL == "pyridine" and list(p.COMPONENTS) == ["sr", "es", "vdw"]
+    assert p.SAMPLEGRID is True
+    assert p.TIPGRID is False            # "True " with a trailing blank is not the exact text "True"
+    assert p.BBOX is None and str(p.SAMPLE) == "sample" and "NPAR" not in vars(p)
+    assert default_params["V"] == 42.91 and default_params["MINMETHOD"] == "Powell"
+    q = _params(tmp_path, "BBOX0 = 0 0 1\nBBOXF = 2 3 4\nCOMPONENTS = 1 2\n")
+    assert q.BBOX.shape == (2, 3) and q.BBOX[1, 2] == 4.0
+
+
+def test_step_aliases():
+    on = lambda words: {k for k, v in vars(setup_calc(words)).items() if v}
+    assert on(["sr"]) == {"sr"} and on(["pauli"]) == {"sr"}
+    assert on(["dens"]) == {"sr", "es"} and on(["static"]) == {"sr", "es", "vdw"}
+    assert on(["afm"]) == on(["fdbm"]) == {"sr", "es", "vdw", "relax"}
+    assert on(["fullauto"]) == {"sample", "tip", "grid", "sr", "es", "vdw", "relax"}
+    assert on(["nonsense", "relax"]) == {"relax"}
+
+
+@pytest.mark.parametrize("name,shape,cell,z0,zf", [
+    ("pyridine", (196, 196, 240), (15.0, 15.0, 18.0), 2.7, 4.5),
+    ("triangulene", (240, 320, 240), (18.0, 24.0, 18.0), 2.5, 5.0),
+])
+def test_window_geometry_matches_reference(manifest, name, shape, cell, z0, zf):
+    want = manifest["geometry"][name]
+    p = Namespace(**{**default_params, "Z0": z0, "ZF": zf, "ZREF": 3.0})
+    g = Grid(shape, cell=np.diag(cell), positions=np.zeros((1, 3)), numbers=np.array([1]))
+    assert np.allclose(g.dr, want["dr"], rtol=0, atol=0)
+    win, nidx = get_grid_from_params(p, g, nidx=True, rpivot=p.RPIVOT, zpad=p.ZPAD)
+    assert [int(v) for v in win.shape] == want["window_shape"]
+    assert [nidx[2].start, nidx[2].stop] == want["window_z"]
+    assert np.array_equal(win.origin, want["window_origin"]) and np.array_equal(win.span, want["window_span"])
+    rel, ridx, nbox = get_grid_from_params(p, g, nidx=True, nbox=True)
+    assert [int(v) for v in rel.shape] == want["relax_shape"] and [ridx[2].start, ridx[2].stop] == want["relax_z"]
+    assert rel.z[0] == want["relax_z_first"] and rel.z[-1] == want["relax_z_last"]
+    assert p.BBOX is not None                     # side effect kept from the reference
+
+
+def test_npz_layout_roundtrip(tmp_path):
+    g = Grid((4, 5, 6), cell=np.diag([2.0, 2.5, 3.0]), positions=np.zeros((2, 3)), numbers=np.array([1, 6]))
+    data = np.arange(120.0).reshape(4, 5, 6)
+    g.set_density("sr", data)
+    f = tmp_path / "x_sr_a1.08.npz"
+    g.save_density("sr", filename=str(f))
+    z = np.load(f)
+    assert z.files == ["sr", "shape", "span", "origin", "ortho", "cell", "numbers", "positions", "zref"]
+    assert z["sr"].dtype == np.float64 and np.array_equal(z["sr"], data)
+    back = read_grid(str(f))
+    assert np.array_equal(back.sr, data) and np.array_equal(back.dr, g.dr)
+    with pytest.raises(AssertionError):
+        save_grid(str(f), g, sr=np.zeros((4, 5, 7)))
+    with pytest.raises(ValueError):
+        Grid((4, 4, 4), cell=np.array([[1.0, 0, 0.2], [0, 1, 0], [0, 0, 1]]))   # z not orthogonal
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "dbspm_b200.h")).read()
+    declared = set(re.findall(r"\b(dbspm_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    L = _lib.lib()                                 # dlopen; no compute call without a GPU
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert "sm_100a" in _lib.version()
+    assert L.dbspm_corr3d_workspace_bytes(196, 196, 240, 76, 130, 0) == 2 * 196 * 196 * 240 * 8
+    assert L.dbspm_corr3d_workspace_bytes(4, 4, 4, 3, 2, 0) == 0
+    # argument validation happens before any CUDA call
+    rc = L.dbspm_corr3d_f64(None, None, 1.0, 1.0, 1.0, 4, 4, 4, 0, 4, None, None, 0, 0, None)
+    assert rc == _lib.EINVAL and b"null" in L.dbspm_last_error()
+
+
+def test_sass_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dbspm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "liboracle" not in text and "libdbspm_emu" not in text, f
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dbspm_b200 import interactions as ops
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ops.get_density_overlap(np.zeros((4, 4, 4)), np.zeros((4, 4, 4)), np.ones(3))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ops.relax_grid(np.zeros((4, 4, 4)), 0.2, 3.0, np.ones(3), 2)
+    with pytest.raises(NotImplementedError):
+        ops.relax_grid(np.zeros((4, 4, 4)), 0.2, 3.0, np.ones(3), 2, method="BFGS")
+
+    class HostInterp:
+        def ip(self, xyz):
+            return 0.0
+    with pytest.raises(TypeError):
+        ops.relax_tip_z(0, 0, HostInterp(), 0.2, 40.0, np.arange(3), np.ones(3))
+
+
+def test_split_range():
+    assert parallel.split_range(76, 130, 8) == [(76, 82), (82, 89), (89, 96), (96, 103), (103, 109),
+                                                (109, 116), (116, 123), (123, 130)]
+    assert parallel.split_range(0, 3, 4) == [(0, 0), (0, 1), (1, 2), (2, 3)]
+    parts = parallel.split_range(0, 1024, 8)
+    assert parts[0] == (0, 128) and parts[-1] == (896, 1024)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch
+from dbspm_b200 import parallel
+rank, world, device = parallel.init_from_env("gloo")
+assert world == 2 and device.type == "cpu"
+rng = np.random.default_rng(5)
+full = torch.from_numpy(rng.random((5, 4, 7)))            # "window" every rank could compute
+def slab(zl, zh):
+    return full[:, :, zl - 10:zh - 10].contiguous()
+win = parallel.corr3d_sharded(slab, 5, 4, 10, 17, device)
+tiles = {{k: torch.from_numpy(rng.random((5, 4, 3))) for k in ("E", "tip_x")}}
+def tile(i_lo, i_hi):
+    return {{k: v[i_lo:i_hi].contiguous() for k, v in tiles.items()}}
+res = parallel.relax_sharded(tile, 5, device)
+t = torch.arange(3.0) if rank == 0 else torch.zeros(3)
+parallel.broadcast_(t)
+assert torch.equal(t, torch.arange(3.0))
+if rank == 0:
+    assert torch.equal(win, full), "z-slab gather/interleave"
+    assert all(torch.equal(res[k], tiles[k]) for k in tiles), "x-tile gather"
+    print("RANK0_OK")
+else:
+    assert win is None and res is None
+torch.distributed.barrier()
+torch.distributed.destroy_process_group()
+'''
+
+
+def test_partition_and_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2", CUDA_VISIBLE_DEVICES="")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "RANK0_OK" in outs[0]
+
+
+def test_sph2cart_matches_definition():
+    th, az = np.array([3.0, 2.5]), np.array([0.3, -1.0])
+    x, y, z = sph2cart(th, az, 3.02)
+    assert np.allclose(x ** 2 + y ** 2 + z ** 2, 3.02 ** 2)
+    assert np.allclose(z, 3.02 * np.cos(th))
