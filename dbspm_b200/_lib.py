@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdbspm_b200.so")
+# DBSPM_B200_LIB selects another build of the same CUDA library (developer A/B timing of kernel variants)
+LIB_PATH = os.environ.get("DBSPM_B200_LIB") or os.path.join(_HERE, "libdbspm_b200.so")
 
 OK = 0
 EINVAL, EUNSUPPORTED, EWORKSPACE, ECUDA = -1, -2, -3, -4
@@ -36,7 +37,8 @@ _SIGNATURES = {
     "dbspm_relax_powell_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
                                          C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int,
-                                         _vp, _vp, _vp, _vp]),
+                                         _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "dbspm_relax_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "dbspm_tricubic_gather_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp, _vp]),
     "dbspm_dfz_gradient_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp]),
 }

@@ -16,10 +16,25 @@ __global__ void __launch_bounds__(DBSPM_THREADS) axis_pass_kernel(const __grid_c
     axis_pass_body<D>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
 }
 
+template <int D>
+__global__ void __launch_bounds__(DBSPM_THREADS, 2) axis_pass2_kernel(const __grid_constant__ AxisParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    axis_pass_body_v2<D>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
+}
+
 __global__ void __launch_bounds__(DBSPM_THREADS) zfused_kernel(const __grid_constant__ ZFusedParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     zfused_body(P, smem, (long long)blockIdx.x, (int)threadIdx.x, (int)blockDim.x);
+}
+
+#define ZF2_PAIRS 4
+#define ZF2_THREADS 128
+__global__ void __launch_bounds__(ZF2_THREADS) zfused2_kernel(const __grid_constant__ ZFusedParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    zfused_body_v2<ZF2_PAIRS>(P, smem, (long long)blockIdx.x, (int)threadIdx.x, (int)blockDim.x);
 }
 
 __global__ void __launch_bounds__(DBSPM_THREADS) compact_kernel(const double *W, double *E, long long ncol, int nzw, int ldw)
@@ -33,6 +48,7 @@ struct DevPlan {
     HostPlan host;
     cplx *tw = nullptr;
     int *pos_of = nullptr;
+    int *freq_of = nullptr;
 };
 
 static std::mutex g_plan_mu;
@@ -56,6 +72,8 @@ static int get_plan(int n, cudaStream_t st, DevPlan **out)
     // the host vectors live as long as the cache entry, so the async copies stay valid
     DBSPM_CUDA_TRY(cudaMemcpyAsync(p->tw, p->host.tw.data(), sizeof(cplx) * (size_t)n, cudaMemcpyHostToDevice, st));
     DBSPM_CUDA_TRY(cudaMemcpyAsync(p->pos_of, p->host.pos_of.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    DBSPM_CUDA_TRY(cudaMalloc((void **)&p->freq_of, sizeof(int) * (size_t)n));
+    DBSPM_CUDA_TRY(cudaMemcpyAsync(p->freq_of, p->host.freq_of.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
     // tables may be used from other streams later: make them visible before returning
     DBSPM_CUDA_TRY(cudaStreamSynchronize(st));
     g_plans[{dev, n}] = p;
@@ -78,7 +96,7 @@ static int pick_tshift(int n, long long inner)
 template <int D>
 static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, int narrays,
                        double alpha0, double alpha1, int use_pow, int n, long long inner, long long outer,
-                       cudaStream_t st)
+                       cudaStream_t st, int flags)
 {
     DevPlan *pl = nullptr;
     int rc = get_plan(n, st, &pl);
@@ -88,15 +106,30 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     P.alpha[0] = alpha0; P.alpha[1] = alpha1;
     P.use_pow = use_pow; P.narrays = narrays;
     P.n = n; P.inner = inner; P.outer = outer;
-    P.tshift = pick_tshift(n, inner);
-    DBSPM_REQUIRE(P.tshift >= 0, DBSPM_EUNSUPPORTED, "axis length %d does not fit in shared memory", n);
+    P.plan = pl->host.dev; P.tw = pl->tw; P.pos_of = pl->pos_of; P.freq_of = pl->freq_of;
+    P.v2 = axis_v2_ok(P.plan) && !(flags & DBSPM_CORR_AXIS_V1);
+    P.tw_smem = 0;
+    size_t smem;
+    if (P.v2) {
+        axis2_config(n, inner, P.plan.nstages, &P.tshift, &P.tw_smem);
+        smem = axis2_smem_bytes(n, P.tshift, P.plan.nstages, P.tw_smem);
+        if (smem > 227 * 1024) P.v2 = 0;
+    }
+    if (!P.v2) {
+        P.tshift = pick_tshift(n, inner);
+        DBSPM_REQUIRE(P.tshift >= 0, DBSPM_EUNSUPPORTED, "axis length %d does not fit in shared memory", n);
+        smem = axis_smem_bytes(n, P.tshift);
+    }
     P.tiles = (inner + (1LL << P.tshift) - 1) >> P.tshift;
-    P.plan = pl->host.dev; P.tw = pl->tw; P.pos_of = pl->pos_of;
     const long long nblocks = outer * P.tiles;
     DBSPM_REQUIRE(nblocks > 0 && nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large (%lld blocks)", nblocks);
-    const size_t smem = axis_smem_bytes(n, P.tshift);
-    DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    axis_pass_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), DBSPM_THREADS, smem, st>>>(P);
+    if (P.v2) {
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        axis_pass2_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), DBSPM_THREADS, smem, st>>>(P);
+    } else {
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        axis_pass_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), DBSPM_THREADS, smem, st>>>(P);
+    }
     DBSPM_CUDA_TRY(cudaGetLastError());
     return DBSPM_OK;
 }
@@ -137,11 +170,11 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
     int rc;
     // forward x (out of place, power fused into the load), then y in place
     if (!(flags & DBSPM_CORR_SKIP_XFWD)) {
-        rc = launch_axis<-1>((const cplx *)A, WA, (const cplx *)B, WB, 2, alphaA, alphaB, 1, nx, (long long)ny * n, 1, st);
+        rc = launch_axis<-1>((const cplx *)A, WA, (const cplx *)B, WB, 2, alphaA, alphaB, 1, nx, (long long)ny * n, 1, st, flags);
         if (rc) return rc;
     }
     if (!(flags & DBSPM_CORR_SKIP_YFWD)) {
-        rc = launch_axis<-1>(WA, WA, WB, WB, 2, 1.0, 1.0, 0, ny, n, nx, st);
+        rc = launch_axis<-1>(WA, WA, WB, WB, 2, 1.0, 1.0, 0, ny, n, nx, st, flags);
         if (rc) return rc;
     }
 
@@ -158,22 +191,32 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
         P.scale = dV / ((double)nx * (double)ny * (double)nz) * 0.25;
         P.plan = pl->host.dev; P.tw = pl->tw; P.pos_of = pl->pos_of; P.twN = plN->tw;
         P.npairs = (long long)(nx / 2 + 1) * ny;
-        const long long nblocks = (P.npairs + ZL - 1) / ZL;
-        const size_t smem = zfused_smem_bytes(n);
-        DBSPM_REQUIRE(smem <= 227 * 1024, DBSPM_EUNSUPPORTED, "nz=%d too long for the fused z kernel", nz);
-        DBSPM_REQUIRE(nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large");
-        DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        zfused_kernel<<<(unsigned)nblocks, DBSPM_THREADS, smem, st>>>(P);
+        const bool v2 = axis_v2_ok(P.plan) && zfused2_smem_bytes<ZF2_PAIRS>(n) <= 113 * 1024 &&
+                        !(flags & DBSPM_CORR_AXIS_V1);
+        if (v2) {
+            const long long nblocks = (P.npairs + ZF2_PAIRS - 1) / ZF2_PAIRS;
+            const size_t smem = zfused2_smem_bytes<ZF2_PAIRS>(n);
+            DBSPM_REQUIRE(nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large");
+            DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            zfused2_kernel<<<(unsigned)nblocks, ZF2_THREADS, smem, st>>>(P);
+        } else {
+            const long long nblocks = (P.npairs + ZL - 1) / ZL;
+            const size_t smem = zfused_smem_bytes(n);
+            DBSPM_REQUIRE(smem <= 227 * 1024, DBSPM_EUNSUPPORTED, "nz=%d too long for the fused z kernel", nz);
+            DBSPM_REQUIRE(nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large");
+            DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            zfused_kernel<<<(unsigned)nblocks, DBSPM_THREADS, smem, st>>>(P);
+        }
         DBSPM_CUDA_TRY(cudaGetLastError());
     }
 
     // inverse y, then x on the packed window (in place)
     if (!(flags & DBSPM_CORR_SKIP_YINV)) {
-        rc = launch_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, st);
+        rc = launch_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, st, flags);
         if (rc) return rc;
     }
     if (!(flags & DBSPM_CORR_SKIP_XINV)) {
-        rc = launch_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)ny * nwh, 1, st);
+        rc = launch_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)ny * nwh, 1, st, flags);
         if (rc) return rc;
     }
 

@@ -32,7 +32,10 @@ struct AxisParams {
     long long tiles;          // ceil(inner / T)
     FftPlanDev plan;
     const cplx *tw;           // device tables for length n
-    const int *pos_of;
+    const int *pos_of;        // frequency -> in-place position
+    const int *freq_of;       // in-place position -> frequency
+    int v2;                   // 1: register-first/last body (axis_pass_body_v2)
+    int tw_smem;              // v2: stage the twiddle table in shared memory (else read it through L1)
 };
 
 HD size_t axis_smem_bytes(int n, int tshift)
@@ -82,6 +85,182 @@ HD void axis_pass_body(const AxisParams &P, unsigned char *smem_raw, long long b
     for (int idx = tid; idx < total; idx += nthr) {
         const int t = idx & tmask, K = idx >> P.tshift;
         if (t < tcount) gout[(size_t)K * P.inner + t] = s[((size_t)pos_of[K] << P.tshift) + t];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// v2 of the strided-axis pass ("register first, register last").  The first radix stage reads
+// its r rows straight from global memory into registers (r independent 128-bit streaming loads
+// in flight per thread), applies the optional power, the butterfly and the twiddles, and only
+// then touches shared memory; the last stage reads shared memory, does its butterfly and
+// streams the rows to their frequency positions in global memory.  Shared-memory traffic per
+// element drops from 2*(stages+1) to 2*(stages-1) 16-byte accesses and two block barriers
+// disappear.  Used when every radix of the plan is one of {2,3,4,5,7,8,16}.
+// ------------------------------------------------------------------------------------------
+HD cplx ld_stream(const cplx *p)
+{
+#if defined(__CUDA_ARCH__)
+    const double2 v = __ldcs(reinterpret_cast<const double2 *>(p));
+    return cmake(v.x, v.y);
+#else
+    return *p;
+#endif
+}
+
+HD void st_stream(cplx *p, cplx v)
+{
+#if defined(__CUDA_ARCH__)
+    __stcs(reinterpret_cast<double2 *>(p), make_double2(v.x, v.y));
+#else
+    *p = v;
+#endif
+}
+
+HD bool axis_v2_ok(const FftPlanDev &pl)
+{
+    if (pl.nstages < 1) return false;
+    for (int i = 0; i < pl.nstages; ++i) {
+        const int r = pl.radix[i];
+        if (!(r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16)) return false;
+    }
+    return true;
+}
+
+// shared memory of the v2 body: [twiddles n*16 if tw_smem] [tile n*T*16 if nstages > 1]
+HD size_t axis2_smem_bytes(int n, int tshift, int nstages, int tw_smem)
+{
+    return (tw_smem ? (size_t)n * 16 : 0) + (nstages > 1 ? ((size_t)n << tshift) * 16 : 0);
+}
+
+// launch geometry of the v2 body: widest tile (8,4,2,1 lines) that still leaves room for three
+// resident CTAs per SM; the twiddle table is staged in shared memory only if that still holds
+HD void axis2_config(int n, long long inner, int nstages, int *tshift, int *tw_smem)
+{
+    const size_t budget = 220 * 1024 / 3;
+    int ts = 3;
+    while (ts > 0 && ((1LL << ts) > 2 * inner || axis2_smem_bytes(n, ts, nstages, 0) > budget)) --ts;
+    *tshift = ts;
+    *tw_smem = axis2_smem_bytes(n, ts, nstages, 1) <= budget ? 1 : 0;
+}
+
+template <int D, int R>
+HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gin, cplx *gout, int tcount,
+                    bool do_pow, double alpha, int tid, int nthr)
+{
+    const int n = P.n, q = n / R, tmask = (1 << P.tshift) - 1;
+    const bool single = P.plan.nstages == 1;
+    const int total = q << P.tshift;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int t = idx & tmask, j = idx >> P.tshift;
+        cplx v[R];
+        if (t < tcount) {
+            const cplx *src = gin + (size_t)j * P.inner + t;
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = ld_stream(src + (size_t)k * q * P.inner);
+            if (do_pow) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) { v[k].x = pow_nonneg(v[k].x, alpha); v[k].y = pow_nonneg(v[k].y, alpha); }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = cmake(0.0, 0.0);
+        }
+        bfly<R, D>(v);
+        if (single) {
+            if (t < tcount) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) st_stream(gout + (size_t)k * P.inner + t, v[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 1; k < R; ++k) {
+                const cplx w = tw[j * k];
+                v[k] = D < 0 ? cmul(v[k], w) : cmulc(v[k], w);
+            }
+            cplx *dst = s + ((size_t)j << P.tshift) + t;
+#pragma unroll
+            for (int k = 0; k < R; ++k) dst[((size_t)k * q) << P.tshift] = v[k];
+        }
+    }
+}
+
+template <int D, int R>
+HD void axis2_last(const AxisParams &P, const cplx *s, cplx *gout, int tcount, int tid, int nthr)
+{
+    const int n = P.n, nb = n / R, tmask = (1 << P.tshift) - 1;
+    const int total = nb << P.tshift;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int t = idx & tmask, blk = idx >> P.tshift;
+        const cplx *src = s + ((size_t)(blk * R) << P.tshift) + t;
+        cplx v[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = src[(size_t)k << P.tshift];
+        bfly<R, D>(v);
+        if (t < tcount) {
+            const int K0 = LDG(P.freq_of + blk * R);           // frequency held by position blk*R
+            cplx *dst = gout + (size_t)K0 * P.inner + t;
+#pragma unroll
+            for (int k = 0; k < R; ++k) st_stream(dst + (size_t)k * nb * P.inner, v[k]);
+        }
+    }
+}
+
+template <int D>
+HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long long bid, int which, int tid, int nthr)
+{
+    const int n = P.n, T = 1 << P.tshift;
+    const FftPlanDev &pl = P.plan;
+    cplx *twbuf = (cplx *)smem_raw;
+    cplx *s = P.tw_smem ? twbuf + n : twbuf;
+    const cplx *tw = P.tw_smem ? (const cplx *)twbuf : P.tw;
+
+    const long long o = bid / P.tiles;
+    const long long tile = bid - o * P.tiles;
+    const long long i0 = tile << P.tshift;
+    const int tcount = (int)((P.inner - i0) < T ? (P.inner - i0) : T);
+    const cplx *gin = P.in[which] + (size_t)o * n * P.inner + i0;
+    cplx *gout = P.out[which] + (size_t)o * n * P.inner + i0;
+    const double alpha = P.alpha[which];
+    const bool do_pow = P.use_pow && alpha != 1.0;
+
+    if (P.tw_smem && pl.nstages > 1) {
+        for (int e = tid; e < n; e += nthr) twbuf[e] = ldg_c(P.tw + e);
+        BLOCK_SYNC();
+    }
+    switch (pl.radix[0]) {
+    case 2: axis2_first<D, 2>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
+    case 3: axis2_first<D, 3>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
+    case 4: axis2_first<D, 4>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
+    case 5: axis2_first<D, 5>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
+    case 7: axis2_first<D, 7>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
+    case 8: axis2_first<D, 8>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
+    default: axis2_first<D, 16>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
+    }
+    if (pl.nstages == 1) return;
+    BLOCK_SYNC();
+    int m = n / pl.radix[0];
+    for (int st = 1; st + 1 < pl.nstages; ++st) {
+        const int r = pl.radix[st];
+        switch (r) {
+        case 2: fft_stage<2, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
+        case 3: fft_stage<3, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
+        case 4: fft_stage<4, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
+        case 5: fft_stage<5, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
+        case 7: fft_stage<7, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
+        case 8: fft_stage<8, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
+        default: fft_stage<16, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
+        }
+        m /= r;
+        BLOCK_SYNC();
+    }
+    switch (pl.radix[pl.nstages - 1]) {
+    case 2: axis2_last<D, 2>(P, s, gout, tcount, tid, nthr); break;
+    case 3: axis2_last<D, 3>(P, s, gout, tcount, tid, nthr); break;
+    case 4: axis2_last<D, 4>(P, s, gout, tcount, tid, nthr); break;
+    case 5: axis2_last<D, 5>(P, s, gout, tcount, tid, nthr); break;
+    case 7: axis2_last<D, 7>(P, s, gout, tcount, tid, nthr); break;
+    case 8: axis2_last<D, 8>(P, s, gout, tcount, tid, nthr); break;
+    default: axis2_last<D, 16>(P, s, gout, tcount, tid, nthr); break;
     }
 }
 
@@ -220,6 +399,162 @@ HD void zfused_body(const ZFusedParams &P, unsigned char *smem_raw, long long bi
         if (!pr[l].valid || (role == 1 && pr[l].self)) continue;
         const int x = role ? pr[l].mx : pr[l].kx, y = role ? pr[l].my : pr[l].ky;
         P.W[((size_t)x * P.ny + y) * P.nwh + j] = S[(size_t)pos_of[j] * ZLD_INV + line];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// v2 of the fused z kernel: ZLV line pairs per block (4*ZLV forward lines keep every butterfly
+// stage at >= one work item per thread with radix-16 stages), and the first forward stage reads
+// the contiguous z-lines straight from global memory into registers (coalesced: consecutive
+// threads take consecutive positions of one line) and writes the transposed, padded tile.
+// Pair bookkeeping lives in shared memory (no per-thread arrays).  Same algebra as zfused_body.
+// ------------------------------------------------------------------------------------------
+template <int ZLV> HD size_t zfused2_smem_bytes(int n)
+{
+    return (size_t)n * 16 * 2 + (size_t)n * (4 * ZLV + 1) * 16 + (size_t)n * (2 * ZLV + 1) * 16 + (size_t)n * 4 + ZLV * 6 * 4 + 16;
+}
+
+template <int D, int R, int ZLV>
+HD void zfused2_first(const ZFusedParams &P, cplx *U, const cplx *tw, const int *pinfo, int tid, int nthr)
+{
+    constexpr int LDF = 4 * ZLV + 1;
+    const int n = P.n, q = n / R;
+    const int total = 4 * ZLV * q;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int line = idx / q, j = idx - line * q;
+        const int l = line >> 2, role = line & 3;
+        const int *pi = pinfo + 6 * l;
+        cplx v[R];
+        if (pi[4]) {
+            const cplx *src = ((role & 2) ? P.ZB : P.ZA)
+                              + ((size_t)((role & 1) ? pi[2] : pi[0]) * P.ny + ((role & 1) ? pi[3] : pi[1])) * n + j;
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = ld_stream(src + k * q);
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = cmake(0.0, 0.0);
+        }
+        bfly<R, D>(v);
+        if (q > 1) {
+#pragma unroll
+            for (int k = 1; k < R; ++k) {
+                const cplx w = tw[j * k];
+                v[k] = D < 0 ? cmul(v[k], w) : cmulc(v[k], w);
+            }
+        }
+        cplx *dst = U + (size_t)j * LDF + line;
+#pragma unroll
+        for (int k = 0; k < R; ++k) dst[(size_t)k * q * LDF] = v[k];
+    }
+}
+
+template <int D>
+HD void fft_stages_from(cplx *s, int ld, int tshift, const FftPlanDev &pl, int first, const cplx *tw, int tid, int nthr)
+{
+    int m = pl.n;
+    for (int st = 0; st < first; ++st) m /= pl.radix[st];
+    for (int st = first; st < pl.nstages; ++st) {
+        const int r = pl.radix[st];
+        switch (r) {
+        case 2: fft_stage<2, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 3: fft_stage<3, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 4: fft_stage<4, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 5: fft_stage<5, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 7: fft_stage<7, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 8: fft_stage<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        default: fft_stage<16, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        }
+        m /= r;
+        BLOCK_SYNC();
+    }
+}
+
+template <int ZLV>
+HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long bid, int tid, int nthr)
+{
+    constexpr int TF = 4 * ZLV, TI = 2 * ZLV, LDF = TF + 1, LDI = TI + 1;
+    constexpr int TSF = ZLV == 1 ? 2 : (ZLV == 2 ? 3 : (ZLV == 4 ? 4 : 5));
+    constexpr int TSI = TSF - 1;
+    const int n = P.n;
+    cplx *tw = (cplx *)smem_raw;
+    cplx *twh = tw + n;
+    cplx *U = twh + n;
+    cplx *S = U + (size_t)n * LDF;
+    int *pos_of = (int *)(S + (size_t)n * LDI);
+    int *pinfo = pos_of + n;                  // per pair: kx, ky, mx, my, valid, self
+
+    for (int e = tid; e < n; e += nthr) {
+        tw[e] = ldg_c(P.tw + e);
+        twh[e] = ldg_c(P.twN + e);
+        pos_of[e] = LDG(P.pos_of + e);
+    }
+    for (int l = tid; l < ZLV; l += nthr) {
+        const ZPair z = zpair_of(P, bid * ZLV + l);
+        int *pi = pinfo + 6 * l;
+        pi[0] = z.kx; pi[1] = z.ky; pi[2] = z.mx; pi[3] = z.my; pi[4] = z.valid; pi[5] = z.self;
+    }
+    BLOCK_SYNC();
+    switch (P.plan.radix[0]) {
+    case 2: zfused2_first<-1, 2, ZLV>(P, U, tw, pinfo, tid, nthr); break;
+    case 3: zfused2_first<-1, 3, ZLV>(P, U, tw, pinfo, tid, nthr); break;
+    case 4: zfused2_first<-1, 4, ZLV>(P, U, tw, pinfo, tid, nthr); break;
+    case 5: zfused2_first<-1, 5, ZLV>(P, U, tw, pinfo, tid, nthr); break;
+    case 7: zfused2_first<-1, 7, ZLV>(P, U, tw, pinfo, tid, nthr); break;
+    case 8: zfused2_first<-1, 8, ZLV>(P, U, tw, pinfo, tid, nthr); break;
+    default: zfused2_first<-1, 16, ZLV>(P, U, tw, pinfo, tid, nthr); break;
+    }
+    BLOCK_SYNC();
+    fft_stages_from<-1>(U, LDF, TSF, P.plan, 1, tw, tid, nthr);
+
+    const int nk = n / 2 + 1;
+    const double sgn = (P.z_lo & 1) ? -1.0 : 1.0;
+    const long long N2 = 2LL * n;
+    for (int idx = tid; idx < nk * ZLV; idx += nthr) {
+        const int l = idx / nk, k = idx - l * nk;
+        const int ks = k == 0 ? 0 : n - k;
+        if (k > ks) continue;
+        const cplx *Uk = U + (size_t)pos_of[k] * LDF + 4 * l;
+        const cplx *Us = U + (size_t)pos_of[ks] * LDF + 4 * l;
+        cplx G1[2], G2[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int kk = h == 0 ? k : ks;
+            const cplx *Ua = h == 0 ? Uk : Us, *Ub = h == 0 ? Us : Uk;
+            const cplx w = twh[kk];
+            const cplx miw = cmake(w.y, -w.x);
+            cplx a1 = Ua[0], a2 = cconj(Ub[1]);
+            cplx b1 = Ua[2], b2 = cconj(Ub[3]);
+            cplx ea = cadd(a1, a2), ta = cmul(miw, csub(a1, a2));
+            cplx eb = cadd(b1, b2), tb = cmul(miw, csub(b1, b2));
+            cplx alo = cadd(ea, ta), ahi = csub(ea, ta);
+            cplx blo = cadd(eb, tb), bhi = csub(eb, tb);
+            cplx plo = cscale(cmulc(alo, blo), P.scale);
+            cplx phi = cscale(cmulc(ahi, bhi), P.scale * sgn);
+            const cplx ph = cconj(ldg_c(P.twN + (int)(((long long)kk * P.z_lo) % N2)));
+            plo = cmul(plo, ph);
+            phi = cmul(phi, ph);
+            G1[h] = cadd(plo, phi);
+            G2[h] = cmulc(csub(plo, phi), w);
+        }
+        cplx *Sk = S + (size_t)k * LDI + 2 * l;
+        cplx *Ss = S + (size_t)ks * LDI + 2 * l;
+        Sk[0] = cmake(G1[0].x - G2[0].y, G1[0].y + G2[0].x);
+        Sk[1] = cmake(G1[1].x + G2[1].y, -G1[1].y + G2[1].x);
+        if (ks != k) {
+            Ss[0] = cmake(G1[1].x - G2[1].y, G1[1].y + G2[1].x);
+            Ss[1] = cmake(G1[0].x + G2[0].y, -G1[0].y + G2[0].x);
+        }
+    }
+    BLOCK_SYNC();
+    fft_stages_from<1>(S, LDI, TSI, P.plan, 0, tw, tid, nthr);
+
+    for (int idx = tid; idx < P.nwh * TI; idx += nthr) {
+        const int line = idx / P.nwh, j = idx - line * P.nwh;
+        const int l = line >> 1, role = line & 1;
+        const int *pi = pinfo + 6 * l;
+        if (!pi[4] || (role == 1 && pi[5])) continue;
+        const int x = role ? pi[2] : pi[0], y = role ? pi[3] : pi[1];
+        st_stream(P.W + ((size_t)x * P.ny + y) * P.nwh + j, S[(size_t)pos_of[j] * LDI + line]);
     }
 }
 

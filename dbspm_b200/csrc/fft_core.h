@@ -55,6 +55,43 @@ template <int D> HD void bfly8(cplx *v)
     v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
 }
 
+// v * (cr + i*D*ci)
+template <int D> HD cplx cmul_cD(cplx v, double cr, double ci)
+{
+    return cmake(v.x * cr - D * (v.y * ci), v.y * cr + D * (v.x * ci));
+}
+
+// radix 16 = 4 x 4: X[k1 + 4 k2] = sum_b W16^{b k1} W4^{b k2} sum_a x[4a + b] W4^{a k1}
+template <int D> HD void bfly16(cplx *v)
+{
+    const double c1 = 0.92387953251128674, s1 = 0.38268343236508977, h = 0.70710678118654752440;
+    cplx t[4][4];                                     // t[b][k1]
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        cplx col[4] = {v[b], v[4 + b], v[8 + b], v[12 + b]};
+        bfly4<D>(col);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) t[b][k1] = col[k1];
+    }
+    // twiddles W16^{b k1} = exp(i D 2 pi b k1 / 16)
+    t[1][1] = cmul_cD<D>(t[1][1], c1, s1);            // W^1
+    t[1][2] = cmul_cD<D>(t[1][2], h, h);              // W^2
+    t[1][3] = cmul_cD<D>(t[1][3], s1, c1);            // W^3
+    t[2][1] = cmul_cD<D>(t[2][1], h, h);              // W^2
+    t[2][2] = cmul_iD<D>(t[2][2]);                    // W^4
+    t[2][3] = cmul_cD<D>(t[2][3], -h, h);             // W^6
+    t[3][1] = cmul_cD<D>(t[3][1], s1, c1);            // W^3
+    t[3][2] = cmul_cD<D>(t[3][2], -h, h);             // W^6
+    t[3][3] = cmul_cD<D>(t[3][3], -c1, -s1);          // W^9
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        cplx row[4] = {t[0][k1], t[1][k1], t[2][k1], t[3][k1]};
+        bfly4<D>(row);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) v[k1 + 4 * k2] = row[k2];
+    }
+}
+
 template <int P> struct OddTab;
 template <> struct OddTab<3> {
     static HD double c(int m) { const double t[3] = {1.0, -0.5, -0.5}; return t[m]; }
@@ -107,6 +144,7 @@ template <int R, int D> HD void bfly(cplx *v)
     else if (R == 5) bfly_odd<5, D>(v);
     else if (R == 7) bfly_odd<7, D>(v);
     else if (R == 8) bfly8<D>(v);
+    else if (R == 16) bfly16<D>(v);
 }
 
 // ---- one DIF stage over the whole tile ----------------------------------------------------
@@ -193,6 +231,7 @@ HD void fft_tile(cplx *s, int ld, int tshift, const FftPlanDev &pl, const cplx *
         case 5: fft_stage<5, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
         case 7: fft_stage<7, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
         case 8: fft_stage<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 16: fft_stage<16, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
         default: fft_stage_generic<D>(s, ld, tshift, pl.n, m, r, tw, tid, nthr); break;
         }
         m /= r;

@@ -22,9 +22,13 @@
 
 #if defined(__CUDA_ARCH__)
 #define BLOCK_SYNC() __syncthreads()
+#define WARP_SYNC() __syncwarp()
+#define WARP_ALL(p) __all_sync(0xffffffffu, (p))
 #define LDG(p) __ldg(p)
 #else
 #define BLOCK_SYNC() ((void)0)
+#define WARP_SYNC() ((void)0)
+#define WARP_ALL(p) (p)
 #define LDG(p) (*(p))
 #endif
 

@@ -24,13 +24,13 @@ bool dbspm_make_plan(int n, HostPlan &out)
     int twos = 0;
     while (rem % 2 == 0) { rem /= 2; ++twos; }
     if (rem != 1) return false;                    // prime factor > DBSPM_MAX_RADIX
-    // 2^twos as radix-8 stages, remainder 1 -> (4,4) replaces (8,2), remainder 2 -> one radix-4
-    int n8 = twos / 3, r = twos % 3;
-    if (r == 1 && n8 >= 1) { n8 -= 1; for (int i = 0; i < n8; ++i) if (!push(8)) return false; if (!push(4) || !push(4)) return false; }
-    else {
-        for (int i = 0; i < n8; ++i) if (!push(8)) return false;
-        if (r == 1) { if (!push(2)) return false; }
-        if (r == 2) { if (!push(4)) return false; }
+    // 2^twos over ceil(twos/4) stages of radix <= 16, bits spread evenly, larger radices first
+    if (twos > 0) {
+        const int ns = (twos + 3) / 4;
+        for (int i = 0; i < ns; ++i) {
+            const int bits = twos / ns + (i < twos % ns ? 1 : 0);
+            if (!push(1 << bits)) return false;
+        }
     }
     if (n == 1) { d.nstages = 0; }
 
@@ -42,6 +42,7 @@ bool dbspm_make_plan(int n, HostPlan &out)
         out.tw[e].y = (double)(-sinl(a));
     }
     out.pos_of.assign(n, 0);
+    out.freq_of.assign(n, 0);
     for (int p = 0; p < n; ++p) {
         int r0 = p, sub = n, K = 0, mult = 1;
         for (int st = 0; st < d.nstages; ++st) {
@@ -52,6 +53,7 @@ bool dbspm_make_plan(int n, HostPlan &out)
             mult *= d.radix[st];
         }
         out.pos_of[K] = p;
+        out.freq_of[p] = K;
     }
     return true;
 }

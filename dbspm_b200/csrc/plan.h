@@ -7,6 +7,7 @@ struct HostPlan {
     FftPlanDev dev;
     std::vector<cplx> tw;       // tw[e] = exp(-2 pi i e / n)
     std::vector<int> pos_of;    // pos_of[K] = in-place position holding frequency K after the DIF stages
+    std::vector<int> freq_of;   // inverse table: freq_of[pos_of[K]] = K
 };
 
 // returns false if n has a prime factor > DBSPM_MAX_RADIX or needs too many stages

@@ -6,12 +6,32 @@
 #include "capi_common.h"
 #include "relax_body.h"
 
+#ifndef RELAX_THREADS
 #define RELAX_THREADS 128
+#endif
+#ifndef RELAX_MIN_BLOCKS
+#define RELAX_MIN_BLOCKS 3   /* measured on B200: 3 CTAs of 128 (168 regs) beat 2 (183) and 4 (128 + spills) */
+#endif
 
-__global__ void __launch_bounds__(RELAX_THREADS) relax_kernel(const __grid_constant__ RelaxParams P, long long ncol)
+__global__ void __launch_bounds__(256) relax_cart_kernel(const double *etp, double *cart, long long npos, double rpivot)
+{
+    relax_cart_body(etp, cart, npos, rpivot, (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                    (long long)gridDim.x * blockDim.x);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(RELAX_THREADS, RELAX_MIN_BLOCKS) relax_kernel(const __grid_constant__ RelaxParams P, long long ncol)
 {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col < ncol) relax_column_body(P, col);
+    relax_column_body<LAYOUT>(P, col, ncol);      // lanes past the end idle inside (warp barrier)
+}
+
+// (nx,ny,nz) -> (nx,nz,ny) so that the lanes of a warp (adjacent y columns) read adjacent addresses
+__global__ void __launch_bounds__(256) transpose_yz_kernel(const double *in, double *out, int ny, int nz)
+{
+    __shared__ double tile[32 * 33];
+    transpose_yz_tile(in, out, ny, nz, tile, (int)blockIdx.x, (int)blockIdx.y, (long long)blockIdx.z,
+                      (int)threadIdx.x, (int)threadIdx.y, (int)blockDim.y);
 }
 
 __global__ void __launch_bounds__(256) accumulate_kernel(double *acc, const double *comp, double scale, size_t n, int init)
@@ -26,9 +46,10 @@ __global__ void __launch_bounds__(256) accumulate_kernel(double *acc, const doub
 __global__ void __launch_bounds__(256) gather_kernel(const double *data, int nx, int ny, int nz,
                                                      const double *pts, size_t npts, double *out)
 {
+    const double inv_n[3] = {1.0 / nx, 1.0 / ny, 1.0 / nz};
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += stride)
-        out[i] = tricubic_eval(data, nx, ny, nz, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+        out[i] = tricubic_eval<0>(data, nx, ny, nz, inv_n, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
 }
 
 // np.gradient(E, -dz, axis=2): central differences inside, one-sided first order at the ends
@@ -75,11 +96,18 @@ extern "C" int dbspm_static_accumulate_f64(double *acc, const double *comp, doub
     return DBSPM_OK;
 }
 
+extern "C" size_t dbspm_relax_workspace_bytes(int nx, int ny, int nzc)
+{
+    if (nx < 1 || ny < 1 || nzc < 1) return 0;
+    return (size_t)nx * ny * nzc * sizeof(double);
+}
+
 extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
                                       int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
                                       double kappa, double rpivot, const double dr[3], const double *dR,
                                       double xtol, double ftol, int maxfev,
-                                      double *out_E_theta_phi, double *out_cart, int *out_nfev, void *stream)
+                                      double *out_E_theta_phi, double *out_cart, int *out_nfev,
+                                      void *workspace, size_t workspace_bytes, void *stream)
 {
     DBSPM_REQUIRE(static_win && dr && out_E_theta_phi, DBSPM_EINVAL, "null pointer argument");
     DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nzc >= 1, DBSPM_EINVAL, "bad grid shape (%d,%d,%d)", nx, ny, nzc);
@@ -93,6 +121,7 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
     P.npivot = rpivot / dr[2];
     P.rpivot_rt = P.npivot * dr[2];
     P.dr[0] = dr[0]; P.dr[1] = dr[1]; P.dr[2] = dr[2];
+    P.inv_n[0] = 1.0 / nx; P.inv_n[1] = 1.0 / ny; P.inv_n[2] = 1.0 / nzc;
     P.noortho = dR != nullptr;
     for (int q = 0; q < 9; ++q) P.Minv[q] = 0.0;
     if (dR) {
@@ -105,8 +134,26 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
     if (ncol == 0 || nz_relax == 0) return DBSPM_OK;
     const long long blocks = (ncol + RELAX_THREADS - 1) / RELAX_THREADS;
     DBSPM_REQUIRE(blocks < 2147483647LL, DBSPM_EUNSUPPORTED, "tile too large");
-    relax_kernel<<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
+    if (workspace) {
+        // re-lay the potential with y fastest (once per call, ~2 passes over the window)
+        DBSPM_REQUIRE(workspace_bytes >= dbspm_relax_workspace_bytes(nx, ny, nzc) && ((uintptr_t)workspace & 15) == 0,
+                      DBSPM_EWORKSPACE, "relax workspace needs %zu bytes (got %zu)",
+                      dbspm_relax_workspace_bytes(nx, ny, nzc), workspace_bytes);
+        DBSPM_REQUIRE(nx <= 65535, DBSPM_EUNSUPPORTED, "nx too large for the transpose grid");
+        dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 31) / 32), (unsigned)nx);
+        transpose_yz_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_win, (double *)workspace, ny, nzc);
+        DBSPM_CUDA_TRY(cudaGetLastError());
+        P.grid = (const double *)workspace;
+        relax_kernel<1><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
+    } else {
+        relax_kernel<0><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
+    }
     DBSPM_CUDA_TRY(cudaGetLastError());
+    if (out_cart) {
+        const long long npos = ncol * nz_relax;
+        relax_cart_kernel<<<grid_for((size_t)npos, 256), 256, 0, (cudaStream_t)stream>>>(out_E_theta_phi, out_cart, npos, rpivot);
+        DBSPM_CUDA_TRY(cudaGetLastError());
+    }
     return DBSPM_OK;
 }
 

@@ -24,7 +24,7 @@
 #endif
 
 struct RelaxParams {
-    const double *grid;       // (nx,ny,nzc) static potential, z fastest
+    const double *grid;       // static potential: (nx,ny,nzc) z fastest [LAYOUT 0] or (nx,nzc,ny) [LAYOUT 1]
     int nx, ny, nzc;
     int i_lo, i_hi, j_lo, j_hi;
     int nz_relax;
@@ -33,6 +33,7 @@ struct RelaxParams {
     double npivot;            // rpivot / dr[2]                     (dbspm:558)
     double rpivot_rt;         // npivot * dr[2]                     (interactions.py:73)
     double dr[3];
+    double inv_n[3];          // 1/nx, 1/ny, 1/nzc
     int noortho;
     double Minv[9];           // inv(dR^T), row-major
     double xtol, ftol;
@@ -43,10 +44,27 @@ struct RelaxParams {
 };
 
 // ---- periodic Catmull-Rom (a = -1/2) tricubic stencil in index units ---------------------
-HD void cr_axis(double p, int n, int *i0, double *w)
+// d = fmod(p, n), then "+= n if negative": the reference's periodic wrap, bit for bit.  fmod is
+// exact by definition; q = trunc(p/n) computed with a reciprocal can be off by one, the
+// fused p - q*n is still exact (Sterbenz) and one +-n correction restores fmod's range.
+HD double wrap_coord(double p, double n, double inv_n)
+{   // selects only, no branches: the 64-point stencil that follows must stay warp-converged
+    const double q = trunc(p * inv_n);
+    const double r = fma(-q, n, p);
+    const double pos = (r < 0.0) ? r + n : ((r >= n) ? r - n : r);          // p >= 0: fmod in [0,n)
+    double neg = (r > 0.0) ? r - n : ((r <= -n) ? r + n : r);               // p <  0: fmod in (-n,0]
+    neg = (neg < 0.0) ? neg + n : neg;                 // the reference's `if (dx < 0) dx += n` (rounds)
+    return (p >= 0.0) ? pos : neg;
+}
+
+HD void cr_axis(double p, int n, double inv_n, int *i0, double *w)
 {
+#if defined(RELAX_OLD_WRAP)
     double d = fmod(p, (double)n);
     if (d < 0) d += (double)n;
+#else
+    const double d = wrap_coord(p, (double)n, inv_n);
+#endif
     const double fl = floor(d);
     const double u = d - fl, u2 = u * u, u3 = u2 * u;
     *i0 = (int)fl;
@@ -57,39 +75,57 @@ HD void cr_axis(double p, int n, int *i0, double *w)
 }
 
 HD int wrap_idx(int i, int n)
-{
+{   // i in [-1, n+2] (stencil around a wrapped coordinate): selects instead of integer division;
+    // tiny grids (n < 4) can need more than one correction and take the modulo (uniform branch)
+#if defined(RELAX_OLD_WRAP)
     i %= n;
     return i < 0 ? i + n : i;
+#else
+    if (n < 4) {
+        i %= n;
+        return i < 0 ? i + n : i;
+    }
+    i = (i < 0) ? i + n : i;
+    return (i >= n) ? i - n : i;
+#endif
 }
 
-HD double tricubic_eval(const double *g, int nx, int ny, int nz, double x, double y, double z)
+// LAYOUT 0: g[(x*ny + y)*nz + z] (the caller's array, z fastest)
+// LAYOUT 1: g[(x*nz + z)*ny + y] (y fastest: the 32 lanes of a warp, which own adjacent y columns,
+//           read adjacent addresses -> 2-3 L1 wavefronts per load instead of ~8 and a 5x smaller
+//           per-warp cache footprint)
+template <int LAYOUT>
+HD double tricubic_eval(const double *g, int nx, int ny, int nz, const double *inv_n, double x, double y, double z)
 {
     int ix, iy, iz;
     double wx[4], wy[4], wz[4];
-    cr_axis(x, nx, &ix, wx);
-    cr_axis(y, ny, &iy, wy);
-    cr_axis(z, nz, &iz, wz);
-    int zi[4], yo[4];
+    cr_axis(x, nx, inv_n[0], &ix, wx);
+    cr_axis(y, ny, inv_n[1], &iy, wy);
+    cr_axis(z, nz, inv_n[2], &iz, wz);
+    int zi[4], yi[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         zi[c] = wrap_idx(iz - 1 + c, nz);
-        yo[c] = wrap_idx(iy - 1 + c, ny) * nz;
+        yi[c] = wrap_idx(iy - 1 + c, ny);
     }
     double r = 0.0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const double *gx = g + (size_t)wrap_idx(ix - 1 + a, nx) * ny * nz;
-        double ry = 0.0;
+        double rx = 0.0;
+        // same summation order for both layouts (y innermost), so the result does not depend on
+        // whether the caller supplied the transposition workspace
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const double *gy = gx + yo[b];
-            double rz = wz[0] * LDG(gy + zi[0]);
-            rz = fma(wz[1], LDG(gy + zi[1]), rz);
-            rz = fma(wz[2], LDG(gy + zi[2]), rz);
-            rz = fma(wz[3], LDG(gy + zi[3]), rz);
-            ry = fma(wy[b], rz, ry);
+        for (int c = 0; c < 4; ++c) {
+            const int sy = LAYOUT == 0 ? nz : 1;
+            const double *gz = gx + (LAYOUT == 0 ? zi[c] : zi[c] * ny);
+            double ry = wy[0] * LDG(gz + yi[0] * sy);
+            ry = fma(wy[1], LDG(gz + yi[1] * sy), ry);
+            ry = fma(wy[2], LDG(gz + yi[2] * sy), ry);
+            ry = fma(wy[3], LDG(gz + yi[3] * sy), ry);
+            rx = fma(wz[c], ry, rx);
         }
-        r = fma(wx[a], ry, r);
+        r = fma(wx[a], rx, r);
     }
     return r;
 }
@@ -99,6 +135,7 @@ extern double (*dbspm_emu_interp_hook)(double, double, double);
 #endif
 
 // ---- objective: Emin / Emin_norm ----------------------------------------------------------
+template <int LAYOUT>
 HD double relax_objective(const RelaxParams &P, int oi, int oj, int ok, double th, double az)
 {
     const double d = M_PI - th;
@@ -127,7 +164,7 @@ HD double relax_objective(const RelaxParams &P, int oi, int oj, int ok, double t
     if (dbspm_emu_interp_hook)
         return dbspm_emu_interp_hook((double)oi + ox, (double)oj + oy, (double)ok + oz) + spr;
 #endif
-    return tricubic_eval(P.grid, P.nx, P.ny, P.nzc, (double)oi + ox, (double)oj + oy, (double)ok + oz) + spr;
+    return tricubic_eval<LAYOUT>(P.grid, P.nx, P.ny, P.nzc, P.inv_n, (double)oi + ox, (double)oj + oy, (double)ok + oz) + spr;
 }
 
 // ---- Powell / Brent / bracket state machine -----------------------------------------------
@@ -192,19 +229,19 @@ HDN inline bool powell_advance(PowellMachine &M, double fe, double xtol, double 
         case RS_INIT:
             M.fval = fe;
             M.x1[0] = M.x[0]; M.x1[1] = M.x[1];
-            M.state = RS_ITER_BEGIN;
-            break;
+            goto L_ITER_BEGIN;
         case RS_ITER_BEGIN:
+        L_ITER_BEGIN:
             M.fx = M.fval; M.bigind = 0; M.delta = 0.0;
             M.which = 0;
-            M.state = RS_LS_BEGIN;
-            break;
+            goto L_LS_BEGIN;
         case RS_LS_BEGIN:
+        L_LS_BEGIN:
             if (M.which == 0) { M.xi[0] = M.d0[0]; M.xi[1] = M.d0[1]; }
             else if (M.which == 1) { M.xi[0] = M.d1[0]; M.xi[1] = M.d1[1]; }
             /* which == 2: xi already holds the extrapolation direction */
             if (M.which < 2) M.fx2 = M.fval;
-            if (M.xi[0] == 0.0 && M.xi[1] == 0.0) { M.state = RS_AFTER_LS; break; }
+            if (M.xi[0] == 0.0 && M.xi[1] == 0.0) { goto L_AFTER_LS; }
             M.p[0] = M.x[0]; M.p[1] = M.x[1];
             M.xa = 0.0; M.xb = 1.0;
             pm_request_alpha(M, M.xa, RS_BR_FA);
@@ -225,10 +262,10 @@ HDN inline bool powell_advance(PowellMachine &M, double fe, double xtol, double 
         case RS_BR_FC:
             M.fc = fe;
             M.br_iter = 0;
-            M.state = RS_BR_LOOP;
-            break;
-        case RS_BR_LOOP: {
-            if (!(M.fc < M.fb)) { M.state = RS_BR_DONE; break; }
+            goto L_BR_LOOP;
+        case RS_BR_LOOP:
+        L_BR_LOOP: {
+            if (!(M.fc < M.fb)) { goto L_BR_DONE; }
             const double tmp1 = (M.xb - M.xa) * (M.fb - M.fc);
             const double tmp2 = (M.xb - M.xc) * (M.fb - M.fa);
             const double val = tmp2 - tmp1;
@@ -237,7 +274,7 @@ HDN inline bool powell_advance(PowellMachine &M, double fe, double xtol, double 
             else denom = 2.0 * val;
             M.w = M.xb - ((M.xb - M.xc) * tmp2 - (M.xb - M.xa) * tmp1) / denom;
             const double wlim = M.xb + grow_limit * (M.xc - M.xb);
-            if (M.br_iter > 1000) { M.state = RS_BR_DONE; break; }
+            if (M.br_iter > 1000) { goto L_BR_DONE; }
             M.br_iter += 1;
             if ((M.w - M.xc) * (M.xb - M.w) > 0.0) {
                 pm_request_alpha(M, M.w, RS_BR_A1);
@@ -256,10 +293,10 @@ HDN inline bool powell_advance(PowellMachine &M, double fe, double xtol, double 
             M.fw = fe;
             if (M.fw < M.fc) {
                 M.xa = M.xb; M.xb = M.w; M.fa = M.fb; M.fb = M.fw;
-                M.state = RS_BR_DONE; break;
+                goto L_BR_DONE;
             } else if (M.fw > M.fb) {
                 M.xc = M.w; M.fc = M.fw;
-                M.state = RS_BR_DONE; break;
+                goto L_BR_DONE;
             }
             M.w = M.xc + _gold * (M.xc - M.xb);
             pm_request_alpha(M, M.w, RS_BR_GEN);
@@ -274,15 +311,14 @@ HDN inline bool powell_advance(PowellMachine &M, double fe, double xtol, double 
             }
             M.xa = M.xb; M.xb = M.xc; M.xc = M.w;
             M.fa = M.fb; M.fb = M.fc; M.fc = M.fw;
-            M.state = RS_BR_LOOP;
-            break;
+            goto L_BR_LOOP;
         case RS_BR_GEN:
             M.fw = fe;
             M.xa = M.xb; M.xb = M.xc; M.xc = M.w;
             M.fa = M.fb; M.fb = M.fc; M.fc = M.fw;
-            M.state = RS_BR_LOOP;
-            break;
-        case RS_BR_DONE: {
+            goto L_BR_LOOP;
+        case RS_BR_DONE:
+        L_BR_DONE: {
             const bool cond1 = (M.fb < M.fc && M.fb <= M.fa) || (M.fb < M.fa && M.fb <= M.fc);
             const bool cond2 = (M.xa < M.xb && M.xb < M.xc) || (M.xc < M.xb && M.xb < M.xa);
             const bool cond3 = isfinite(M.xa) && isfinite(M.xb) && isfinite(M.xc);
@@ -294,25 +330,24 @@ HDN inline bool powell_advance(PowellMachine &M, double fe, double xtol, double 
                     if (M.fb < M.fret) { M.alpha_min = M.xb; M.fret = M.fb; }
                     if (M.fc < M.fret) { M.alpha_min = M.xc; M.fret = M.fc; }
                 }
-                M.state = RS_LS_FINISH;
-                break;
+                goto L_LS_FINISH;
             }
             M.bx = M.bw = M.bv = M.xb;
             M.bfw = M.bfv = M.bfx = M.fb;
             if (M.xa < M.xc) { M.a = M.xa; M.b = M.xc; } else { M.a = M.xc; M.b = M.xa; }
             M.deltax = 0.0; M.rat = 0.0;
             M.bt_iter = 0;
-            M.state = RS_BT_LOOP;
-            break;
+            goto L_BT_LOOP;
         }
-        case RS_BT_LOOP: {
-            if (!(M.bt_iter < 500)) { M.alpha_min = M.bx; M.fret = M.bfx; M.state = RS_LS_FINISH; break; }
+        case RS_BT_LOOP:
+        L_BT_LOOP: {
+            if (!(M.bt_iter < 500)) { M.alpha_min = M.bx; M.fret = M.bfx; goto L_LS_FINISH; }
             const double x = M.bx;
             const double tol1 = tol * fabs(x) + _mintol;
             const double tol2 = 2.0 * tol1;
             const double xmid = 0.5 * (M.a + M.b);
             if (fabs(x - xmid) < (tol2 - 0.5 * (M.b - M.a))) {
-                M.alpha_min = M.bx; M.fret = M.bfx; M.state = RS_LS_FINISH; break;
+                M.alpha_min = M.bx; M.fret = M.bfx; goto L_LS_FINISH;
             }
             if (fabs(M.deltax) <= tol1) {
                 if (x >= xmid) M.deltax = M.a - x; else M.deltax = M.b - x;
@@ -354,29 +389,29 @@ HDN inline bool powell_advance(PowellMachine &M, double fe, double xtol, double 
                 M.bfv = M.bfw; M.bfw = M.bfx; M.bfx = fu;
             }
             M.bt_iter += 1;
-            M.state = RS_BT_LOOP;
-            break;
+            goto L_BT_LOOP;
         }
         case RS_LS_FINISH:
+        L_LS_FINISH:
             M.xi[0] = M.alpha_min * M.xi[0]; M.xi[1] = M.alpha_min * M.xi[1];
             M.x[0] = M.p[0] + M.xi[0]; M.x[1] = M.p[1] + M.xi[1];
             M.fval = M.fret;
-            M.state = RS_AFTER_LS;
-            break;
+            goto L_AFTER_LS;
         case RS_AFTER_LS:
+        L_AFTER_LS:
             if (M.which < 2) {
                 if ((M.fx2 - M.fval) > M.delta) { M.delta = M.fx2 - M.fval; M.bigind = M.which; }
-                if (M.which == 0) { M.which = 1; M.state = RS_LS_BEGIN; }
-                else M.state = RS_ITER_END;
+                if (M.which == 0) { M.which = 1; goto L_LS_BEGIN; }
+                goto L_ITER_END;
             } else {
                 if (M.xi[0] != 0.0 || M.xi[1] != 0.0) {
                     if (M.bigind == 0) { M.d0[0] = M.d1[0]; M.d0[1] = M.d1[1]; }
                     M.d1[0] = M.xi[0]; M.d1[1] = M.xi[1];
                 }
-                M.state = RS_ITER_BEGIN;
+                goto L_ITER_BEGIN;
             }
-            break;
-        case RS_ITER_END: {
+        case RS_ITER_END:
+        L_ITER_END: {
             M.iter += 1;
             const double bnd = ftol * (fabs(M.fx) + fabs(M.fval)) + 1e-20;
             if (2.0 * (M.fx - M.fval) <= bnd) { M.state = RS_FINISHED; return false; }
@@ -400,9 +435,8 @@ HDN inline bool powell_advance(PowellMachine &M, double fe, double xtol, double 
                 t -= M.delta * temp * temp;
                 if (t < 0.0) again = true;
             }
-            if (again) { M.which = 2; M.state = RS_LS_BEGIN; }
-            else M.state = RS_ITER_BEGIN;
-            break;
+            if (again) { M.which = 2; goto L_LS_BEGIN; }
+            goto L_ITER_BEGIN;
         }
         default:
             return false;
@@ -418,40 +452,70 @@ HDN inline bool powell_advance(PowellMachine &M, double fe, double xtol, double 
 }
 
 // ---- one lateral column: sweep z from the top with warm start ------------------------------
-HDN inline void relax_column_body(const RelaxParams &P, long long col)
+template <int LAYOUT>
+HDN inline void relax_column_body(const RelaxParams &P, long long col, long long ncol)
 {
+    // Every lane of the warp stays in the loop until all of them are finished (lanes past the
+    // end of the tile start out finished), so the full-mask warp barrier below is legal.
+    bool done = col >= ncol;
     const int nj = P.j_hi - P.j_lo;
-    const int ci = (int)(col / nj), cj = (int)(col - (long long)ci * nj);
+    const long long c = done ? 0 : col;
+    const int ci = (int)(c / nj), cj = (int)(c - (long long)ci * nj);
     const int oi = P.i_lo + ci, oj = P.j_lo + cj;
-    const long long ncol = (long long)(P.i_hi - P.i_lo) * nj;
     PowellMachine M;
     M.x[0] = M_PI; M.x[1] = 0.0;
     int k = P.nz_relax - 1;
     int ok = (int)((double)k + P.npivot);                    // int64 store truncates
     M.state = RS_START;
     double fe = 0.0;
-    // One flat loop: a thread that finishes height k stores its row and immediately asks for
-    // the first value of height k-1, so the lanes of a warp stay together at the (expensive)
-    // objective evaluation instead of waiting for the slowest lane at every height.
     for (;;) {
-        if (powell_advance(M, fe, P.xtol, P.ftol, P.maxiter, P.maxfev)) {
-            fe = relax_objective(P, oi, oj, ok, M.ex[0], M.ex[1]);
-            continue;
+        // cheap, divergent part: advance this lane's optimiser until it needs a function value.
+        // Finishing a height stores its row and immediately starts the next one, so lanes do not
+        // wait for the slowest lane at every height.
+        while (!done && !powell_advance(M, fe, P.xtol, P.ftol, P.maxiter, P.maxfev)) {
+            const size_t o = (size_t)col * P.nz_relax + k;
+            P.out_etp[3 * o + 0] = M.fval;
+            P.out_etp[3 * o + 1] = M.x[0];
+            P.out_etp[3 * o + 2] = M.x[1];
+            if (P.out_nfev) P.out_nfev[o] = M.nfev;
+            if (--k < 0) { done = true; break; }
+            ok = (int)((double)k + P.npivot);
+            M.state = RS_START;
         }
-        const size_t o = (size_t)col * P.nz_relax + k;
-        P.out_etp[3 * o + 0] = M.fval;
-        P.out_etp[3 * o + 1] = M.x[0];
-        P.out_etp[3 * o + 2] = M.x[1];
-        if (P.out_cart) {
-            const double th = M.x[0], az = M.x[1];
-            const size_t plane = (size_t)ncol * P.nz_relax;
-            P.out_cart[o] = P.rpivot * sin(th) * cos(az);
-            P.out_cart[plane + o] = P.rpivot * sin(th) * sin(az);
-            P.out_cart[2 * plane + o] = P.rpivot * cos(th);
-        }
-        if (P.out_nfev) P.out_nfev[o] = M.nfev;
-        if (--k < 0) break;
-        ok = (int)((double)k + P.npivot);
-        M.state = RS_START;
+        // expensive part: re-converge the warp, then all unfinished lanes evaluate the 64-point
+        // stencil together (without the barrier the compiler threads the jump from each state
+        // straight into a private copy of the evaluation and the lanes run it one group at a time)
+        WARP_SYNC();
+        if (WARP_ALL(done)) break;
+        if (!done) fe = relax_objective<LAYOUT>(P, oi, oj, ok, M.ex[0], M.ex[1]);
+    }
+}
+
+// sph2cart of every relaxed position (dbspm:603-605), one converged pass instead of divergent
+// tail work inside the column loop
+HD void relax_cart_body(const double *etp, double *cart, long long npos, double rpivot, long long gid, long long gstride)
+{
+    for (long long o = gid; o < npos; o += gstride) {
+        const double th = etp[3 * o + 1], az = etp[3 * o + 2];
+        cart[o] = rpivot * sin(th) * cos(az);
+        cart[npos + o] = rpivot * sin(th) * sin(az);
+        cart[2 * npos + o] = rpivot * cos(th);
+    }
+}
+
+// (nx, ny, nz) -> (nx, nz, ny): 32x32 tiles through shared memory (tile[32][33]), one x-slab per blockIdx.z
+HD void transpose_yz_tile(const double *in, double *out, int ny, int nz, double *tile /* 32*33 */,
+                          int bx /* z tile */, int by /* y tile */, long long slab, int tx, int ty, int nty)
+{
+    const double *src = in + (size_t)slab * ny * nz;
+    double *dst = out + (size_t)slab * ny * nz;
+    for (int r = ty; r < 32; r += nty) {
+        const int y = by * 32 + r, z = bx * 32 + tx;
+        if (y < ny && z < nz) tile[r * 33 + tx] = src[(size_t)y * nz + z];
+    }
+    BLOCK_SYNC();
+    for (int r = ty; r < 32; r += nty) {
+        const int z = bx * 32 + r, y = by * 32 + tx;
+        if (y < ny && z < nz) dst[(size_t)z * ny + y] = tile[tx * 33 + r];
     }
 }

@@ -168,7 +168,7 @@ class TricubicField:
 
 
 def relax_grid(static, kappa, rpivot, dr, nz_relax, dR=None, tile=None, xtol=1e-4, ftol=1e-4,
-               maxfev=2000, method="Powell", want_nfev=False, device=None):
+               maxfev=2000, method="Powell", want_nfev=False, device=None, coalesce=True):
     """Relax the probe at every (i, j, k) of a lateral tile (default: the whole window).
 
     static: (Nx,Ny,Nzc) window potential (numpy, CUDA tensor or TricubicField).
@@ -192,11 +192,19 @@ def relax_grid(static, kappa, rpivot, dr, nz_relax, dR=None, tile=None, xtol=1e-
     dR9 = None
     if dR is not None:
         dR9 = (C.c_double * 9)(*[float(v) for v in np.asarray(dR, dtype=np.float64).reshape(9)])
-    with torch.cuda.device(dev):
-        _lib.check(_lib.lib().dbspm_relax_powell_f64(
-            field.data.data_ptr(), nx, ny, nzc, i_lo, i_hi, j_lo, j_hi, nz, float(kappa), float(rpivot),
-            dr3, dR9, float(xtol), float(ftol), int(maxfev), etp.data_ptr(), cart.data_ptr(),
-            nfev.data_ptr() if nfev is not None else None, _stream_ptr(dev)))
+    if not (0 <= i_lo <= i_hi <= nx and 0 <= j_lo <= j_hi <= ny):
+        raise ValueError(f"tile {(i_lo, i_hi, j_lo, j_hi)} outside the {nx}x{ny} lateral grid")
+    if etp.numel() > 0:                     # an empty tile (a rank with no columns) launches nothing
+        with torch.cuda.device(dev):
+            # y-fastest copy of the potential (coalesced stencil loads); single columns read in place
+            ws = None
+            if coalesce and ni * nj >= 1024:
+                ws = torch.empty(_lib.lib().dbspm_relax_workspace_bytes(nx, ny, nzc), dtype=torch.uint8, device=dev)
+            _lib.check(_lib.lib().dbspm_relax_powell_f64(
+                field.data.data_ptr(), nx, ny, nzc, i_lo, i_hi, j_lo, j_hi, nz, float(kappa), float(rpivot),
+                dr3, dR9, float(xtol), float(ftol), int(maxfev), etp.data_ptr(), cart.data_ptr(),
+                nfev.data_ptr() if nfev is not None else None,
+                ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, _stream_ptr(dev)))
     res = {"E": etp[..., 0], "theta": etp[..., 1], "phi": etp[..., 2],
            "tip_x": cart[0], "tip_y": cart[1], "tip_z": cart[2]}
     if want_nfev:

@@ -145,8 +145,9 @@ def make_tip(cfg: Config, device="cpu", variant="noisy"):
         t = torch.clamp(rmin / rc, max=1.0)
         rho = rho * (1 - t * t) ** 2          # C^1 at the cutoff, exact zero beyond it
     elif variant == "noisy":
-        g = torch.Generator(device="cpu").manual_seed(cfg.seed + 7)
-        noise = torch.rand(cfg.shape, dtype=torch.float64, generator=g).to(device)
+        gdev = device if torch.device(device).type == "cuda" else "cpu"   # big grids: draw on the GPU
+        g = torch.Generator(device=gdev).manual_seed(cfg.seed + 7)
+        noise = torch.rand(cfg.shape, dtype=torch.float64, generator=g, device=gdev)
         rho = rho + 1e-7 * float(rho.max()) * noise
     else:
         raise ValueError(variant)

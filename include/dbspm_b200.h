@@ -45,6 +45,7 @@ extern "C" {
 
 /* flags for dbspm_corr3d_f64 */
 #define DBSPM_CORR_DEFAULT    0
+#define DBSPM_CORR_AXIS_V1    (1 << 1)   /* force the all-in-shared-memory axis pass (A/B timing) */
 /* profiling aid: skip stages (results are then meaningless); bench.py times each launch alone */
 #define DBSPM_CORR_SKIP_XFWD  (1 << 8)
 #define DBSPM_CORR_SKIP_YFWD  (1 << 9)
@@ -79,12 +80,17 @@ int dbspm_static_accumulate_f64(double *acc, const double *comp, double scale, s
  * inv(dR^T).(x,y,z); NULL selects the orthogonal path.
  * out_E_theta_phi: (ni,nj,nz_relax,3) rows [E_min, theta, phi]
  * out_cart:        (3,ni,nj,nz_relax) tip_x, tip_y, tip_z = sph2cart(theta, phi, rpivot); nullable
- * out_nfev:        (ni,nj,nz_relax) objective evaluations per position; nullable            */
+ * out_nfev:        (ni,nj,nz_relax) objective evaluations per position; nullable
 int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
                            int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
                            double kappa, double rpivot, const double dr[3], const double *dR,
                            double xtol, double ftol, int maxfev,
-                           double *out_E_theta_phi, double *out_cart, int *out_nfev, void *stream);
+                           double *out_E_theta_phi, double *out_cart, int *out_nfev,
+                           void *workspace, size_t workspace_bytes, void *stream);
+/* workspace (nullable): dbspm_relax_workspace_bytes(nx,ny,nzc) bytes, 16-byte aligned.  With it the
+ * potential is re-laid with y fastest so a warp's loads coalesce (about 2x faster); without it the
+ * kernel reads static_win in place.  Results are identical either way.                              */
+size_t dbspm_relax_workspace_bytes(int nx, int ny, int nzc);
 
 /* ---- tricubic gather: out[p] = interp(data)(pts[p,0], pts[p,1], pts[p,2]), index units ---- */
 int dbspm_tricubic_gather_f64(const double *data, int nx, int ny, int nz,

@@ -33,7 +33,8 @@ def main():
         balg = 8 * (2 * N + nx * ny * (zhi - zlo))
         t_es = timeit(lambda: ops.density_overlap_window(A, B, dr, zlo, zhi, out=out))
         t_sr = timeit(lambda: ops.density_overlap_window(A, B, dr, zlo, zhi, 1.08, 1.08, out=out))
-        line = f"{name}: es {t_es:.3f} ms ({balg/t_es/1e6:.0f} GB/s alg) sr {t_sr:.3f} ms ({balg/t_sr/1e6:.0f} GB/s alg) |"
+        t_v1 = timeit(lambda: ops.density_overlap_window(A, B, dr, zlo, zhi, out=out, flags=2))
+        line = f"{name}: es {t_es:.3f} ms ({balg/t_es/1e6:.0f} GB/s alg) [axis v1: {t_v1:.3f}] sr {t_sr:.3f} ms ({balg/t_sr/1e6:.0f} GB/s alg) |"
         for k, bit in SKIP.items():
             t = timeit(lambda: ops.density_overlap_window(A, B, dr, zlo, zhi, out=out, flags=ALL & ~bit))
             line += f" {k} {t:.3f}"

@@ -49,7 +49,7 @@ class Emu:
         L.emu_fft_lines.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int]
         L.emu_relax_powell_f64.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_int, C.c_double, C.c_double, _dp, _dp, C.c_double, C.c_double,
-                                           C.c_int, _dp, _dp, _ip]
+                                           C.c_int, _dp, _dp, _ip, C.c_int]
         L.emu_tricubic.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
         L.emu_tricubic.restype = C.c_double
         self.L = L
@@ -79,7 +79,7 @@ class Emu:
             raise RuntimeError(f"emu_fft_lines -> {rc}")
         return out.view(np.complex128).reshape(n, T)
 
-    def relax(self, s, tile, nz, kappa, rpivot, dr, dR=None, maxfev=2000, xtol=1e-4, ftol=1e-4):
+    def relax(self, s, tile, nz, kappa, rpivot, dr, dR=None, maxfev=2000, xtol=1e-4, ftol=1e-4, transposed=0):
         s = np.ascontiguousarray(s, dtype=np.float64)
         nx, ny, nzc = s.shape
         i_lo, i_hi, j_lo, j_hi = tile
@@ -91,7 +91,7 @@ class Emu:
         dRv = None if dR is None else np.ascontiguousarray(dR, dtype=np.float64).reshape(9)
         rc = self.L.emu_relax_powell_f64(self._p(s), nx, ny, nzc, i_lo, i_hi, j_lo, j_hi, nz, kappa, rpivot,
                                          self._p(drv), None if dRv is None else self._p(dRv), xtol, ftol, maxfev,
-                                         self._p(etp), self._p(cart), nfev.ctypes.data_as(_ip))
+                                         self._p(etp), self._p(cart), nfev.ctypes.data_as(_ip), transposed)
         if rc:
             raise RuntimeError(f"emu_relax_powell_f64 -> {rc}")
         return etp, cart, nfev

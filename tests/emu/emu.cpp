@@ -37,13 +37,28 @@ static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, in
     P.in[0] = in0; P.in[1] = in1; P.out[0] = out0; P.out[1] = out1;
     P.alpha[0] = a0; P.alpha[1] = a1; P.use_pow = use_pow; P.narrays = narrays;
     P.n = n; P.inner = inner; P.outer = outer;
-    P.tshift = force_tshift >= 0 ? force_tshift : pick_tshift(n, inner);
+    P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data(); P.freq_of = hp.freq_of.data();
+    // same selection as launch_axis() in corr3d.cu; force_tshift >= 100 selects the v1 body
+    P.v2 = axis_v2_ok(P.plan) && force_tshift < 100;
+    P.tw_smem = 0;
+    if (force_tshift >= 100) force_tshift -= 101;
+    size_t bytes;
+    if (P.v2) {
+        axis2_config(n, inner, P.plan.nstages, &P.tshift, &P.tw_smem);
+        if (force_tshift >= 0) { P.tshift = force_tshift; P.tw_smem = force_tshift & 1; }
+        bytes = axis2_smem_bytes(n, P.tshift, P.plan.nstages, P.tw_smem);
+    } else {
+        P.tshift = force_tshift >= 0 ? force_tshift : pick_tshift(n, inner);
+        bytes = axis_smem_bytes(n, P.tshift);
+    }
     P.tiles = (inner + (1LL << P.tshift) - 1) >> P.tshift;
-    P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data();
-    std::vector<unsigned char> smem(axis_smem_bytes(n, P.tshift) + 64);
+    std::vector<unsigned char> smem(bytes + 64);
     unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
     for (int w = 0; w < narrays; ++w)
-        for (long long b = 0; b < outer * P.tiles; ++b) axis_pass_body<D>(P, sm, b, w, 0, 1);
+        for (long long b = 0; b < outer * P.tiles; ++b) {
+            if (P.v2) axis_pass_body_v2<D>(P, sm, b, w, 0, 1);
+            else axis_pass_body<D>(P, sm, b, w, 0, 1);
+        }
     return 0;
 }
 
@@ -77,9 +92,12 @@ extern "C" int emu_corr3d_f64(const double *A, const double *B, double alphaA, d
         P.scale = dV / ((double)nx * (double)ny * (double)nz) * 0.25;
         P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data(); P.twN = hpN.tw.data();
         P.npairs = (long long)(nx / 2 + 1) * ny;
-        std::vector<unsigned char> smem(zfused_smem_bytes(n) + 64);
+        // same selection as dbspm_corr3d_f64: v2 (4 pairs / block) when the plan is all fast radices
+        const bool v2 = axis_v2_ok(P.plan) && force_tshift < 100;
+        std::vector<unsigned char> smem((v2 ? zfused2_smem_bytes<4>(n) : zfused_smem_bytes(n)) + 64);
         unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
-        for (long long b = 0; b < (P.npairs + ZL - 1) / ZL; ++b) zfused_body(P, sm, b, 0, 1);
+        if (v2) for (long long b = 0; b < (P.npairs + 3) / 4; ++b) zfused_body_v2<4>(P, sm, b, 0, 1);
+        else for (long long b = 0; b < (P.npairs + ZL - 1) / ZL; ++b) zfused_body(P, sm, b, 0, 1);
     }
     if ((rc = run_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, force_tshift))) return rc;
     if ((rc = run_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)ny * nwh, 1, force_tshift))) return rc;
@@ -118,13 +136,14 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
                                     int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
                                     double kappa, double rpivot, const double dr[3], const double *dR,
                                     double xtol, double ftol, int maxfev,
-                                    double *out_etp, double *out_cart, int *out_nfev)
+                                    double *out_etp, double *out_cart, int *out_nfev, int transposed)
 {
     RelaxParams P;
     P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc;
     P.i_lo = i_lo; P.i_hi = i_hi; P.j_lo = j_lo; P.j_hi = j_hi; P.nz_relax = nz_relax;
     P.kappa = kappa; P.rpivot = rpivot; P.npivot = rpivot / dr[2]; P.rpivot_rt = P.npivot * dr[2];
     P.dr[0] = dr[0]; P.dr[1] = dr[1]; P.dr[2] = dr[2];
+    P.inv_n[0] = 1.0 / nx; P.inv_n[1] = 1.0 / ny; P.inv_n[2] = 1.0 / nzc;
     P.noortho = dR != nullptr;
     for (int q = 0; q < 9; ++q) P.Minv[q] = 0.0;
     if (dR) {
@@ -134,11 +153,39 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
     P.xtol = xtol; P.ftol = ftol; P.maxfev = maxfev; P.maxiter = 2000;
     P.out_etp = out_etp; P.out_cart = out_cart; P.out_nfev = out_nfev;
     const long long ncol = (long long)(i_hi - i_lo) * (j_hi - j_lo);
-    for (long long c = 0; c < ncol; ++c) relax_column_body(P, c);
+    std::vector<double> tr;
+    if (transposed) {
+        // what transpose_yz_kernel does, block by block (blockDim = 32 x 8 emulated as tx loop, ty = 0, nty = 1)
+        tr.resize((size_t)nx * ny * nzc);
+        std::vector<double> tile(32 * 33);
+        for (int x = 0; x < nx; ++x)
+            for (int by = 0; by < (ny + 31) / 32; ++by)
+                for (int bx = 0; bx < (nzc + 31) / 32; ++bx) {
+                    // two phases separated by the block barrier: emulate each phase over all tx
+                    const double *src = static_win + (size_t)x * ny * nzc;
+                    for (int tx = 0; tx < 32; ++tx)
+                        for (int r = 0; r < 32; ++r) {
+                            const int y = by * 32 + r, z = bx * 32 + tx;
+                            if (y < ny && z < nzc) tile[r * 33 + tx] = src[(size_t)y * nzc + z];
+                        }
+                    double *dst = tr.data() + (size_t)x * ny * nzc;
+                    for (int tx = 0; tx < 32; ++tx)
+                        for (int r = 0; r < 32; ++r) {
+                            const int z = bx * 32 + r, y = by * 32 + tx;
+                            if (y < ny && z < nzc) dst[(size_t)z * ny + y] = tile[tx * 33 + r];
+                        }
+                }
+        P.grid = tr.data();
+        for (long long c = 0; c < ncol; ++c) relax_column_body<1>(P, c, ncol);
+    } else {
+        for (long long c = 0; c < ncol; ++c) relax_column_body<0>(P, c, ncol);
+    }
+    if (out_cart) relax_cart_body(out_etp, out_cart, ncol * nz_relax, rpivot, 0, 1);
     return 0;
 }
 
 extern "C" double emu_tricubic(const double *g, int nx, int ny, int nz, double x, double y, double z)
 {
-    return tricubic_eval(g, nx, ny, nz, x, y, z);
+    const double inv_n[3] = {1.0 / nx, 1.0 / ny, 1.0 / nz};
+    return tricubic_eval<0>(g, nx, ny, nz, inv_n, x, y, z);
 }

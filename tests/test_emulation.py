@@ -49,7 +49,8 @@ def test_corr3d_edge_shapes_all_tile_widths(emu, shape, window):
     a, b = rng.random(shape), rng.random(shape) - 0.4
     dr = np.array([0.1, 0.2, 0.3])
     ref = O.density_overlap_fft(a, b, dr)[:, :, window[0]:window[1]]
-    for tshift in (-1, 0, 1, 2):
+    # -1/0/1/2: register-first/last body with auto/forced tile width; 100+: the all-in-smem body
+    for tshift in (-1, 0, 1, 2, 100, 101, 103):
         got = emu.corr3d(a, b, dr, *window, tshift=tshift)
         assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, window, tshift)
 
@@ -124,6 +125,19 @@ def test_relax_tile_against_oracle_with_outlier_budget(emu, relax_golden):
     r2, n2 = O.relax_tile(static, 2, 6, 2, 6, 24, 0.2, 3.02, dr, maxfev=17, want_nfev=True)
     e2, _, m2 = emu.relax(static, (2, 6, 2, 6), 24, 0.2, 3.02, dr, maxfev=17)
     assert np.array_equal(n2, m2) and np.abs(e2[..., 0] - r2[..., 0]).max() < 1e-9
+
+
+def test_relax_transposed_layout_is_bit_identical(emu, relax_golden):
+    """The y-fastest copy of the potential (coalesced loads on the GPU) must not change a bit."""
+    static, dr = relax_golden["static"], relax_golden["dr"]
+    a = emu.relax(static, (0, 24, 0, 20), 8, 0.2, 3.02, dr)
+    b = emu.relax(static, (0, 24, 0, 20), 8, 0.2, 3.02, dr, transposed=1)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+    odd = np.ascontiguousarray(static[:23, :19, :37])            # tile edges of the 32x32 transpose
+    a = emu.relax(odd, (3, 9, 2, 17), 5, 0.2, 3.02, dr)
+    b = emu.relax(odd, (3, 9, 2, 17), 5, 0.2, 3.02, dr, transposed=1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
 
 
 def test_relax_empty_tile_and_periodic_wrap(emu, relax_golden):
