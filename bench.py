@@ -198,6 +198,7 @@ def run_gpu_arm(args):
     from dbspm_b200.input_parser import default_params
     from argparse import Namespace
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("DBSPM_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
     rank, world, dev = parallel.init_from_env()
     assert dev.type == "cuda", "bench.py needs a GPU (use --impl reference for the CPU arm)"
     if world != args.gpus and rank == 0:

@@ -189,7 +189,7 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
         P.ZA = WA; P.ZB = WB; P.W = W;
         P.nx = nx; P.ny = ny; P.n = n; P.nwh = nwh; P.z_lo = z_lo;
         P.scale = dV / ((double)nx * (double)ny * (double)nz) * 0.25;
-        P.plan = pl->host.dev; P.tw = pl->tw; P.pos_of = pl->pos_of; P.twN = plN->tw;
+        P.plan = pl->host.dev; P.tw = pl->tw; P.pos_of = pl->pos_of; P.freq_of = pl->freq_of; P.twN = plN->tw;
         P.npairs = (long long)(nx / 2 + 1) * ny;
         const bool v2 = axis_v2_ok(P.plan) && zfused2_smem_bytes<ZF2_PAIRS>(n) <= 113 * 1024 &&
                         !(flags & DBSPM_CORR_AXIS_V1);
@@ -198,6 +198,7 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
             const size_t smem = zfused2_smem_bytes<ZF2_PAIRS>(n);
             DBSPM_REQUIRE(nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large");
             DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             zfused2_kernel<<<(unsigned)nblocks, ZF2_THREADS, smem, st>>>(P);
         } else {
             const long long nblocks = (P.npairs + ZL - 1) / ZL;
@@ -205,6 +206,7 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
             DBSPM_REQUIRE(smem <= 227 * 1024, DBSPM_EUNSUPPORTED, "nz=%d too long for the fused z kernel", nz);
             DBSPM_REQUIRE(nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large");
             DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             zfused_kernel<<<(unsigned)nblocks, DBSPM_THREADS, smem, st>>>(P);
         }
         DBSPM_CUDA_TRY(cudaGetLastError());

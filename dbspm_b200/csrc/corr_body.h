@@ -286,7 +286,8 @@ struct ZFusedParams {
     double scale;             // dV / (nx*ny*nz) / 4
     FftPlanDev plan;          // length n
     const cplx *tw;           // length-n table
-    const int *pos_of;        // length n
+    const int *pos_of;        // length n: frequency -> tile row
+    const int *freq_of;       // length n: tile row -> frequency
     const cplx *twN;          // length-2n table: twN[e] = exp(-2 pi i e / nz)
     long long npairs;         // (nx/2+1) * ny candidate pairs
 };
@@ -411,7 +412,7 @@ HD void zfused_body(const ZFusedParams &P, unsigned char *smem_raw, long long bi
 // ------------------------------------------------------------------------------------------
 template <int ZLV> HD size_t zfused2_smem_bytes(int n)
 {
-    return (size_t)n * 16 * 2 + (size_t)n * (4 * ZLV + 1) * 16 + (size_t)n * (2 * ZLV + 1) * 16 + (size_t)n * 4 + ZLV * 6 * 4 + 16;
+    return (size_t)n * 16 * 2 + (size_t)n * (4 * ZLV + 1) * 16 + (size_t)n * (2 * ZLV + 1) * 16 + (size_t)n * 8 + ZLV * 6 * 4 + 16;
 }
 
 template <int D, int R, int ZLV>
@@ -481,12 +482,14 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
     cplx *U = twh + n;
     cplx *S = U + (size_t)n * LDF;
     int *pos_of = (int *)(S + (size_t)n * LDI);
-    int *pinfo = pos_of + n;                  // per pair: kx, ky, mx, my, valid, self
+    int *freq_of = pos_of + n;
+    int *pinfo = freq_of + n;                 // per pair: kx, ky, mx, my, valid, self
 
     for (int e = tid; e < n; e += nthr) {
         tw[e] = ldg_c(P.tw + e);
         twh[e] = ldg_c(P.twN + e);
         pos_of[e] = LDG(P.pos_of + e);
+        freq_of[e] = LDG(P.freq_of + e);
     }
     for (int l = tid; l < ZLV; l += nthr) {
         const ZPair z = zpair_of(P, bid * ZLV + l);
@@ -506,47 +509,41 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
     BLOCK_SYNC();
     fft_stages_from<-1>(U, LDF, TSF, P.plan, 1, tw, tid, nthr);
 
-    const int nk = n / 2 + 1;
+    // pointwise stage in POSITION order: one work item = (pair l, tile row p) owns frequency
+    // k = freq_of[p].  Consecutive threads read consecutive rows (bank-conflict free); only the
+    // mirror frequency k* = (n-k)%n lives in a scattered row.  It writes S_p at its own row and
+    // S_m at the mirror row, i.e. the inverse tile holds the spectra in the same permuted order
+    // and the inverse transform runs the transposed (decimation-in-time) stages.
     const double sgn = (P.z_lo & 1) ? -1.0 : 1.0;
     const long long N2 = 2LL * n;
-    for (int idx = tid; idx < nk * ZLV; idx += nthr) {
-        const int l = idx / nk, k = idx - l * nk;
+    for (int idx = tid; idx < n * ZLV; idx += nthr) {
+        const int l = idx / n, p = idx - l * n;
+        const int k = freq_of[p];
         const int ks = k == 0 ? 0 : n - k;
-        if (k > ks) continue;
-        const cplx *Uk = U + (size_t)pos_of[k] * LDF + 4 * l;
-        const cplx *Us = U + (size_t)pos_of[ks] * LDF + 4 * l;
-        cplx G1[2], G2[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int kk = h == 0 ? k : ks;
-            const cplx *Ua = h == 0 ? Uk : Us, *Ub = h == 0 ? Us : Uk;
-            const cplx w = twh[kk];
-            const cplx miw = cmake(w.y, -w.x);
-            cplx a1 = Ua[0], a2 = cconj(Ub[1]);
-            cplx b1 = Ua[2], b2 = cconj(Ub[3]);
-            cplx ea = cadd(a1, a2), ta = cmul(miw, csub(a1, a2));
-            cplx eb = cadd(b1, b2), tb = cmul(miw, csub(b1, b2));
-            cplx alo = cadd(ea, ta), ahi = csub(ea, ta);
-            cplx blo = cadd(eb, tb), bhi = csub(eb, tb);
-            cplx plo = cscale(cmulc(alo, blo), P.scale);
-            cplx phi = cscale(cmulc(ahi, bhi), P.scale * sgn);
-            const cplx ph = cconj(ldg_c(P.twN + (int)(((long long)kk * P.z_lo) % N2)));
-            plo = cmul(plo, ph);
-            phi = cmul(phi, ph);
-            G1[h] = cadd(plo, phi);
-            G2[h] = cmulc(csub(plo, phi), w);
-        }
-        cplx *Sk = S + (size_t)k * LDI + 2 * l;
-        cplx *Ss = S + (size_t)ks * LDI + 2 * l;
-        Sk[0] = cmake(G1[0].x - G2[0].y, G1[0].y + G2[0].x);
-        Sk[1] = cmake(G1[1].x + G2[1].y, -G1[1].y + G2[1].x);
-        if (ks != k) {
-            Ss[0] = cmake(G1[1].x - G2[1].y, G1[1].y + G2[1].x);
-            Ss[1] = cmake(G1[0].x + G2[0].y, -G1[0].y + G2[0].x);
-        }
+        const int ps = pos_of[ks];
+        const cplx *Uk = U + (size_t)p * LDF + 4 * l;
+        const cplx *Us = U + (size_t)ps * LDF + 4 * l;
+        const cplx w = twh[k];                                    // exp(-2 pi i k / nz)
+        const cplx miw = cmake(w.y, -w.x);                        // -i * w
+        const cplx a1 = Uk[0], a2 = cconj(Us[1]);
+        const cplx b1 = Uk[2], b2 = cconj(Us[3]);
+        const cplx ea = cadd(a1, a2), ta = cmul(miw, csub(a1, a2));
+        const cplx eb = cadd(b1, b2), tb = cmul(miw, csub(b1, b2));
+        const cplx alo = cadd(ea, ta), ahi = csub(ea, ta);        // 2*A^[k], 2*A^[k+n]
+        const cplx blo = cadd(eb, tb), bhi = csub(eb, tb);
+        cplx plo = cscale(cmulc(alo, blo), P.scale);
+        cplx phi = cscale(cmulc(ahi, bhi), P.scale * sgn);
+        const cplx ph = cconj(ldg_c(P.twN + (int)(((long long)k * P.z_lo) % N2)));   // e^{+2 pi i k z_lo / nz}
+        plo = cmul(plo, ph);
+        phi = cmul(phi, ph);
+        const cplx G1 = cadd(plo, phi);
+        const cplx G2 = cmulc(csub(plo, phi), w);                 // * e^{+2 pi i k / nz}
+        // S_p[k] = G1 + i G2 ; S_m[k*] = conj(G1[k]) + i conj(G2[k])
+        S[(size_t)p * LDI + 2 * l] = cmake(G1.x - G2.y, G1.y + G2.x);
+        S[(size_t)ps * LDI + 2 * l + 1] = cmake(G1.x + G2.y, -G1.y + G2.x);
     }
     BLOCK_SYNC();
-    fft_stages_from<1>(S, LDI, TSI, P.plan, 0, tw, tid, nthr);
+    fft_tile_t<1>(S, LDI, TSI, P.plan, tw, tid, nthr);
 
     for (int idx = tid; idx < P.nwh * TI; idx += nthr) {
         const int line = idx / P.nwh, j = idx - line * P.nwh;
@@ -554,7 +551,7 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
         const int *pi = pinfo + 6 * l;
         if (!pi[4] || (role == 1 && pi[5])) continue;
         const int x = role ? pi[2] : pi[0], y = role ? pi[3] : pi[1];
-        st_stream(P.W + ((size_t)x * P.ny + y) * P.nwh + j, S[(size_t)pos_of[j] * LDI + line]);
+        st_stream(P.W + ((size_t)x * P.ny + y) * P.nwh + j, S[(size_t)j * LDI + line]);
     }
 }
 

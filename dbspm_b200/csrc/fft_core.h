@@ -216,6 +216,64 @@ HD void fft_stage_generic(cplx *s, int ld, int tshift, int n, int m, int r, cons
     }
 }
 
+// ---- transposed stage (decimation in time): twiddle first, then butterfly ----------------------
+// The DFT matrix is symmetric, so running the transposes of the DIF stages in reverse order maps
+// an input stored in the DIF *output* order (value of frequency K at position pos_of[K]) to the
+// transform in natural order.  Used for the inverse z transform: the spectrum never has to be
+// un-permuted between the forward and the inverse FFT.
+template <int R, int D>
+HD void fft_stage_t(cplx *s, int ld, int tshift, int n, int m, const cplx *tw, int tid, int nthr)
+{
+    const int q = m / R;
+    const int nb = n / R;
+    const int twstride = n / m;
+    const int tmask = (1 << tshift) - 1;
+    const int total = nb << tshift;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int t = idx & tmask;
+        const int b = idx >> tshift;
+        const int blk = b / q;
+        const int j = b - blk * q;
+        cplx *p = s + (size_t)(blk * m + j) * ld + t;
+        const size_t step = (size_t)q * ld;
+        cplx v[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = p[k * step];
+        if (q > 1) {
+            const int e1 = j * twstride;
+#pragma unroll
+            for (int k = 1; k < R; ++k) {
+                cplx w = tw[e1 * k];
+                v[k] = D < 0 ? cmul(v[k], w) : cmulc(v[k], w);
+            }
+        }
+        bfly<R, D>(v);
+#pragma unroll
+        for (int k = 0; k < R; ++k) p[k * step] = v[k];
+    }
+}
+
+// all stages, last to first; fast radices only (callers check the plan)
+template <int D>
+HD void fft_tile_t(cplx *s, int ld, int tshift, const FftPlanDev &pl, const cplx *tw, int tid, int nthr)
+{
+    int m = 1;
+    for (int st = pl.nstages - 1; st >= 0; --st) {
+        const int r = pl.radix[st];
+        m *= r;
+        switch (r) {
+        case 2: fft_stage_t<2, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 3: fft_stage_t<3, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 4: fft_stage_t<4, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 5: fft_stage_t<5, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 7: fft_stage_t<7, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 8: fft_stage_t<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        default: fft_stage_t<16, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        }
+        BLOCK_SYNC();
+    }
+}
+
 // ---- whole transform; caller guarantees a BLOCK_SYNC() before entry, one is issued after
 // every stage (so the tile is consistent on return) ----------------------------------------
 template <int D>

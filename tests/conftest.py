@@ -47,6 +47,7 @@ class Emu:
         L.emu_corr3d_f64.argtypes = [_dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, _dp, C.c_int]
         L.emu_fft_lines.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int]
+        L.emu_fft_lines_t.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int]
         L.emu_relax_powell_f64.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_int, C.c_double, C.c_double, _dp, _dp, C.c_double, C.c_double,
                                            C.c_int, _dp, _dp, _ip, C.c_int]
@@ -70,11 +71,12 @@ class Emu:
             raise RuntimeError(f"emu_corr3d_f64 -> {rc}")
         return out
 
-    def fft_lines(self, x, direction, tshift):
+    def fft_lines(self, x, direction, tshift, transposed=False):
         n, T = x.shape
         xin = np.ascontiguousarray(x.astype(np.complex128)).view(np.float64)
         out = np.empty_like(xin)
-        rc = self.L.emu_fft_lines(self._p(xin), self._p(out), n, tshift, direction)
+        fn = self.L.emu_fft_lines_t if transposed else self.L.emu_fft_lines
+        rc = fn(self._p(xin), self._p(out), n, tshift, direction)
         if rc < 0:
             raise RuntimeError(f"emu_fft_lines -> {rc}")
         return out.view(np.complex128).reshape(n, T)

@@ -90,7 +90,7 @@ extern "C" int emu_corr3d_f64(const double *A, const double *B, double alphaA, d
         P.ZA = WA.data(); P.ZB = WB.data(); P.W = W;
         P.nx = nx; P.ny = ny; P.n = n; P.nwh = nwh; P.z_lo = z_lo;
         P.scale = dV / ((double)nx * (double)ny * (double)nz) * 0.25;
-        P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data(); P.twN = hpN.tw.data();
+        P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data(); P.freq_of = hp.freq_of.data(); P.twN = hpN.tw.data();
         P.npairs = (long long)(nx / 2 + 1) * ny;
         // same selection as dbspm_corr3d_f64: v2 (4 pairs / block) when the plan is all fast radices
         const bool v2 = axis_v2_ok(P.plan) && force_tshift < 100;
@@ -118,6 +118,22 @@ extern "C" int emu_fft_lines(const double *in, double *out, int n, int tshift, i
     cplx *o = (cplx *)out;
     for (int K = 0; K < n; ++K)
         for (int t = 0; t < T; ++t) o[(size_t)K * T + t] = s[(size_t)hp.pos_of[K] * T + t];
+    return hp.dev.nstages;
+}
+
+// transposed (decimation-in-time) stages: natural input is placed in DIF output order first
+extern "C" int emu_fft_lines_t(const double *in, double *out, int n, int tshift, int dir)
+{
+    HostPlan hp;
+    if (!dbspm_make_plan(n, hp) || !axis_v2_ok(hp.dev)) return -2;
+    const int T = 1 << tshift;
+    std::vector<cplx> s((size_t)n * T);
+    const cplx *u = (const cplx *)in;
+    for (int p = 0; p < n; ++p)
+        for (int t = 0; t < T; ++t) s[(size_t)p * T + t] = u[(size_t)hp.freq_of[p] * T + t];
+    if (dir < 0) fft_tile_t<-1>(s.data(), T, tshift, hp.dev, hp.tw.data(), 0, 1);
+    else fft_tile_t<1>(s.data(), T, tshift, hp.dev, hp.tw.data(), 0, 1);
+    memcpy(out, s.data(), sizeof(cplx) * s.size());
     return hp.dev.nstages;
 }
 

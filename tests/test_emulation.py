@@ -10,6 +10,16 @@ LENGTHS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 20, 21, 27, 28, 30, 32
            128, 160, 196, 240, 256, 320, 384, 512, 1024, 11, 13, 22, 26, 33, 62, 169]
 
 
+def _factors(n):
+    out, p = [], 2
+    while n > 1:
+        while n % p == 0:
+            out.append(p)
+            n //= p
+        p += 1
+    return out
+
+
 @pytest.mark.parametrize("n", LENGTHS)
 def test_tile_fft_matches_numpy(emu, n):
     rng = np.random.default_rng(n)
@@ -20,6 +30,12 @@ def test_tile_fft_matches_numpy(emu, n):
         scale = max(1.0, np.abs(np.fft.fft(x, axis=0)).max())
         assert np.abs(fwd - np.fft.fft(x, axis=0)).max() < 2e-14 * scale * max(1, np.log2(n + 1))
         assert np.abs(inv - np.fft.ifft(x, axis=0) * n).max() < 2e-14 * scale * max(1, np.log2(n + 1))
+        if all(f in (2, 3, 5, 7) for f in _factors(n)) and n > 1:
+            # transposed (decimation-in-time) stages: permuted input -> natural output
+            fwd_t = emu.fft_lines(x, -1, tshift, transposed=True)
+            inv_t = emu.fft_lines(x, +1, tshift, transposed=True)
+            assert np.abs(fwd_t - np.fft.fft(x, axis=0)).max() < 2e-14 * scale * max(1, np.log2(n + 1))
+            assert np.abs(inv_t - np.fft.ifft(x, axis=0) * n).max() < 2e-14 * scale * max(1, np.log2(n + 1))
 
 
 def test_unsupported_length_is_reported(emu):
