@@ -44,6 +44,16 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled_traffic(workload):
+    """DRAM bytes (read + write) of one interaction's five launches from the committed ncu
+    capture (profiles/traffic.json); None when that workload has not been profiled."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return float(json.load(fh)[workload]["total_per_interaction"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -395,7 +405,9 @@ def run_gpu_arm(args):
     t_corr = t_sr + t_es
     achieved = 2 * balg / (t_corr * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak / world,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": (2 * profiled_traffic(args.workload) if world == 1 and profiled_traffic(args.workload) else None),
+            "traffic_note": "dram bytes read+write of sr+es (2 x 5 launches), ncu --set full, profiles/traffic.json",
+            "peak_source": peak_src,
             "kernel": "dbspm_corr3d_f64 = 5 launches (axis_pass x_fwd, y_fwd, zfused, axis_pass y_inv, x_inv)",
             "algorithmic_bytes_per_interaction": balg, "ms_sr": t_sr, "ms_es": t_es,
             "note": "frac = algorithmic bytes of sr+es / (time * n_gpus * peak); es alone: %.4f of peak"

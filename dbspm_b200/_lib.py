@@ -41,6 +41,7 @@ _SIGNATURES = {
     "dbspm_relax_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "dbspm_tricubic_gather_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp, _vp]),
     "dbspm_dfz_gradient_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp]),
+    "dbspm_convz_valid_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_double, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -68,6 +68,27 @@ __global__ void __launch_bounds__(256) gradz_kernel(const double *E, long long n
     }
 }
 
+// out[c, i] = scale * sum_j w[j] * F[c, i + nw - 1 - j]: np.convolve(F[c,:], w, mode="valid") along z
+// (pydbspm/tools.py:30, the Giessibl weights of get_fs); nw <= 64 weights live in shared memory
+__global__ void __launch_bounds__(256) convz_valid_kernel(const double *F, long long ncol, int nz, const double *w, int nw,
+                                                          double scale, double *out)
+{
+    __shared__ double sw[64];
+    if (threadIdx.x < nw) sw[threadIdx.x] = w[threadIdx.x];
+    __syncthreads();
+    const int nout = nz - nw + 1;
+    const long long total = ncol * nout;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long c = i / nout;
+        const int z = (int)(i - c * nout);
+        const double *f = F + c * nz + z + nw - 1;
+        double acc = 0.0;
+        for (int j = 0; j < nw; ++j) acc = fma(sw[j], f[-j], acc);
+        out[i] = acc * scale;
+    }
+}
+
 static unsigned grid_for(size_t n, int threads)
 {
     size_t b = (n + threads - 1) / threads;
@@ -174,6 +195,18 @@ extern "C" int dbspm_dfz_gradient_f64(const double *E, int nx, int ny, int nz, d
     DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1 && dz != 0.0, DBSPM_EINVAL, "bad arguments");
     const long long ncol = (long long)nx * ny;
     gradz_kernel<<<grid_for((size_t)ncol * nz, 256), 256, 0, (cudaStream_t)stream>>>(E, ncol, nz, -dz, out);
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    return DBSPM_OK;
+}
+
+extern "C" int dbspm_convz_valid_f64(const double *F, int nx, int ny, int nz, const double *w, int nw, double scale,
+                                     double *out, void *stream)
+{
+    DBSPM_REQUIRE(F && w && out, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1 && nw >= 1 && nw <= 64 && nw <= nz, DBSPM_EINVAL,
+                  "need 1 <= nw <= min(64, nz) (nw=%d, nz=%d)", nw, nz);
+    const long long ncol = (long long)nx * ny;
+    convz_valid_kernel<<<grid_for((size_t)ncol * (nz - nw + 1), 256), 256, 0, (cudaStream_t)stream>>>(F, ncol, nz, w, nw, scale, out);
     DBSPM_CUDA_TRY(cudaGetLastError());
     return DBSPM_OK;
 }

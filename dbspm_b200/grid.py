@@ -182,3 +182,44 @@ def sph2grid(th, az, r, dr):
 def sph2cart(th, az, r):
     """(theta, phi, r) -> Cartesian (grid.py:381-386)."""
     return r * np.sin(th) * np.cos(az), r * np.sin(th) * np.sin(az), r * np.cos(th)
+
+
+def interpolate_data(grid_new, grid_data, label, rpivot=3.02):
+    """Tricubic gather of `grid_data.<label>` at the relaxed tip-apex positions of `grid_new`
+    (pydbspm/grid.py:325-361, the BRSTM step dbspm:655-664): every point (x,y,z) of grid_new is
+    displaced by (tip_x, tip_y, tip_z + rpivot), converted to index units of grid_data and
+    interpolated -- one gather kernel launch instead of a Python nditer loop.
+
+    Points of grid_new outside grid_data's extent are dropped on all operands (the reference
+    only masks the tip offsets, which fails unless the mask is all-True)."""
+    from .interactions import TricubicField
+
+    field = TricubicField(np.ascontiguousarray(getattr(grid_data, label), dtype=np.float64))
+
+    def lateral(g):
+        return (np.linalg.norm([g.x[:, 0], g.y[:, 0]], axis=0), np.linalg.norm([g.x[0, :], g.y[0, :]], axis=0))
+
+    dx_, dy_ = lateral(grid_data)
+    grid_new.x_, grid_new.y_ = lateral(grid_new)
+    x_min, x_max = dx_.min(), dx_.max() + grid_data.dr[0]
+    y_min, y_max = dy_.min(), dy_.max() + grid_data.dr[1]
+    z_min, z_max = grid_data.z.min(), grid_data.z.max()
+    keep = [(grid_new.x_ >= x_min) & (grid_new.x_ <= x_max),
+            (grid_new.y_ >= y_min) & (grid_new.y_ <= y_max),
+            (grid_new.z >= z_min) & (grid_new.z <= z_max)]
+    sel = np.ix_(*keep)
+    nz = len(grid_new.z)
+    X = np.repeat(grid_new.x[..., np.newaxis], nz, axis=2) - x_min
+    Y = np.repeat(grid_new.y[..., np.newaxis], nz, axis=2) - y_min
+    Z = np.ones(tuple(int(v) for v in grid_new.shape)) * grid_new.z - z_min
+    pts = np.stack([(X[sel] + grid_new.tip_x[sel]) / grid_data.dr[0],
+                    (Y[sel] + grid_new.tip_y[sel]) / grid_data.dr[1],
+                    (Z[sel] + grid_new.tip_z[sel] + rpivot) / grid_data.dr[2]], axis=-1)
+    res = field.gather(pts)
+    new = copy.deepcopy(grid_new)
+    if tuple(int(v) for v in new.shape) != res.shape:
+        new.shape = np.array(res.shape)
+        new.x, new.y, new.z = grid_new.x[keep[0]], grid_new.y[keep[1]], grid_new.z[keep[2]]
+        new.grid = [new.x, new.y, new.z]
+    new.set_density("data", res, safe=False)
+    return new

@@ -1,0 +1,36 @@
+"""Batched FDBM parameter sweep (BASELINE.json configs[3]; motivated by scripts/fdbmfit:136-154,
+which re-runs the FFT correlation inside a least-squares loop).
+
+For a list of (alpha, V0, kappa) sets: the es grid is computed once, one sr grid per distinct
+alpha (both densities are raised to alpha, dbspm:329), and one relax per set
+(static = V0*sr_alpha + es + vdw, dbspm:479-486).  All arrays stay in HBM between steps."""
+from __future__ import annotations
+
+import torch
+
+from . import interactions as ops
+
+
+def fdbm_sweep(rhoS, potS, rhoT, nrhoT, dr, z_window, nz_relax, param_sets, rpivot, vdw=None, dR=None,
+               keep_static=False):
+    """param_sets: iterable of (alpha, V0, kappa).  Inputs: CUDA tensors (or numpy, uploaded once).
+    Returns {"es": window, "sr": {alpha: window}, "relax": [dict per set]} with CUDA tensors."""
+    dev = rhoS.device if isinstance(rhoS, torch.Tensor) and rhoS.is_cuda else ops._device()
+    A, P, T, NT = (ops._to_dev(a, dev) for a in (rhoS, potS, rhoT, nrhoT))
+    z_lo, z_hi = z_window
+    es = ops.density_overlap_window(P, NT, dr, z_lo, z_hi)
+    vd = ops._to_dev(vdw, dev) if vdw is not None else None
+    sr = {}
+    out = []
+    for alpha, V0, kappa in param_sets:
+        a = float(alpha)
+        if a not in sr:
+            sr[a] = ops.density_overlap_window(A, T, dr, z_lo, z_hi, a, a)
+        comps = [(sr[a], float(V0)), (es, 1.0)] + ([(vd, 1.0)] if vd is not None else [])
+        static = ops.build_static(comps)
+        r = ops.relax_grid(static, float(kappa), rpivot, dr, nz_relax, dR=dR)
+        r.update(alpha=a, V=float(V0), kappa=float(kappa))
+        if keep_static:
+            r["static"] = static
+        out.append(r)
+    return {"es": es, "sr": sr, "relax": out}

@@ -17,6 +17,7 @@
  *   dbspm_tricubic_gather_f64   pydbspm/grid.py:325-361 interpolate_data (tricubic .ip at
  *                               explicit index-space points; also grid.py:122-139)
  *   dbspm_dfz_gradient_f64      pydbspm/SPMGrid.py:375-379 np.gradient(E, -dz, axis=2)
+ *   dbspm_convz_valid_f64       pydbspm/tools.py:5-32 get_fs (np.convolve(..., 'valid') along z)
  *
  * Conventions
  *   - every array pointer is a DEVICE pointer to C-contiguous float64 memory (z fastest),
@@ -98,6 +99,11 @@ int dbspm_tricubic_gather_f64(const double *data, int nx, int ny, int nz,
 
 /* ---- dE/dz image: out = np.gradient(E, -dz, axis=2) for E of shape (nx,ny,nz) ------------- */
 int dbspm_dfz_gradient_f64(const double *E, int nx, int ny, int nz, double dz, double *out, void *stream);
+
+/* ---- valid 1-D convolution along z: out (nx,ny,nz-nw+1) = scale * np.convolve(F[x,y,:], w, "valid") ----
+ * (the force -> frequency-shift weighting of pydbspm/tools.py:5-32 get_fs; w, nw <= 64, on the device) */
+int dbspm_convz_valid_f64(const double *F, int nx, int ny, int nz, const double *w, int nw, double scale,
+                          double *out, void *stream);
 
 #ifdef __cplusplus
 }

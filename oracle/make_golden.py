@@ -102,11 +102,42 @@ def geometry_cases():
     return out
 
 
+def next_row_cases():
+    """§8f rows: tricubic gather at relaxed tip positions (grid.py:325-361) and force -> Delta-f
+    (tools.py:5-32), both run through the reference's own functions."""
+    import types
+    import pydbspm.tools as RT
+    fake = types.ModuleType("tricubic")           # the reference does `import tricubic` inside the function
+    fake.tricubic = O.Tricubic
+    sys.modules["tricubic"] = fake
+    rng = np.random.default_rng(20260101)
+    cell = np.diag([3.6, 3.0, 4.5])
+    data_grid = RG.Grid((24, 20, 30), cell=cell, positions=np.zeros((1, 3)), numbers=np.array([6]))
+    x, y, z = np.meshgrid(np.arange(24), np.arange(20), np.arange(30), indexing="ij")
+    sp = np.exp(-((x - 11.5) ** 2 + (y - 9.0) ** 2) / 40.0 - z / 8.0) + 0.05 * np.cos(2 * np.pi * x / 24) * np.sin(2 * np.pi * y / 20)
+    data_grid.set_density("sp", sp)
+    dr = data_grid.dr
+    new_grid = RG.Grid(np.array([24, 20, 6]), cell=cell, span=np.diag([24, 20, 6]) * dr, origin=np.array([0.0, 0.0, 4 * dr[2]]),
+                       zref=0.0, positions=np.zeros((1, 3)), numbers=np.array([6]))
+    tip = rng.normal(0.0, 0.05, (3, 24, 20, 6))
+    tip[2] = -0.3 + 0.02 * rng.standard_normal((24, 20, 6))
+    for lab, arr in zip(("tip_x", "tip_y", "tip_z"), tip):
+        new_grid.set_density(lab, arr)
+    out = RG.interpolate_data(new_grid, data_grid, "sp", rpivot=0.3)
+    F = rng.standard_normal((6, 5, 40))
+    fs = RT.get_fs(F, dz=0.075, n=10)
+    fs6 = RT.get_fs(F, dz=0.1, k0=1500.0, f0=25000.0, n=6)
+    np.savez_compressed(os.path.join(OUT, "nextrow_reference.npz"), sp=sp, cell=cell, tip=tip, interp=out.data,
+                        F=F, fs=fs, fs6=fs6)
+    return {"interp_shape": list(out.data.shape), "rpivot": 0.3, "new_origin_z_index": 4}
+
+
 if __name__ == "__main__":
     manifest = {
         "generator": "oracle/make_golden.py", "reference": "/root/reference (SPMTH/DBSPM, unmodified)",
         "numpy": np.__version__, "scipy": scipy.__version__,
         "overlap": overlap_cases(), "relax": relax_cases(), "geometry": geometry_cases(),
+        "nextrow": next_row_cases(),
     }
     with open(os.path.join(OUT, "manifest.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)

@@ -101,3 +101,17 @@ def test_pivot_height_truncation_quirk(relax_golden):
     z_trunc = int(0 + 3.02 / dr[2]) + r * np.cos(th) / dr[2]
     e = tc.ip([4 + r * np.sin(th) * np.cos(az) / dr[0], 4 + r * np.sin(th) * np.sin(az) / dr[1], z_trunc])
     assert abs(e + 0.5 * 0.2 * (np.pi - th) ** 2 - out[0, 0]) < 1e-14
+
+
+def test_get_fs_restatement_matches_reference_golden():
+    """tools.py:5-32 restated with numpy (the checker used by the GPU Delta-f test)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nextrow_reference.npz"))
+    F = g["F"]
+    for key, (dz, k0, f0, n) in {"fs": (0.075, 1800, 30300, 10), "fs6": (0.1, 1500.0, 25000.0, 6)}.items():
+        x = np.linspace(-1, 1, n + 1)
+        y = np.sqrt(1 - x * x)
+        dy = (y[1:] - y[:-1]) / (dz * n)
+        pref = (1 + (n - 2) ** 2 * (2 / np.pi)) / ((n - 2) ** 2 + 1)
+        got = -pref * np.apply_along_axis(lambda m: np.convolve(m, dy, mode="valid"), 2, F) * 16.0217656 * f0 / k0
+        assert np.array_equal(got, g[key])
