@@ -208,7 +208,12 @@ def run_gpu_arm(args):
     from dbspm_b200.input_parser import default_params
     from argparse import Namespace
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("DBSPM_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: NCCL prints its version banner there at any NCCL_DEBUG level
+    if "DBSPM_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["DBSPM_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
     rank, world, dev = parallel.init_from_env()
     assert dev.type == "cuda", "bench.py needs a GPU (use --impl reference for the CPU arm)"
     if world != args.gpus and rank == 0:
@@ -234,47 +239,51 @@ def run_gpu_arm(args):
     vdw = synth.make_vdw_window(cfg, atoms, (nx, ny, nzw), float(win.origin[2]), dev)
     torch.cuda.synchronize()
 
-    slabs = parallel.split_range(z_lo, z_hi, world)
+    # sr and es are independent: with N >= 2 half of the ranks compute sr and the other half es
+    # (each half splits the window's planes); with N = 1 the single rank runs both
+    plan = parallel.interaction_plan(world, z_lo, z_hi)
+    jobs = plan[rank]
     tiles = parallel.split_range(0, nx, world)
-    my_zl, my_zh = slabs[rank]
     my_il, my_ih = tiles[rank]
-    sr_slab = torch.empty((nx, ny, my_zh - my_zl), dtype=torch.float64, device=dev)
-    es_slab = torch.empty_like(sr_slab)
+    inputs = {0: (rhoS, rhoT, cfg.alpha), 1: (potS, nrhoT, 1.0)}
+    bufs = [torch.empty((nx, ny, zh - zl), dtype=torch.float64, device=dev) for (_, zl, zh) in jobs]
     launches = {"n": 0}
-
-    def overlap(a, b, alpha, out):
-        if my_zh > my_zl:
-            ops.density_overlap_window(a, b, dr, my_zl, my_zh, alpha, alpha, out=out)
-            launches["n"] += 5 + (1 if (my_zh - my_zl) & 1 else 0)
-        full = parallel.corr3d_sharded(lambda zl, zh: out, nx, ny, z_lo, z_hi, dev)   # gather (N>1)
-        return full
 
     def ev():
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         return e
 
+    def corr_phase(src, marks=None):
+        for (which, zl, zh), buf in zip(jobs, bufs):
+            a, b, al = src[which]
+            if zh > zl:
+                ops.density_overlap_window(a, b, dr, zl, zh, al, al, out=buf)
+                launches["n"] += 5 + (1 if (zh - zl) & 1 else 0)
+            if marks is not None:
+                marks.append(ev())
+        return parallel.gather_windows(plan, bufs, nx, ny, z_lo, z_hi, dev)        # rank 0: [sr, es]
+
     def step(timed):
         e0 = ev()
-        sr = overlap(rhoS, rhoT, cfg.alpha, sr_slab)
-        e1 = ev()
-        es = overlap(potS, nrhoT, 1.0, es_slab)
+        mid = []
+        wins = corr_phase(inputs, mid)
         e2 = ev()
         if world > 1:                       # every rank needs the whole static window
             if rank != 0:
-                sr = torch.empty((nx, ny, nzw), dtype=torch.float64, device=dev)
-                es = torch.empty_like(sr)
-            parallel.broadcast_(sr); parallel.broadcast_(es)
+                wins = [torch.empty((nx, ny, nzw), dtype=torch.float64, device=dev) for _ in range(2)]
+            parallel.broadcast_(wins[0]); parallel.broadcast_(wins[1])
+        sr, es = wins
         static = ops.build_static([(sr, cfg.V), (es, 1.0), (vdw, 1.0)])
         launches["n"] += 3
         res = parallel.relax_sharded(
             lambda il, ih: {k: v for k, v in ops.relax_grid(static, cfg.kappa, cfg.rpivot, dr, nz_relax,
                                                             tile=(il, ih, 0, ny)).items() if k in ("E", "tip_x", "tip_y", "tip_z")},
             nx, dev)
-        launches["n"] += 1 if my_ih > my_il else 0
+        launches["n"] += 3 if my_ih > my_il else 0          # transpose + relax + cart
         e3 = ev()
         if timed is not None:
-            timed.append((e0, e1, e2, e3))
+            timed.append((e0, mid[0], e2, e3))
         return static
 
     def barrier():
@@ -300,6 +309,8 @@ def run_gpu_arm(args):
             static = step(marks)
         barrier()
         t_wall = time.perf_counter() - t_wall0
+    # N = 1: first job = sr, then es, no gather.  N > 1: sr and es run concurrently on different ranks;
+    # only their sum (start -> both windows assembled on rank 0) is meaningful
     t_sr = sum(a.elapsed_time(b) for a, b, _, _ in marks) / args.steps
     t_es = sum(b.elapsed_time(c) for _, b, c, _ in marks) / args.steps
     t_rest = sum(c.elapsed_time(d) for _, _, c, d in marks) / args.steps
@@ -307,16 +318,17 @@ def run_gpu_arm(args):
     t_sr, t_es, t_rest, t_all = max_over_ranks([t_sr, t_es, t_rest, t_all])
     n_launch = launches["n"]
 
-    # ---- per-launch durations of the correlation (stage-skip flags), rank 0's slab ---------
+    # ---- per-launch durations of the correlation (stage-skip flags), this rank's first job ----
     stages = {}
     relax_ms = None
-    if my_zh > my_zl:
+    which0, zl0, zh0 = jobs[0]
+    if zh0 > zl0:
         allskip = sum(SKIP.values())
         for name, bit in SKIP.items():
             ts = []
             for it in range(4):
                 a = ev()
-                ops.density_overlap_window(potS, nrhoT, dr, my_zl, my_zh, out=es_slab, flags=allskip & ~bit)
+                ops.density_overlap_window(potS, nrhoT, dr, zl0, zh0, out=bufs[0], flags=allskip & ~bit)
                 b = ev(); torch.cuda.synchronize()
                 if it:
                     ts.append(a.elapsed_time(b))
@@ -324,7 +336,7 @@ def run_gpu_arm(args):
         ts = []
         for it in range(3):
             a = ev()
-            ops.density_overlap_window(rhoS, rhoT, dr, my_zl, my_zh, cfg.alpha, cfg.alpha, out=sr_slab,
+            ops.density_overlap_window(rhoS, rhoT, dr, zl0, zh0, cfg.alpha, cfg.alpha, out=bufs[0],
                                        flags=allskip & ~SKIP["x_fwd"])
             b = ev(); torch.cuda.synchronize()
             if it:
@@ -345,32 +357,30 @@ def run_gpu_arm(args):
     # ---- end to end: pinned host inputs in, results out, inside the timed region -----------
     e2e = None
     if not args.no_e2e:
-        hosts = {k: torch.empty(v.shape, dtype=torch.float64).pin_memory().copy_(v) for k, v in
-                 (("rhoS", rhoS), ("potS", potS), ("rhoT", rhoT), ("nrhoT", nrhoT), ("vdw", vdw))}
-        out_sr = torch.empty((nx, ny, my_zh - my_zl), dtype=torch.float64).pin_memory()
-        out_es = torch.empty_like(out_sr).pin_memory()
+        need = {"vdw"} | {n for (w, _, _) in jobs for n in (("rhoS", "rhoT") if w == 0 else ("potS", "nrhoT"))}
+        dev_src = {"rhoS": rhoS, "potS": potS, "rhoT": rhoT, "nrhoT": nrhoT, "vdw": vdw}
+        hosts = {k: torch.empty(dev_src[k].shape, dtype=torch.float64).pin_memory().copy_(dev_src[k]) for k in sorted(need)}
+        outs_h = [torch.empty(tuple(b.shape), dtype=torch.float64).pin_memory() for b in bufs]
         ni = my_ih - my_il
         out_rel = torch.empty((4, ni, ny, nz_relax), dtype=torch.float64).pin_memory()
         d_in = {k: torch.empty_like(v, device=dev) for k, v in hosts.items()}
-        del rhoS, potS, rhoT, nrhoT
+        del rhoS, potS, rhoT, nrhoT, dev_src, inputs
         torch.cuda.empty_cache()
+        names = {0: ("rhoS", "rhoT", cfg.alpha), 1: ("potS", "nrhoT", 1.0)}
 
         def e2e_step(rec):
             e0 = ev()
-            for k in ("rhoS", "rhoT"):
-                d_in[k].copy_(hosts[k], non_blocking=True)
-            if my_zh > my_zl:
-                ops.density_overlap_window(d_in["rhoS"], d_in["rhoT"], dr, my_zl, my_zh, cfg.alpha, cfg.alpha, out=sr_slab)
-            out_sr.copy_(sr_slab, non_blocking=True)
-            for k in ("potS", "nrhoT"):
-                d_in[k].copy_(hosts[k], non_blocking=True)
-            if my_zh > my_zl:
-                ops.density_overlap_window(d_in["potS"], d_in["nrhoT"], dr, my_zl, my_zh, out=es_slab)
-            out_es.copy_(es_slab, non_blocking=True)
+            for (which, zl, zh), buf, oh in zip(jobs, bufs, outs_h):
+                na, nb, al = names[which]
+                d_in[na].copy_(hosts[na], non_blocking=True)
+                d_in[nb].copy_(hosts[nb], non_blocking=True)
+                if zh > zl:
+                    ops.density_overlap_window(d_in[na], d_in[nb], dr, zl, zh, al, al, out=buf)
+                oh.copy_(buf, non_blocking=True)
             e1 = ev()
             d_in["vdw"].copy_(hosts["vdw"], non_blocking=True)
             if world == 1:
-                st = ops.build_static([(sr_slab, cfg.V), (es_slab, 1.0), (d_in["vdw"], 1.0)])
+                st = ops.build_static([(bufs[0], cfg.V), (bufs[1], 1.0), (d_in["vdw"], 1.0)])
             else:
                 st = static
             rr = ops.relax_grid(st, cfg.kappa, cfg.rpivot, dr, nz_relax, tile=(my_il, my_ih, 0, ny))
@@ -388,12 +398,13 @@ def run_gpu_arm(args):
             e2e_step(rec)
         barrier()
         tc, tr = max_over_ranks([float(np.mean([x[0] for x in rec])), float(np.mean([x[1] for x in rec]))])
-        h2d = 8 * (4 * N + Nw)
-        d2h = 8 * (2 * nx * ny * (my_zh - my_zl) + 4 * ni * ny * nz_relax)
+        h2d = 8 * (2 * len(jobs) * N + Nw)
+        d2h = 8 * (sum(int(b.numel()) for b in bufs) + 4 * ni * ny * nz_relax)
         e2e = {"value": 2 * N / (tc * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_sr_es": tc, "relax_value": nx * ny * nz_relax / (tr * 1e-3), "relax_unit": "tip positions/s",
-               "ms_relax": tr, "note": "pinned host -> HBM copies of all four input grids + vdw, window and relax "
-                                       "results copied back, all inside the timed region"}
+               "ms_relax": tr, "note": "per rank: pinned host -> HBM copies of the input grids of its interaction(s) "
+                                       "+ vdw, its window slab(s) and relax tile copied back, all inside the timed "
+                                       "region; byte counts are per rank"}
 
     if rank != 0:
         if world > 1:
@@ -409,9 +420,11 @@ def run_gpu_arm(args):
             "traffic_note": "dram bytes read+write of sr+es (2 x 5 launches), ncu --set full, profiles/traffic.json",
             "peak_source": peak_src,
             "kernel": "dbspm_corr3d_f64 = 5 launches (axis_pass x_fwd, y_fwd, zfused, axis_pass y_inv, x_inv)",
-            "algorithmic_bytes_per_interaction": balg, "ms_sr": t_sr, "ms_es": t_es,
-            "note": "frac = algorithmic bytes of sr+es / (time * n_gpus * peak); es alone: %.4f of peak"
-                    % (balg / (t_es * 1e-3) / 1e9 / peak / world)}
+            "algorithmic_bytes_per_interaction": balg, "ms_sr_plus_es": t_corr,
+            "ms_sr": t_sr if world == 1 else None, "ms_es": t_es if world == 1 else None,
+            "note": "frac = algorithmic bytes of sr+es / (time * n_gpus * peak)"
+                    + ("; es alone: %.4f of peak" % (balg / (t_es * 1e-3) / 1e9 / peak) if world == 1 else
+                       "; sr and es run concurrently on disjoint rank groups, time includes the gather to rank 0")}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         c = cpu_reference_pass()
@@ -425,7 +438,8 @@ def run_gpu_arm(args):
                    "window_z": [z_lo, z_hi], "relax_shape": [nx, ny, nz_relax], "alpha": cfg.alpha, "V": cfg.V,
                    "kappa": cfg.kappa, "rpivot": cfg.rpivot, "tip": "noisy (non-compact, full-z path)",
                    "l2": "inputs are %.2f GB each, far larger than the 126 MB L2 (no flush needed)" % (8 * N / 1e9),
-                   "parallelism": f"z-slab x{world} (sr/es), x-tile x{world} (relax), gather to rank 0"},
+                   "parallelism": (f"sr | es on disjoint rank groups, z-slab within a group ({world} ranks), "
+                                   f"x-tile x{world} (relax), gather to rank 0") if world > 1 else "single GPU"},
         "relax": {"value": nx * ny * nz_relax / (relax_ms_max * 1e-3), "unit": "tip positions/s",
                   "ms": relax_ms_max, "mean_nfev": nfev_mean, "in_step_ms_static_relax_gather": t_rest},
         "stages_ms": stages, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,

@@ -92,6 +92,49 @@ def corr3d_sharded(compute_slab, nx, ny, z_lo, z_hi, device):
     return torch.cat(parts, dim=0).permute(1, 2, 0).contiguous()
 
 
+def interaction_plan(world: int, z_lo: int, z_hi: int, n_inter: int = 2):
+    """Which (interaction, z-slab) jobs each rank runs when several independent interaction
+    grids (sr, es) are wanted at once.
+
+    The forward transforms of a correlation cannot be split by output plane (every output plane
+    needs the whole spectrum), so z-slab sharding alone does not scale; sr and es, however, share
+    no work at all.  With world >= n_inter the ranks are divided into n_inter groups, one per
+    interaction, and each group splits the window's planes among its ranks.  With fewer ranks
+    every rank runs the interactions one after the other on its slab of a plain z-slab split."""
+    if world < n_inter:
+        slabs = split_range(z_lo, z_hi, world)
+        return [[(i, zl, zh) for i in range(n_inter)] for (zl, zh) in slabs]
+    plan = []
+    for i, (r_lo, r_hi) in enumerate(split_range(0, world, n_inter)):
+        for zl, zh in split_range(z_lo, z_hi, r_hi - r_lo):
+            plan.append([(i, zl, zh)])
+    return plan
+
+
+def gather_windows(plan, mine, nx, ny, z_lo, z_hi, device, n_inter: int = 2, dst: int = 0):
+    """Assemble the n_inter full (nx,ny,z_hi-z_lo) windows on rank `dst` from the slabs each rank
+    computed under `plan` (`mine`: this rank's slabs, in the order of its jobs).  One gather of
+    slab-major buffers per job slot; other ranks get None."""
+    rank, world = _world()
+    if world == 1:
+        return list(mine)
+    nslots = max(len(jobs) for jobs in plan)
+    nzw = z_hi - z_lo
+    out = [torch.empty((nx, ny, nzw), dtype=torch.float64, device=device) for _ in range(n_inter)] if rank == dst else None
+    for slot in range(nslots):
+        jobs = [p[slot] if slot < len(p) else None for p in plan]
+        sizes = [(j[2] - j[1]) * nx * ny if j else 0 for j in jobs]
+        # slabs travel as flat buffers (z stays the fastest axis); rank dst drops each one into its
+        # z-range of the full window with a single strided copy -- no transposes on either side
+        local = mine[slot].reshape(-1) if slot < len(mine) else torch.empty(0, dtype=torch.float64, device=device)
+        parts = _gather_padded(local, sizes, dst)
+        if rank == dst:
+            for j, part in zip(jobs, parts):
+                if j and part.numel() > 0:
+                    out[j[0]][:, :, j[1] - z_lo:j[2] - z_lo] = part.view(nx, ny, j[2] - j[1])
+    return out
+
+
 def relax_sharded(compute_tile, nx, device):
     """compute_tile(i_lo, i_hi) -> dict of tensors whose first axis is the tile's x extent
     (E, theta, phi, tip_x, tip_y, tip_z: (ni,ny,nz)).  Rank 0 returns the concatenated dict."""

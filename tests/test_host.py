@@ -156,6 +156,18 @@ def test_split_range():
     assert parallel.split_range(0, 3, 4) == [(0, 0), (0, 1), (1, 2), (2, 3)]
     parts = parallel.split_range(0, 1024, 8)
     assert parts[0] == (0, 128) and parts[-1] == (896, 1024)
+    # sr / es interaction plan: 1 rank runs both; N >= 2 ranks split into an sr half and an es half
+    assert parallel.interaction_plan(1, 76, 130) == [[(0, 76, 130), (1, 76, 130)]]
+    p4 = parallel.interaction_plan(4, 76, 130)
+    assert p4 == [[(0, 76, 103)], [(0, 103, 130)], [(1, 76, 103)], [(1, 103, 130)]]
+    p3 = parallel.interaction_plan(3, 0, 10)
+    assert p3 == [[(0, 0, 10)], [(1, 0, 5)], [(1, 5, 10)]]
+    for world in (2, 3, 5, 8):
+        cover = {0: [], 1: []}
+        for jobs in parallel.interaction_plan(world, 76, 130):
+            for w, zl, zh in jobs:
+                cover[w].extend(range(zl, zh))
+        assert sorted(cover[0]) == sorted(cover[1]) == list(range(76, 130))
 
 
 _WORKER = r'''
@@ -174,6 +186,16 @@ tiles = {{k: torch.from_numpy(rng.random((5, 4, 3))) for k in ("E", "tip_x")}}
 def tile(i_lo, i_hi):
     return {{k: v[i_lo:i_hi].contiguous() for k, v in tiles.items()}}
 res = parallel.relax_sharded(tile, 5, device)
+# sr on rank 0, es on rank 1 (interaction-parallel plan), one gather assembles both windows
+plan = parallel.interaction_plan(2, 10, 17)
+assert plan == [[(0, 10, 17)], [(1, 10, 17)]]
+full2 = [full, full * 2.0 + 1.0]
+which, zl, zh = plan[rank][0]
+wins = parallel.gather_windows(plan, [full2[which][:, :, zl - 10:zh - 10].contiguous()], 5, 4, 10, 17, device)
+if rank == 0:
+    assert torch.equal(wins[0], full2[0]) and torch.equal(wins[1], full2[1]), "interaction gather"
+else:
+    assert wins is None
 t = torch.arange(3.0) if rank == 0 else torch.zeros(3)
 parallel.broadcast_(t)
 assert torch.equal(t, torch.arange(3.0))
