@@ -29,12 +29,19 @@ __global__ void __launch_bounds__(DBSPM_THREADS) zfused_kernel(const __grid_cons
     zfused_body(P, smem, (long long)blockIdx.x, (int)threadIdx.x, (int)blockDim.x);
 }
 
+#ifndef ZF2_PAIRS
 #define ZF2_PAIRS 4
+#endif
+#ifndef ZF2_THREADS
 #define ZF2_THREADS 128
-__global__ void __launch_bounds__(ZF2_THREADS) zfused2_kernel(const __grid_constant__ ZFusedParams P)
+#endif
+#ifndef ZF2_MIN_BLOCKS
+#define ZF2_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(ZF2_THREADS, ZF2_MIN_BLOCKS) zfused2_kernel(const __grid_constant__ ZFusedParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    zfused_body_v2<ZF2_PAIRS>(P, smem, (long long)blockIdx.x, (int)threadIdx.x, (int)blockDim.x);
+    zfused_body_v2<ZF2_PAIRS>(P, smem, (long long)blockIdx.x, (long long)gridDim.x, (int)threadIdx.x, (int)blockDim.x);
 }
 
 __global__ void __launch_bounds__(DBSPM_THREADS) compact_kernel(const double *W, double *E, long long ncol, int nzw, int ldw)
@@ -52,17 +59,18 @@ struct DevPlan {
 };
 
 static std::mutex g_plan_mu;
-static std::map<std::pair<int, int>, DevPlan *> g_plans;   // (device, n)
+static std::map<std::pair<int, int>, DevPlan *> g_plans;   // (device, n + 65536 * max radix)
 
-static int get_plan(int n, cudaStream_t st, DevPlan **out)
+static int get_plan(int n, cudaStream_t st, DevPlan **out, int max_radix = 16)
 {
     int dev = 0;
     DBSPM_CUDA_TRY(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_plan_mu);
-    auto it = g_plans.find({dev, n});
+    const int key = n + 65536 * max_radix;
+    auto it = g_plans.find({dev, key});
     if (it != g_plans.end()) { *out = it->second; return DBSPM_OK; }
     DevPlan *p = new DevPlan();
-    if (!dbspm_make_plan(n, p->host)) {
+    if (!dbspm_make_plan(n, p->host, max_radix)) {
         delete p;
         dbspm_set_error("FFT length %d has a prime factor > %d (unsupported)", n, DBSPM_MAX_RADIX);
         return DBSPM_EUNSUPPORTED;
@@ -76,7 +84,7 @@ static int get_plan(int n, cudaStream_t st, DevPlan **out)
     DBSPM_CUDA_TRY(cudaMemcpyAsync(p->freq_of, p->host.freq_of.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
     // tables may be used from other streams later: make them visible before returning
     DBSPM_CUDA_TRY(cudaStreamSynchronize(st));
-    g_plans[{dev, n}] = p;
+    g_plans[{dev, key}] = p;
     *out = p;
     return DBSPM_OK;
 }
@@ -181,7 +189,7 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
     // fused z: forward, untangle, product, window phase, pruned inverse
     if (!(flags & DBSPM_CORR_SKIP_Z)) {
         DevPlan *pl = nullptr, *plN = nullptr;
-        rc = get_plan(n, st, &pl);
+        rc = get_plan(n, st, &pl, ZF2_MAX_RADIX);
         if (rc) return rc;
         rc = get_plan(nz, st, &plN);
         if (rc) return rc;
@@ -194,9 +202,13 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
         const bool v2 = axis_v2_ok(P.plan) && zfused2_smem_bytes<ZF2_PAIRS>(n) <= 113 * 1024 &&
                         !(flags & DBSPM_CORR_AXIS_V1);
         if (v2) {
-            const long long nblocks = (P.npairs + ZF2_PAIRS - 1) / ZF2_PAIRS;
+            const long long ngroups = (P.npairs + ZF2_PAIRS - 1) / ZF2_PAIRS;
             const size_t smem = zfused2_smem_bytes<ZF2_PAIRS>(n);
-            DBSPM_REQUIRE(nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large");
+            // persistent blocks: a few per SM (148 SMs), each walking over its share of the pair groups
+            int per_sm = (int)((220 * 1024) / (smem + 1024));
+            per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+            long long nblocks = 148LL * per_sm * 2;
+            if (nblocks > ngroups) nblocks = ngroups;
             DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             zfused2_kernel<<<(unsigned)nblocks, ZF2_THREADS, smem, st>>>(P);

@@ -13,6 +13,10 @@
 #pragma once
 #include "fft_core.h"
 
+#ifndef ZF2_MAX_RADIX
+#define ZF2_MAX_RADIX 16   /* power-of-two radix cap of the z-kernel plan (registers vs stage count) */
+#endif
+
 // ------------------------------------------------------------------------------------------
 // Strided-axis pass: FFT along an axis of length n whose elements are `inner` complex apart;
 // `outer` independent slabs.  One block = T adjacent lines of one slab, staged in shared
@@ -462,8 +466,12 @@ HD void fft_stages_from(cplx *s, int ld, int tshift, const FftPlanDev &pl, int f
         case 4: fft_stage<4, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
         case 5: fft_stage<5, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
         case 7: fft_stage<7, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+#if ZF2_MAX_RADIX >= 16
         case 8: fft_stage<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
         default: fft_stage<16, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+#else
+        default: fft_stage<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+#endif
         }
         m /= r;
         BLOCK_SYNC();
@@ -471,7 +479,7 @@ HD void fft_stages_from(cplx *s, int ld, int tshift, const FftPlanDev &pl, int f
 }
 
 template <int ZLV>
-HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long bid, int tid, int nthr)
+HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long bid0, long long bstride, int tid, int nthr)
 {
     constexpr int TF = 4 * ZLV, TI = 2 * ZLV, LDF = TF + 1, LDI = TI + 1;
     constexpr int TSF = ZLV == 1 ? 2 : (ZLV == 2 ? 3 : (ZLV == 4 ? 4 : 5));
@@ -491,6 +499,10 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
         pos_of[e] = LDG(P.pos_of + e);
         freq_of[e] = LDG(P.freq_of + e);
     }
+    // persistent block: the tables above are staged once, then the block walks over its share of
+    // the pair groups
+    const long long ngroups = (P.npairs + ZLV - 1) / ZLV;
+    for (long long bid = bid0; bid < ngroups; bid += bstride) {
     for (int l = tid; l < ZLV; l += nthr) {
         const ZPair z = zpair_of(P, bid * ZLV + l);
         int *pi = pinfo + 6 * l;
@@ -503,8 +515,12 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
     case 4: zfused2_first<-1, 4, ZLV>(P, U, tw, pinfo, tid, nthr); break;
     case 5: zfused2_first<-1, 5, ZLV>(P, U, tw, pinfo, tid, nthr); break;
     case 7: zfused2_first<-1, 7, ZLV>(P, U, tw, pinfo, tid, nthr); break;
+#if ZF2_MAX_RADIX >= 16
     case 8: zfused2_first<-1, 8, ZLV>(P, U, tw, pinfo, tid, nthr); break;
     default: zfused2_first<-1, 16, ZLV>(P, U, tw, pinfo, tid, nthr); break;
+#else
+    default: zfused2_first<-1, 8, ZLV>(P, U, tw, pinfo, tid, nthr); break;
+#endif
     }
     BLOCK_SYNC();
     fft_stages_from<-1>(U, LDF, TSF, P.plan, 1, tw, tid, nthr);
@@ -552,6 +568,8 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
         if (!pi[4] || (role == 1 && pi[5])) continue;
         const int x = role ? pi[2] : pi[0], y = role ? pi[3] : pi[1];
         st_stream(P.W + ((size_t)x * P.ny + y) * P.nwh + j, S[(size_t)j * LDI + line]);
+    }
+    BLOCK_SYNC();                              // S and pinfo are rewritten by the next group
     }
 }
 

@@ -267,8 +267,12 @@ HD void fft_tile_t(cplx *s, int ld, int tshift, const FftPlanDev &pl, const cplx
         case 4: fft_stage_t<4, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
         case 5: fft_stage_t<5, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
         case 7: fft_stage_t<7, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+#if !defined(ZF2_MAX_RADIX) || ZF2_MAX_RADIX >= 16
         case 8: fft_stage_t<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
         default: fft_stage_t<16, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+#else
+        default: fft_stage_t<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+#endif
         }
         BLOCK_SYNC();
     }

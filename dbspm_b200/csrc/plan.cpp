@@ -3,7 +3,7 @@
 #include "plan.h"
 #include <math.h>
 
-bool dbspm_make_plan(int n, HostPlan &out)
+bool dbspm_make_plan(int n, HostPlan &out, int max_pow2_radix)
 {
     if (n < 1) return false;
     FftPlanDev &d = out.dev;
@@ -24,9 +24,10 @@ bool dbspm_make_plan(int n, HostPlan &out)
     int twos = 0;
     while (rem % 2 == 0) { rem /= 2; ++twos; }
     if (rem != 1) return false;                    // prime factor > DBSPM_MAX_RADIX
-    // 2^twos over ceil(twos/4) stages of radix <= 16, bits spread evenly, larger radices first
+    // 2^twos over ceil(twos/maxbits) stages of radix <= max_pow2_radix, bits spread evenly, larger radices first
     if (twos > 0) {
-        const int ns = (twos + 3) / 4;
+        const int maxbits = max_pow2_radix >= 16 ? 4 : (max_pow2_radix >= 8 ? 3 : (max_pow2_radix >= 4 ? 2 : 1));
+        const int ns = (twos + maxbits - 1) / maxbits;
         for (int i = 0; i < ns; ++i) {
             const int bits = twos / ns + (i < twos % ns ? 1 : 0);
             if (!push(1 << bits)) return false;

@@ -11,4 +11,5 @@ struct HostPlan {
 };
 
 // returns false if n has a prime factor > DBSPM_MAX_RADIX or needs too many stages
-bool dbspm_make_plan(int n, HostPlan &out);
+// max_pow2_radix (16, 8, 4 or 2) caps the power-of-two radices: smaller radices need fewer registers
+bool dbspm_make_plan(int n, HostPlan &out, int max_pow2_radix = 16);

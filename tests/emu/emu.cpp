@@ -96,7 +96,7 @@ extern "C" int emu_corr3d_f64(const double *A, const double *B, double alphaA, d
         const bool v2 = axis_v2_ok(P.plan) && force_tshift < 100;
         std::vector<unsigned char> smem((v2 ? zfused2_smem_bytes<4>(n) : zfused_smem_bytes(n)) + 64);
         unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
-        if (v2) for (long long b = 0; b < (P.npairs + 3) / 4; ++b) zfused_body_v2<4>(P, sm, b, 0, 1);
+        if (v2) for (long long b = 0; b < 3; ++b) zfused_body_v2<4>(P, sm, b, 3, 0, 1);   // 3 persistent blocks
         else for (long long b = 0; b < (P.npairs + ZL - 1) / ZL; ++b) zfused_body(P, sm, b, 0, 1);
     }
     if ((rc = run_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, force_tshift))) return rc;
