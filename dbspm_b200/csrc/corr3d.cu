@@ -8,6 +8,12 @@
 #include "plan.h"
 
 #define DBSPM_THREADS 256
+#ifndef AXIS2_THREADS
+#define AXIS2_THREADS 256
+#endif
+#ifndef AXIS2_MIN_BLOCKS
+#define AXIS2_MIN_BLOCKS 2
+#endif
 
 template <int D>
 __global__ void __launch_bounds__(DBSPM_THREADS) axis_pass_kernel(const __grid_constant__ AxisParams P)
@@ -17,7 +23,7 @@ __global__ void __launch_bounds__(DBSPM_THREADS) axis_pass_kernel(const __grid_c
 }
 
 template <int D>
-__global__ void __launch_bounds__(DBSPM_THREADS, 2) axis_pass2_kernel(const __grid_constant__ AxisParams P)
+__global__ void __launch_bounds__(AXIS2_THREADS, AXIS2_MIN_BLOCKS) axis_pass2_kernel(const __grid_constant__ AxisParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     axis_pass_body_v2<D>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
@@ -133,7 +139,7 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     DBSPM_REQUIRE(nblocks > 0 && nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large (%lld blocks)", nblocks);
     if (P.v2) {
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        axis_pass2_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), DBSPM_THREADS, smem, st>>>(P);
+        axis_pass2_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), AXIS2_THREADS, smem, st>>>(P);
     } else {
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         axis_pass_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), DBSPM_THREADS, smem, st>>>(P);

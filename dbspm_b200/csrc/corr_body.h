@@ -13,6 +13,9 @@
 #pragma once
 #include "fft_core.h"
 
+#ifndef AXIS2_TILE_BUDGET
+#define AXIS2_TILE_BUDGET (220 * 1024 / 3)   /* shared-memory bytes per CTA the axis-pass tile may use */
+#endif
 #ifndef ZF2_MAX_RADIX
 #define ZF2_MAX_RADIX 16   /* power-of-two radix cap of the z-kernel plan (registers vs stage count) */
 #endif
@@ -140,7 +143,7 @@ HD size_t axis2_smem_bytes(int n, int tshift, int nstages, int tw_smem)
 // resident CTAs per SM; the twiddle table is staged in shared memory only if that still holds
 HD void axis2_config(int n, long long inner, int nstages, int *tshift, int *tw_smem)
 {
-    const size_t budget = 220 * 1024 / 3;
+    const size_t budget = AXIS2_TILE_BUDGET;
     int ts = 3;
     while (ts > 0 && ((1LL << ts) > 2 * inner || axis2_smem_bytes(n, ts, nstages, 0) > budget)) --ts;
     *tshift = ts;

@@ -135,6 +135,8 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
     DBSPM_REQUIRE(i_lo <= i_hi && j_lo <= j_hi && nz_relax >= 0, DBSPM_EINVAL, "bad tile");
     DBSPM_REQUIRE(dr[0] > 0 && dr[1] > 0 && dr[2] > 0, DBSPM_EINVAL, "grid spacings must be positive");
     DBSPM_REQUIRE(maxfev >= 1, DBSPM_EINVAL, "maxfev must be >= 1");
+    DBSPM_REQUIRE((long long)nx * ny * nzc < 2147483647LL, DBSPM_EUNSUPPORTED,
+                  "potential grid too large for 32-bit element offsets (%d x %d x %d)", nx, ny, nzc);
     RelaxParams P;
     P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc;
     P.i_lo = i_lo; P.i_hi = i_hi; P.j_lo = j_lo; P.j_hi = j_hi; P.nz_relax = nz_relax;
@@ -183,6 +185,7 @@ extern "C" int dbspm_tricubic_gather_f64(const double *data, int nx, int ny, int
 {
     DBSPM_REQUIRE(data && pts && out, DBSPM_EINVAL, "null pointer argument");
     DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1, DBSPM_EINVAL, "bad grid shape");
+    DBSPM_REQUIRE((long long)nx * ny * nz < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large for 32-bit element offsets");
     if (npts == 0) return DBSPM_OK;
     gather_kernel<<<grid_for(npts, 256), 256, 0, (cudaStream_t)stream>>>(data, nx, ny, nz, pts, npts, out);
     DBSPM_CUDA_TRY(cudaGetLastError());

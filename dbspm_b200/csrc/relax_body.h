@@ -102,27 +102,28 @@ HD double tricubic_eval(const double *g, int nx, int ny, int nz, const double *i
     cr_axis(x, nx, inv_n[0], &ix, wx);
     cr_axis(y, ny, inv_n[1], &iy, wy);
     cr_axis(z, nz, inv_n[2], &iz, wz);
-    int zi[4], yi[4];
+    // 32-bit element offsets (the C ABI guarantees nx*ny*nz < 2^31): one 3-input add and one
+    // widening multiply-add per load instead of 64-bit pointer arithmetic
+    int xo[4], yo[4], zo[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        zi[c] = wrap_idx(iz - 1 + c, nz);
-        yi[c] = wrap_idx(iy - 1 + c, ny);
+        xo[c] = wrap_idx(ix - 1 + c, nx) * (ny * nz);
+        yo[c] = wrap_idx(iy - 1 + c, ny) * (LAYOUT == 0 ? nz : 1);
+        zo[c] = wrap_idx(iz - 1 + c, nz) * (LAYOUT == 0 ? 1 : ny);
     }
     double r = 0.0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        const double *gx = g + (size_t)wrap_idx(ix - 1 + a, nx) * ny * nz;
         double rx = 0.0;
         // same summation order for both layouts (y innermost), so the result does not depend on
         // whether the caller supplied the transposition workspace
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int sy = LAYOUT == 0 ? nz : 1;
-            const double *gz = gx + (LAYOUT == 0 ? zi[c] : zi[c] * ny);
-            double ry = wy[0] * LDG(gz + yi[0] * sy);
-            ry = fma(wy[1], LDG(gz + yi[1] * sy), ry);
-            ry = fma(wy[2], LDG(gz + yi[2] * sy), ry);
-            ry = fma(wy[3], LDG(gz + yi[3] * sy), ry);
+            const int o = xo[a] + zo[c];
+            double ry = wy[0] * LDG(g + (o + yo[0]));
+            ry = fma(wy[1], LDG(g + (o + yo[1])), ry);
+            ry = fma(wy[2], LDG(g + (o + yo[2])), ry);
+            ry = fma(wy[3], LDG(g + (o + yo[3])), ry);
             rx = fma(wz[c], ry, rx);
         }
         r = fma(wx[a], rx, r);
