@@ -3,8 +3,8 @@
 Same step names and aliases (setup_calculation.py), same flags and precedence
 default < input file < command line (dbspm:216-231), same input files (SAMPLE/sample.npz,
 TIP/tip.npz, LABEL_*.npz) and the same output file names and `.npz` keys as the reference
-driver (dbspm:319-355, :468-620).  Steps that are not on the GPU path (sample tip grid vdw
-stm brstm) are refused with a message instead of being silently skipped: run those with
+driver (dbspm:319-355, :468-620, :644-667).  `brstm` (the tricubic gather at the relaxed tip
+positions) runs too; steps that are not on the GPU path (sample tip grid vdw stm) are refused with a message instead of being silently skipped: run those with
 the reference and point this program at their outputs.
 
 Multi-GPU: launch under torchrun (one process per GPU); sr/es shard by window z-slab and
@@ -40,6 +40,9 @@ def _parser() -> ArgumentParser:
     p.add_argument("-k", "--kappa", dest="K", type=float, help="Probe torsion spring constant. [eV/rad]")
     p.add_argument("-r", "--rpivot", dest="RPIVOT", type=float, help="Length of the probe lever. [Ang]")
     p.add_argument("--min-method", dest="MINMETHOD", type=str, help="Minimization method (only Powell).")
+    p.add_argument("-b", "--bias", action="store", type=float, default=0.5, help="STM bias (V) (brstm step).")
+    p.add_argument("-w", "--weight", action="store", type=float, default=0.5,
+                   help="weight of the s orbital in the BRSTM calculation.")
     return p
 
 
@@ -54,7 +57,7 @@ def _merge_params(options: Namespace, say) -> Namespace:
     merged = dict(default_params)
     merged.update(file_params)
     for k, v in vars(options).items():
-        if k != "steps" and v is not None:
+        if k not in ("steps", "bias", "weight") and v is not None:
             merged[k] = Path(v) if k in ("SAMPLE", "TIP") else v
     for k in default_params:
         src = "c" if getattr(options, k, None) is not None else ("i" if file_params.get(k) is not None else "d")
@@ -154,6 +157,26 @@ def main(argv=None) -> int:
                 relax_grid.set_density(key, res[key].cpu().numpy(), safe=False)
             relax_grid.save_density("E", "tip_x", "tip_y", "tip_z", filename=fname)
         steptime["relax"] = dt.now() - t0
+    if steps.brstm:
+        # dbspm:644-667: s/p-wave STM signal gathered at the relaxed tip-apex positions.  The stm file
+        # (stm_LABEL_V*.npz, written by the reference's `stm` step) and the relax file are read; the
+        # tricubic gather runs on the GPU.  zref comes from the stm file (the reference re-derives it
+        # from the CONTCAR through ASE).
+        if rank == 0:
+            from scipy.ndimage import gaussian_filter
+            from .grid import interpolate_data, read_grid
+            say("Calculating BRSTM image.")
+            t0 = dt.now()
+            rel_name = f"relax_{params.LABEL}_k{params.K:.4f}_a{params.ALPHA:.2f}_V{params.V:.2f}.npz"
+            say("Getting tip position from " + rel_name)
+            relax = read_grid(rel_name)
+            stm = read_grid(f"stm_{params.LABEL}_V{options.bias:.3f}.npz")
+            ws_, wp_ = options.weight, 1 - options.weight
+            stm.set_density("sp", ws_ * stm.s + gaussian_filter(wp_ * stm.p, sigma=2, mode="wrap"))
+            out = interpolate_data(relax, stm, "sp", params.RPIVOT)
+            out.save_density("data", filename=f"brstm_{params.LABEL}_V{options.bias:.3f}_ws{ws_:.2f}.npz")
+            say("BRSTM calculated.")
+            steptime["brstm"] = dt.now() - t0
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     t_end = dt.now()

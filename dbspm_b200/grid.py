@@ -113,6 +113,20 @@ class Grid:
         self.z = (self.z + self.zref) - zref
         self.zref = zref
 
+    def interpolate_density(self, grid, label):
+        """Tricubic resampling of `grid.<label>` onto this grid's points (pydbspm/grid.py:122-139,
+        used at dbspm:458 to bring the stride-2 vdW grid back to the full window): one gather kernel
+        launch over all points instead of a Python nditer loop over `interp.ip`."""
+        from .interactions import TricubicField
+
+        field = TricubicField(np.ascontiguousarray(getattr(grid, label), dtype=np.float64))
+        nz = len(self.z)
+        X = np.repeat(self.x[..., np.newaxis], nz, axis=2) - grid.x.min()
+        Y = np.repeat(self.y[..., np.newaxis], nz, axis=2) - grid.y.min()
+        Z = np.ones(tuple(int(v) for v in self.shape)) * self.z - grid.z.min()
+        pts = np.stack([X / grid.dr[0], Y / grid.dr[1], Z / grid.dr[2]], axis=-1)
+        self.set_density(label, field.gather(pts))
+
     def copy(self):
         return copy.deepcopy(self)
 

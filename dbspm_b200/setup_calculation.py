@@ -24,7 +24,7 @@ _ALIASES = {
 
 mpirequired = ["vdw", "relax"]
 #: steps this package runs on the GPU; the rest stay with the reference implementation
-gpu_steps = ("sr", "es", "relax")
+gpu_steps = ("sr", "es", "relax", "brstm")
 
 
 def setup_calc(words) -> Namespace:

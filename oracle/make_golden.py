@@ -127,8 +127,17 @@ def next_row_cases():
     F = rng.standard_normal((6, 5, 40))
     fs = RT.get_fs(F, dz=0.075, n=10)
     fs6 = RT.get_fs(F, dz=0.1, k0=1500.0, f0=25000.0, n=6)
+    # vdW-style upsample (grid.py:122-139): coarse stride grid -> fine window grid
+    coarse = RG.Grid(np.array([12, 10, 9]), cell=cell, span=np.diag([3.6, 3.0, 2.7]), origin=np.array([0.0, 0.0, 0.9]),
+                     zref=0.0, positions=np.zeros((1, 3)), numbers=np.array([6]))
+    cx, cy, cz = np.meshgrid(np.arange(12), np.arange(10), np.arange(9), indexing="ij")
+    vdw_c = -1.0 / (1.0 + 0.05 * ((cx - 5.5) ** 2 + (cy - 4.5) ** 2) + 0.3 * cz)
+    coarse.set_density("vdw", vdw_c)
+    fine = RG.Grid(np.array([24, 20, 12]), cell=cell, span=np.diag([3.6, 3.0, 1.8]), origin=np.array([0.0, 0.0, 1.2]),
+                   zref=0.0, positions=np.zeros((1, 3)), numbers=np.array([6]))
+    fine.interpolate_density(coarse, "vdw")
     np.savez_compressed(os.path.join(OUT, "nextrow_reference.npz"), sp=sp, cell=cell, tip=tip, interp=out.data,
-                        F=F, fs=fs, fs6=fs6)
+                        F=F, fs=fs, fs6=fs6, vdw_coarse=vdw_c, vdw_fine=fine.vdw)
     return {"interp_shape": list(out.data.shape), "rpivot": 0.3, "new_origin_z_index": 4}
 
 

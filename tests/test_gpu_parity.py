@@ -277,6 +277,35 @@ def test_cli_sr_es_relax_end_to_end(tmp_path, ops):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "dbspm"), "vdw", "-i", "input.in"], cwd=tmp_path,
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 2 and "reference" in r.stdout
+    # brstm step (dbspm:644-667): s/p-wave signal gathered at the relaxed tip positions just written
+    from scipy.ndimage import gaussian_filter
+    from dbspm_b200.grid import read_grid
+    rng = np.random.default_rng(3)
+    xx, yy, zz = np.meshgrid(np.arange(cfg.shape[0]), np.arange(cfg.shape[1]), np.arange(40), indexing="ij")
+    s_w = np.exp(-((xx - 13.0) ** 2 + (yy - 15.0) ** 2) / 60.0 - zz / 12.0)
+    p_w = 0.3 * np.exp(-((xx - 9.0) ** 2 + (yy - 19.0) ** 2) / 30.0 - zz / 9.0) + 1e-3 * rng.random(s_w.shape)
+    stm_grid = Grid(np.array([cfg.shape[0], cfg.shape[1], 40]), cell=cell, span=np.diag([cfg.cell[0], cfg.cell[1], 40 * dr[2]]),
+                    origin=np.array([0.0, 0.0, cfg.zref]), zref=cfg.zref, positions=pos, numbers=num)
+    stm_grid.set_density("s", s_w)
+    stm_grid.set_density("p", p_w)
+    stm_grid.save_density("s", "p", filename=str(tmp_path / "stm_tiny_V0.300.npz"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "dbspm"), "brstm", "-i", "input.in", "-b", "0.3", "-w", "0.6"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    br = np.load(tmp_path / "brstm_tiny_V0.300_ws0.60.npz")
+    assert br.files[0] == "data"
+    relax_g = read_grid(str(tmp_path / f"relax_tiny_k0.2000_a{cfg.alpha:.2f}_V0.50.npz"))
+    sp = 0.6 * s_w + gaussian_filter(0.4 * p_w, sigma=2, mode="wrap")
+    tc = O.Tricubic(sp)
+    nzr_ = relax_g.E.shape[2]
+    want_b = np.empty(relax_g.E.shape)
+    zoff = (relax_g.z - stm_grid.z.min()) / dr[2]
+    for i in range(0, cfg.shape[0], 5):
+        for j in range(0, cfg.shape[1], 7):
+            for k in range(nzr_):
+                want_b[i, j, k] = tc.ip([i + relax_g.tip_x[i, j, k] / dr[0], j + relax_g.tip_y[i, j, k] / dr[1],
+                                         zoff[k] + (relax_g.tip_z[i, j, k] + cfg.rpivot) / dr[2]])
+                assert abs(br["data"][i, j, k] - want_b[i, j, k]) <= 1e-11 * np.abs(sp).max(), (i, j, k)
 
 
 # ------------------------------------------------------------------------------------ next rows
@@ -315,6 +344,21 @@ def test_interpolate_data_matches_reference(ops, manifest):
     out = interpolate_data(new_grid, data_grid, "sp", rpivot=manifest["nextrow"]["rpivot"])
     assert list(out.data.shape) == manifest["nextrow"]["interp_shape"]
     assert np.abs(out.data - g["interp"]).max() <= 1e-12 * np.abs(g["interp"]).max()
+
+
+def test_interpolate_density_matches_reference(ops):
+    """vdW upsample (grid.py:122-139, dbspm:458): coarse stride grid -> window grid."""
+    from dbspm_b200.grid import Grid
+    g = np.load(os.path.join(ROOT, "tests", "golden", "nextrow_reference.npz"))
+    cell = g["cell"]
+    coarse = Grid(np.array([12, 10, 9]), cell=cell, span=np.diag([3.6, 3.0, 2.7]), origin=np.array([0.0, 0.0, 0.9]),
+                  zref=0.0, positions=np.zeros((1, 3)), numbers=np.array([6]))
+    coarse.set_density("vdw", g["vdw_coarse"])
+    fine = Grid(np.array([24, 20, 12]), cell=cell, span=np.diag([3.6, 3.0, 1.8]), origin=np.array([0.0, 0.0, 1.2]),
+                zref=0.0, positions=np.zeros((1, 3)), numbers=np.array([6]))
+    fine.interpolate_density(coarse, "vdw")
+    assert fine.vdw.shape == g["vdw_fine"].shape
+    assert np.abs(fine.vdw - g["vdw_fine"]).max() <= 1e-12 * np.abs(g["vdw_fine"]).max()
 
 
 def test_batched_parameter_sweep(ops):
