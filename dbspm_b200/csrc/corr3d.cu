@@ -1,6 +1,7 @@
 // corr3d.cu -- sm_100a kernels + C ABI for the sr / es interaction grids.
 // Replaces pydbspm/interactions.py:9-22 and the call sites dbspm:329-330, dbspm:348-349.
 // Kernel bodies live in corr_body.h (shared with the CPU emulation used by the tests).
+#include <cuda.h>
 #include <map>
 #include <mutex>
 #include "capi_common.h"
@@ -33,6 +34,24 @@ __global__ void __launch_bounds__(DBSPM_THREADS) zfused_kernel(const __grid_cons
 {
     extern __shared__ __align__(16) unsigned char smem[];
     zfused_body(P, smem, (long long)blockIdx.x, (int)threadIdx.x, (int)blockDim.x);
+}
+
+// TMA-fed persistent axis pass (axis_tma_body): no global load/store instructions in the block
+#ifndef AXIS3_THREADS
+#define AXIS3_THREADS 256
+#endif
+#ifndef AXIS3_MIN_BLOCKS
+#define AXIS3_MIN_BLOCKS 1
+#endif
+template <int D>
+__global__ void __launch_bounds__(AXIS3_THREADS, AXIS3_MIN_BLOCKS)
+axis_tma_kernel(const __grid_constant__ AxisTmaParams P, const __grid_constant__ CUtensorMap l0, const __grid_constant__ CUtensorMap s0,
+                const __grid_constant__ CUtensorMap l1, const __grid_constant__ CUtensorMap s1)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const void *lm[2] = {&l0, &l1};
+    const void *sm[2] = {&s0, &s1};
+    axis_tma_body<D>(P, lm, sm, smem, (long long)blockIdx.x, (long long)gridDim.x, (int)threadIdx.x, (int)blockDim.x);
 }
 
 #ifndef ZF2_PAIRS
@@ -107,6 +126,103 @@ static int pick_tshift(int n, long long inner)
     return axis_smem_bytes(n, 0) <= 227 * 1024 ? 0 : -1;
 }
 
+// ---- tensor maps for the TMA axis pass -----------------------------------------------------
+typedef CUresult (*TmapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static TmapEncodeFn tmap_encoder()
+{
+    static TmapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        cudaDriverEntryPointQueryResult q;
+        void *p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (TmapEncodeFn)p;
+    }
+    return fn;
+}
+
+// load map: (2*inner doubles, n_lo rows, n_hi row groups, outer slabs), box = (2T, n_lo, n_hi, 1): natural row order
+// store map: (2*inner, r_s, ..., r_1, outer) with the radix digits' natural global strides, box = (2T, r_s, ..., r_1, 1):
+//            tile row k_1*(n/r_1) + ... + k_s lands on global row k_1 + r_1*k_2 + ... (mixed-radix digit reversal)
+static bool make_axis_maps(TmapEncodeFn enc, const cplx *in, cplx *out, int n, long long inner, long long outer, int T,
+                           const FftPlanDev &pl, CUtensorMap *lmap, CUtensorMap *smap)
+{
+    int n_lo = 1;
+    for (int d = 256; d >= 1; --d)
+        if (n % d == 0) { n_lo = d; break; }
+    const int n_hi = n / n_lo;
+    if (n_hi > 256 || pl.nstages < 1 || pl.nstages > 3) return false;
+    const cuuint64_t rowb = (cuuint64_t)inner * 16;
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)(2 * inner), (cuuint64_t)n_lo, (cuuint64_t)n_hi, (cuuint64_t)outer};
+        cuuint64_t str[3] = {rowb, rowb * n_lo, rowb * n};
+        cuuint32_t box[4] = {(cuuint32_t)(2 * T), (cuuint32_t)n_lo, (cuuint32_t)n_hi, 1};
+        if (enc(lmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)in, dims, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    {
+        const int ns = pl.nstages;
+        cuuint64_t dims[5], str[4];
+        cuuint32_t box[5];
+        dims[0] = (cuuint64_t)(2 * inner); box[0] = (cuuint32_t)(2 * T);
+        // digit i (1-based) has global stride r_1*...*r_{i-1} rows; listed innermost-first as s, s-1, ..., 1
+        long long mult[4] = {1, 1, 1, 1};
+        for (int i = 1; i < ns; ++i) mult[i] = mult[i - 1] * pl.radix[i - 1];
+        for (int d = 1; d <= ns; ++d) {
+            const int i = ns - d;                       // digit index 0-based
+            dims[d] = (cuuint64_t)pl.radix[i]; box[d] = (cuuint32_t)pl.radix[i];
+            str[d - 1] = rowb * (cuuint64_t)mult[i];
+        }
+        dims[ns + 1] = (cuuint64_t)outer; box[ns + 1] = 1;
+        str[ns] = rowb * n;
+        if (enc(smap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)(ns + 2), (void *)out, dims, str, box, ones,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
+template <int D>
+static int launch_axis_tma(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, int narrays, double alpha0, double alpha1,
+                           int use_pow, int n, long long inner, long long outer, DevPlan *pl, cudaStream_t st, bool *done)
+{
+    *done = false;
+    TmapEncodeFn enc = tmap_encoder();
+    if (!enc || !axis_v2_ok(pl->host.dev) || pl->host.dev.nstages > 3) return DBSPM_OK;
+    if (2 * inner >= (1LL << 31) || outer >= (1LL << 31)) return DBSPM_OK;
+    const int ts = axis3_config(n, inner);
+    if (ts < 0) return DBSPM_OK;
+    AxisTmaParams P;
+    P.in[0] = in0; P.in[1] = in1; P.out[0] = out0; P.out[1] = out1;
+    P.alpha[0] = alpha0; P.alpha[1] = alpha1; P.use_pow = use_pow; P.narrays = narrays;
+    P.n = n; P.tshift = ts; P.inner = inner; P.outer = outer;
+    P.tiles = (inner + (1LL << ts) - 1) >> ts;
+    P.plan = pl->host.dev; P.tw = pl->tw; P.freq_of = pl->freq_of;
+    CUtensorMap lm[2], sm[2];
+    for (int a = 0; a < 2; ++a) {
+        const int w = a < narrays ? a : 0;
+        if (!make_axis_maps(enc, w == 0 ? in0 : in1, w == 0 ? out0 : out1, n, inner, outer, 1 << ts, P.plan, &lm[a], &sm[a]))
+            return DBSPM_OK;                 // fall back to the register-staged kernel
+    }
+    const size_t smem = axis3_smem_bytes(n, ts);
+    const long long total = (long long)narrays * outer * P.tiles;
+    long long nblocks = 148LL * (smem <= 113 * 1024 ? 2 : 1);
+    if (nblocks > total) nblocks = total;
+    DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    axis_tma_kernel<D><<<(unsigned)nblocks, AXIS3_THREADS, smem, st>>>(P, lm[0], sm[0], lm[1], sm[1]);
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    *done = true;
+    return DBSPM_OK;
+}
+
 template <int D>
 static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, int narrays,
                        double alpha0, double alpha1, int use_pow, int n, long long inner, long long outer,
@@ -120,6 +236,11 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     P.alpha[0] = alpha0; P.alpha[1] = alpha1;
     P.use_pow = use_pow; P.narrays = narrays;
     P.n = n; P.inner = inner; P.outer = outer;
+    if ((flags & DBSPM_CORR_USE_TMA) && !(flags & DBSPM_CORR_AXIS_V1)) {
+        bool done = false;
+        rc = launch_axis_tma<D>(in0, out0, in1, out1, narrays, alpha0, alpha1, use_pow, n, inner, outer, pl, st, &done);
+        if (rc || done) return rc;
+    }
     P.plan = pl->host.dev; P.tw = pl->tw; P.pos_of = pl->pos_of; P.freq_of = pl->freq_of;
     P.v2 = axis_v2_ok(P.plan) && !(flags & DBSPM_CORR_AXIS_V1);
     P.tw_smem = 0;

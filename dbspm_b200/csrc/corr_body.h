@@ -272,6 +272,183 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
 }
 
 // ------------------------------------------------------------------------------------------
+// v3 of the strided-axis pass: TMA-fed persistent blocks.  Each block walks over its share of the
+// tiles with a ring of NBUF shared-memory buffers.  One thread issues
+//   - a tensor-map LOAD (cp.async.bulk.tensor, completion on an mbarrier) of the whole n x T tile
+//     for the tile NBUF-1 steps ahead, and
+//   - after the in-place FFT, ONE tensor-map STORE whose box dimensions are the radix digits in
+//     reversed order with their natural global strides: the TMA unit performs the mixed-radix
+//     digit reversal (tile row k1*(n/r1)+...+ks  ->  global row k1 + r1*k2 + ...) on the fly.
+// No global load/store instruction, no register staging and no L1 traffic is left in the block;
+// the FFT stages run on shared memory while the loads of the next two tiles and the store of
+// the previous one are in flight.  On the host (tests/emu) the same body runs with the two TMA
+// operations emulated by plain copies, so tile bookkeeping and stage order are still checked.
+// ------------------------------------------------------------------------------------------
+#ifndef AXIS3_NBUF
+#define AXIS3_NBUF 3
+#endif
+#ifndef AXIS3_MAX_SMEM
+#define AXIS3_MAX_SMEM (225 * 1024)
+#endif
+
+template <int D>
+HD void fft_stages_from(cplx *s, int ld, int tshift, const FftPlanDev &pl, int first, const cplx *tw, int tid, int nthr);
+
+struct AxisTmaParams {
+    const cplx *in[2];        // used by the host emulation only (the device goes through tensor maps)
+    cplx *out[2];
+    double alpha[2];
+    int use_pow;
+    int narrays;
+    int n;
+    int tshift;               // T = 1 << tshift lines per tile
+    long long inner;
+    long long outer;
+    long long tiles;          // tiles per (array, slab) = ceil(inner / T)
+    FftPlanDev plan;
+    const cplx *tw;
+    const int *freq_of;       // host emulation of the permuting store
+};
+
+HD size_t axis3_tile_bytes(int n, int tshift) { return ((size_t)n << tshift) * 16; }
+HD size_t axis3_smem_bytes(int n, int tshift)
+{
+    return AXIS3_NBUF * axis3_tile_bytes(n, tshift) + (size_t)n * 16 + AXIS3_NBUF * 8 + 128;
+}
+// widest tile (8,4,2,1 lines) whose ring fits; -1 if even one line does not
+HD int axis3_config(int n, long long inner)
+{
+    for (int ts = 3; ts >= 0; --ts) {
+        if ((1LL << ts) > 2 * inner && ts > 0) continue;
+        if (axis3_smem_bytes(n, ts) <= AXIS3_MAX_SMEM) return ts;
+    }
+    return -1;
+}
+
+#if defined(__CUDA_ARCH__)
+HD unsigned axis3_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+#endif
+
+// tensor-map arguments: lmap/smap point at CUtensorMap objects in kernel parameter space
+template <int D>
+HD void axis_tma_body(const AxisTmaParams &P, const void *const *lmaps, const void *const *smaps,
+                      unsigned char *smem_raw, long long bid, long long nblocks, int tid, int nthr)
+{
+    const int n = P.n, T = 1 << P.tshift;
+    const size_t tile_bytes = axis3_tile_bytes(n, P.tshift);
+    // 128-byte aligned ring of tiles, then the twiddle table, then the mbarriers
+    unsigned char *base = (unsigned char *)(((size_t)smem_raw + 127) & ~(size_t)127);
+    cplx *tw = (cplx *)(base + AXIS3_NBUF * tile_bytes);
+    unsigned long long *mbar = (unsigned long long *)(tw + n);
+    const long long per_array = P.outer * P.tiles;
+    const long long total = per_array * P.narrays;
+    const long long mine = bid < total ? (total - bid + nblocks - 1) / nblocks : 0;
+
+    for (int e = tid; e < n; e += nthr) tw[e] = ldg_c(P.tw + e);
+#if defined(__CUDA_ARCH__)
+    if (tid == 0) {
+        for (int b = 0; b < AXIS3_NBUF; ++b)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(axis3_smem_u32(mbar + b)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
+    BLOCK_SYNC();
+
+    // issue the load of my i-th tile into ring slot i % NBUF
+    auto issue_load = [&](long long i) {
+        const long long t = bid + i * nblocks;
+        const int which = (int)(t / per_array);
+        const long long r = t - which * per_array;
+        const long long o = r / P.tiles, tile = r - o * P.tiles;
+        cplx *dst = (cplx *)(base + (size_t)(i % AXIS3_NBUF) * tile_bytes);
+#if defined(__CUDA_ARCH__)
+        const unsigned bar = axis3_smem_u32(mbar + (i % AXIS3_NBUF));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)tile_bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                     ::"r"(axis3_smem_u32(dst)), "l"(lmaps[which]), "r"((int)(tile << (P.tshift + 1))), "r"(0), "r"(0), "r"((int)o), "r"(bar)
+                     : "memory");
+#else
+        (void)lmaps;
+        const cplx *src = P.in[which] + (size_t)o * n * P.inner + (tile << P.tshift);
+        const int tcount = (int)((P.inner - (tile << P.tshift)) < T ? (P.inner - (tile << P.tshift)) : T);
+        for (int row = 0; row < n; ++row)
+            for (int c = 0; c < T; ++c) dst[(size_t)row * T + c] = c < tcount ? src[(size_t)row * P.inner + c] : cmake(0.0, 0.0);
+#endif
+    };
+
+    if (tid == 0)
+        for (long long i = 0; i < AXIS3_NBUF - 1 && i < mine; ++i) issue_load(i);
+
+    for (long long i = 0; i < mine; ++i) {
+        const long long t = bid + i * nblocks;
+        const int which = (int)(t / per_array);
+        const long long r = t - which * per_array;
+        const long long o = r / P.tiles, tile = r - o * P.tiles;
+        cplx *s = (cplx *)(base + (size_t)(i % AXIS3_NBUF) * tile_bytes);
+        if (tid == 0 && i + AXIS3_NBUF - 1 < mine) {
+#if defined(__CUDA_ARCH__)
+            // the slot being refilled was stored in the previous iteration: wait until that store has read it
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+            issue_load(i + AXIS3_NBUF - 1);
+        }
+#if defined(__CUDA_ARCH__)
+        {
+            const unsigned bar = axis3_smem_u32(mbar + (i % AXIS3_NBUF));
+            const unsigned parity = (unsigned)((i / AXIS3_NBUF) & 1);
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        }
+#endif
+        const double alpha = P.alpha[which];
+        if (P.use_pow && alpha != 1.0) {
+            const int total_e = n << P.tshift;
+            for (int idx = tid; idx < total_e; idx += nthr) {
+                cplx v = s[idx];
+                v.x = pow_nonneg(v.x, alpha);
+                v.y = pow_nonneg(v.y, alpha);
+                s[idx] = v;
+            }
+            BLOCK_SYNC();
+        }
+        fft_stages_from<D>(s, T, P.tshift, P.plan, 0, tw, tid, nthr);  // ends with a block barrier
+#if defined(__CUDA_ARCH__)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA unit
+        BLOCK_SYNC();
+        if (tid == 0) {
+            const int c0 = (int)(tile << (P.tshift + 1));
+            const int ns = P.plan.nstages;
+            const void *sm = smaps[which];
+            const unsigned src = axis3_smem_u32(s);
+            if (ns == 1)
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                             ::"l"(sm), "r"(c0), "r"(0), "r"((int)o), "r"(src) : "memory");
+            else if (ns == 2)
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                             ::"l"(sm), "r"(c0), "r"(0), "r"(0), "r"((int)o), "r"(src) : "memory");
+            else
+                asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                             ::"l"(sm), "r"(c0), "r"(0), "r"(0), "r"(0), "r"((int)o), "r"(src) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+#else
+        (void)smaps;
+        {
+            cplx *dst = P.out[which] + (size_t)o * n * P.inner + (tile << P.tshift);
+            const int tcount = (int)((P.inner - (tile << P.tshift)) < T ? (P.inner - (tile << P.tshift)) : T);
+            for (int p = 0; p < n; ++p)
+                for (int c = 0; c < tcount; ++c) dst[(size_t)P.freq_of[p] * P.inner + c] = s[(size_t)p * T + c];
+        }
+#endif
+    }
+#if defined(__CUDA_ARCH__)
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before the block exits
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
 // Fused z kernel.  One block = ZL line pairs {p=(kx,ky), m=(-kx,-ky)}; per pair 4 lines
 // (A_p, A_m, B_p, B_m) of n = Nz/2 complex go through a forward FFT; the untangle + product
 // + window phase + first inverse radix-2 split produce 2 lines (spectra of the packed window

@@ -36,6 +36,23 @@ static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, in
     AxisParams P;
     P.in[0] = in0; P.in[1] = in1; P.out[0] = out0; P.out[1] = out1;
     P.alpha[0] = a0; P.alpha[1] = a1; P.use_pow = use_pow; P.narrays = narrays;
+    if (force_tshift >= 200 && (!axis_v2_ok(hp.dev) || hp.dev.nstages > 3)) force_tshift = -1;   // launcher falls back too
+    if (force_tshift >= 200) {
+        // TMA-fed persistent body (axis_tma_body) with the two TMA operations emulated by copies;
+        // 200 = auto tile width, 201.. = forced tshift; three "persistent blocks" walk the tiles
+        AxisTmaParams Q;
+        Q.in[0] = in0; Q.in[1] = in1; Q.out[0] = out0; Q.out[1] = out1;
+        Q.alpha[0] = a0; Q.alpha[1] = a1; Q.use_pow = use_pow; Q.narrays = narrays;
+        Q.n = n; Q.inner = inner; Q.outer = outer;
+        Q.tshift = force_tshift > 200 ? force_tshift - 201 : axis3_config(n, inner);
+        Q.tiles = (inner + (1LL << Q.tshift) - 1) >> Q.tshift;
+        Q.plan = hp.dev; Q.tw = hp.tw.data(); Q.freq_of = hp.freq_of.data();
+        // in-place passes (in == out): a real block reads its tile before storing it and tiles are disjoint,
+        // so the serial emulation is faithful
+        std::vector<unsigned char> sm3(axis3_smem_bytes(n, Q.tshift) + 256);
+        for (long long b = 0; b < 3; ++b) axis_tma_body<D>(Q, nullptr, nullptr, sm3.data(), b, 3, 0, 1);
+        return 0;
+    }
     P.n = n; P.inner = inner; P.outer = outer;
     P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data(); P.freq_of = hp.freq_of.data();
     // same selection as launch_axis() in corr3d.cu; force_tshift >= 100 selects the v1 body
@@ -93,7 +110,7 @@ extern "C" int emu_corr3d_f64(const double *A, const double *B, double alphaA, d
         P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data(); P.freq_of = hp.freq_of.data(); P.twN = hpN.tw.data();
         P.npairs = (long long)(nx / 2 + 1) * ny;
         // same selection as dbspm_corr3d_f64: v2 (4 pairs / block) when the plan is all fast radices
-        const bool v2 = axis_v2_ok(P.plan) && force_tshift < 100;
+        const bool v2 = axis_v2_ok(P.plan) && (force_tshift < 100 || force_tshift >= 200);
         std::vector<unsigned char> smem((v2 ? zfused2_smem_bytes<4>(n) : zfused_smem_bytes(n)) + 64);
         unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
         if (v2) for (long long b = 0; b < 3; ++b) zfused_body_v2<4>(P, sm, b, 3, 0, 1);   // 3 persistent blocks

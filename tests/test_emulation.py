@@ -65,8 +65,9 @@ def test_corr3d_edge_shapes_all_tile_widths(emu, shape, window):
     a, b = rng.random(shape), rng.random(shape) - 0.4
     dr = np.array([0.1, 0.2, 0.3])
     ref = O.density_overlap_fft(a, b, dr)[:, :, window[0]:window[1]]
-    # -1/0/1/2: register-first/last body with auto/forced tile width; 100+: the all-in-smem body
-    for tshift in (-1, 0, 1, 2, 100, 101, 103):
+    # -1/0/1/2: register-first/last body with auto/forced tile width; 100+: the all-in-smem body;
+    # 200+: the TMA-fed persistent body (loads/stores emulated by copies)
+    for tshift in (-1, 0, 1, 2, 100, 101, 103, 200, 201, 203):
         got = emu.corr3d(a, b, dr, *window, tshift=tshift)
         assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, window, tshift)
 

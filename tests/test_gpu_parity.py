@@ -59,6 +59,26 @@ def test_overlap_edge_shapes(ops, shape, window):
     assert _rel(got, ref) <= 1e-9
 
 
+@pytest.mark.parametrize("flags", [0, 1 << 1, 1 << 2])
+def test_overlap_kernel_variants_agree(ops, overlap_golden, manifest, flags):
+    """default (register-first/last) axis pass, all-in-shared-memory variant (1<<1) and the TMA-fed
+    persistent variant (1<<2: tensor-map load + digit-reversing tensor-map store) give the reference's answer."""
+    g = overlap_golden
+    for case in manifest["overlap"]:
+        i, alpha = case["idx"], case["alpha"]
+        a, b, dr, ref = g[f"a{i}"], g[f"b{i}"], g[f"dr{i}"], g[f"E{i}"]
+        nz = a.shape[2]
+        for z_lo, z_hi in [(0, nz), (3, 8), (2, 9)]:
+            win = ops.density_overlap_window(a, b, dr, z_lo, z_hi, alpha, alpha, flags=flags)
+            assert np.abs(win - ref[:, :, z_lo:z_hi]).max() <= 1e-9 * np.abs(ref).max(), (case, flags)
+    rng = np.random.default_rng(5)
+    for shape in [(196, 50, 24), (96, 120, 10), (1024, 6, 8)]:        # n = 196 (4*7*7), 120 (3*5*8), 1024 (16*8*8)
+        a, b = rng.random(shape), rng.random(shape) - 0.5
+        ref = O.density_overlap_fft(a, b, np.ones(3))
+        got = ops.density_overlap_window(a, b, np.ones(3), flags=flags)
+        assert _rel(got, ref) <= 1e-9, (shape, flags)
+
+
 def test_overlap_tiny_config_sr_es(ops, overlap_golden):
     from dbspm_b200 import synth
     cfg = synth.CONFIGS["tiny"]
