@@ -184,9 +184,9 @@ HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gi
                 const cplx w = tw[j * k];
                 v[k] = D < 0 ? cmul(v[k], w) : cmulc(v[k], w);
             }
-            cplx *dst = s + ((size_t)j << P.tshift) + t;
+            cplx *dst = s + ((j << P.tshift) + t);
 #pragma unroll
-            for (int k = 0; k < R; ++k) dst[((size_t)k * q) << P.tshift] = v[k];
+            for (int k = 0; k < R; ++k) dst[(k * q) << P.tshift] = v[k];
         }
     }
 }
@@ -198,10 +198,10 @@ HD void axis2_last(const AxisParams &P, const cplx *s, cplx *gout, int tcount, i
     const int total = nb << P.tshift;
     for (int idx = tid; idx < total; idx += nthr) {
         const int t = idx & tmask, blk = idx >> P.tshift;
-        const cplx *src = s + ((size_t)(blk * R) << P.tshift) + t;
+        const cplx *src = s + (((blk * R) << P.tshift) + t);
         cplx v[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) v[k] = src[(size_t)k << P.tshift];
+        for (int k = 0; k < R; ++k) v[k] = src[k << P.tshift];
         bfly<R, D>(v);
         if (t < tcount) {
             const int K0 = LDG(P.freq_of + blk * R);           // frequency held by position blk*R
@@ -627,9 +627,9 @@ HD void zfused2_first(const ZFusedParams &P, cplx *U, const cplx *tw, const int 
                 v[k] = D < 0 ? cmul(v[k], w) : cmulc(v[k], w);
             }
         }
-        cplx *dst = U + (size_t)j * LDF + line;
+        cplx *dst = U + (j * LDF + line);
 #pragma unroll
-        for (int k = 0; k < R; ++k) dst[(size_t)k * q * LDF] = v[k];
+        for (int k = 0; k < R; ++k) dst[k * q * LDF] = v[k];
     }
 }
 
@@ -717,8 +717,8 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
         const int k = freq_of[p];
         const int ks = k == 0 ? 0 : n - k;
         const int ps = pos_of[ks];
-        const cplx *Uk = U + (size_t)p * LDF + 4 * l;
-        const cplx *Us = U + (size_t)ps * LDF + 4 * l;
+        const cplx *Uk = U + (p * LDF + 4 * l);
+        const cplx *Us = U + (ps * LDF + 4 * l);
         const cplx w = twh[k];                                    // exp(-2 pi i k / nz)
         const cplx miw = cmake(w.y, -w.x);                        // -i * w
         const cplx a1 = Uk[0], a2 = cconj(Us[1]);
@@ -735,8 +735,8 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
         const cplx G1 = cadd(plo, phi);
         const cplx G2 = cmulc(csub(plo, phi), w);                 // * e^{+2 pi i k / nz}
         // S_p[k] = G1 + i G2 ; S_m[k*] = conj(G1[k]) + i conj(G2[k])
-        S[(size_t)p * LDI + 2 * l] = cmake(G1.x - G2.y, G1.y + G2.x);
-        S[(size_t)ps * LDI + 2 * l + 1] = cmake(G1.x + G2.y, -G1.y + G2.x);
+        S[p * LDI + 2 * l] = cmake(G1.x - G2.y, G1.y + G2.x);
+        S[ps * LDI + 2 * l + 1] = cmake(G1.x + G2.y, -G1.y + G2.x);
     }
     BLOCK_SYNC();
     fft_tile_t<1>(S, LDI, TSI, P.plan, tw, tid, nthr);
@@ -747,7 +747,7 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
         const int *pi = pinfo + 6 * l;
         if (!pi[4] || (role == 1 && pi[5])) continue;
         const int x = role ? pi[2] : pi[0], y = role ? pi[3] : pi[1];
-        st_stream(P.W + ((size_t)x * P.ny + y) * P.nwh + j, S[(size_t)j * LDI + line]);
+        st_stream(P.W + ((size_t)x * P.ny + y) * P.nwh + j, S[j * LDI + line]);
     }
     BLOCK_SYNC();                              // S and pinfo are rewritten by the next group
     }

@@ -162,8 +162,8 @@ HD void fft_stage(cplx *s, int ld, int tshift, int n, int m, const cplx *tw, int
         const int b = idx >> tshift;
         const int blk = b / q;
         const int j = b - blk * q;
-        cplx *p = s + (size_t)(blk * m + j) * ld + t;
-        const size_t step = (size_t)q * ld;
+        cplx *p = s + ((blk * m + j) * ld + t);          // 32-bit index: tiles are far below 2^31 elements
+        const int step = q * ld;
         cplx v[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = p[k * step];
@@ -196,8 +196,8 @@ HD void fft_stage_generic(cplx *s, int ld, int tshift, int n, int m, int r, cons
         const int b = idx >> tshift;
         const int blk = b / q;
         const int j = b - blk * q;
-        cplx *p = s + (size_t)(blk * m + j) * ld + t;
-        const size_t step = (size_t)q * ld;
+        cplx *p = s + ((blk * m + j) * ld + t);          // 32-bit index: tiles are far below 2^31 elements
+        const int step = q * ld;
         cplx v[DBSPM_MAX_RADIX], o[DBSPM_MAX_RADIX];
         for (int k = 0; k < r; ++k) v[k] = p[k * step];
         for (int k = 0; k < r; ++k) {
@@ -234,8 +234,8 @@ HD void fft_stage_t(cplx *s, int ld, int tshift, int n, int m, const cplx *tw, i
         const int b = idx >> tshift;
         const int blk = b / q;
         const int j = b - blk * q;
-        cplx *p = s + (size_t)(blk * m + j) * ld + t;
-        const size_t step = (size_t)q * ld;
+        cplx *p = s + ((blk * m + j) * ld + t);          // 32-bit index: tiles are far below 2^31 elements
+        const int step = q * ld;
         cplx v[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = p[k * step];
