@@ -37,9 +37,10 @@ __global__ void __launch_bounds__(DBSPM_THREADS) zfused_kernel(const __grid_cons
 }
 
 // TMA-fed persistent axis pass (axis_tma_body): no global load/store instructions in the block
-#ifndef AXIS3_THREADS
-#define AXIS3_THREADS 256
+#ifndef AXIS3_L2_PROMOTION
+#define AXIS3_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_NONE
 #endif
+#define AXIS3_THREADS AXIS3_BLOCK_THREADS   /* consumer groups + producer warp (corr_body.h) */
 #ifndef AXIS3_MIN_BLOCKS
 #define AXIS3_MIN_BLOCKS 1
 #endif
@@ -164,7 +165,7 @@ static bool make_axis_maps(TmapEncodeFn enc, const cplx *in, cplx *out, int n, l
         cuuint64_t str[3] = {rowb, rowb * n_lo, rowb * n};
         cuuint32_t box[4] = {(cuuint32_t)(2 * T), (cuuint32_t)n_lo, (cuuint32_t)n_hi, 1};
         if (enc(lmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)in, dims, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                CU_TENSOR_MAP_SWIZZLE_NONE, AXIS3_L2_PROMOTION, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return false;
     }
     {
@@ -236,7 +237,11 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     P.alpha[0] = alpha0; P.alpha[1] = alpha1;
     P.use_pow = use_pow; P.narrays = narrays;
     P.n = n; P.inner = inner; P.outer = outer;
-    if ((flags & DBSPM_CORR_USE_TMA) && !(flags & DBSPM_CORR_AXIS_V1)) {
+    // path picked per shape: the TMA-fed persistent kernel wins where a ring of three 8-line tiles fits
+    // (256 <= n <= 576: measured 27 % faster at n = 384); the register-staged kernel wins at n = 1024
+    // (4-line tiles, FP64/shared-memory bound) and ties below 256
+    const bool tma_auto = n >= 256 && axis3_config(n, inner) == 3;
+    if (((flags & DBSPM_CORR_USE_TMA) || (tma_auto && !(flags & DBSPM_CORR_NO_TMA))) && !(flags & DBSPM_CORR_AXIS_V1)) {
         bool done = false;
         rc = launch_axis_tma<D>(in0, out0, in1, out1, narrays, alpha0, alpha1, use_pow, n, inner, outer, pl, st, &done);
         if (rc || done) return rc;

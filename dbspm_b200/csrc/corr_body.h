@@ -313,7 +313,7 @@ struct AxisTmaParams {
 HD size_t axis3_tile_bytes(int n, int tshift) { return ((size_t)n << tshift) * 16; }
 HD size_t axis3_smem_bytes(int n, int tshift)
 {
-    return AXIS3_NBUF * axis3_tile_bytes(n, tshift) + (size_t)n * 16 + AXIS3_NBUF * 8 + 128;
+    return AXIS3_NBUF * axis3_tile_bytes(n, tshift) + (size_t)n * 16 + 2 * AXIS3_NBUF * 8 + 128;
 }
 // widest tile (8,4,2,1 lines) whose ring fits; -1 if even one line does not
 HD int axis3_config(int n, long long inner)
@@ -329,17 +329,66 @@ HD int axis3_config(int n, long long inner)
 HD unsigned axis3_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 #endif
 
-// tensor-map arguments: lmap/smap point at CUtensorMap objects in kernel parameter space
+// Warp-specialised layout of the block: AXIS3_GROUPS consumer groups of AXIS3_GROUP_THREADS threads
+// (each group runs the FFT of one tile, so two tiles are in compute at any time) followed by one
+// producer warp whose lane 0 issues the tensor-map loads.  full[b] / empty[b] mbarriers per ring slot.
+#ifndef AXIS3_GROUPS
+#define AXIS3_GROUPS 2
+#endif
+#ifndef AXIS3_GROUP_THREADS
+#define AXIS3_GROUP_THREADS 192
+#endif
+#define AXIS3_BLOCK_THREADS (AXIS3_GROUPS * AXIS3_GROUP_THREADS + 32)
+
+#if defined(__CUDA_ARCH__)
+#define GROUP_SYNC(id, n) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory")
+#else
+#define GROUP_SYNC(id, n) ((void)0)
+#endif
+
+// all DIF stages on a tile, synchronising only the `nthr` threads of one consumer group (named barrier)
+template <int D>
+HD void fft_stages_group(cplx *s, int ld, int tshift, const FftPlanDev &pl, const cplx *tw, int tid, int nthr, int bar_id)
+{
+    int m = pl.n;
+    for (int st = 0; st < pl.nstages; ++st) {
+        const int r = pl.radix[st];
+        switch (r) {
+        case 2: fft_stage<2, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 3: fft_stage<3, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 4: fft_stage<4, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 5: fft_stage<5, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 7: fft_stage<7, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        case 8: fft_stage<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        default: fft_stage<16, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
+        }
+        m /= r;
+        GROUP_SYNC(bar_id, nthr);
+    }
+}
+
+#if defined(__CUDA_ARCH__)
+HD void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+#endif
+
+// tensor-map arguments: lmaps/smaps point at CUtensorMap objects in kernel parameter space.
+// Device: called by all AXIS3_BLOCK_THREADS threads (tid = threadIdx.x).  Host emulation: tid = 0, nthr = 1.
 template <int D>
 HD void axis_tma_body(const AxisTmaParams &P, const void *const *lmaps, const void *const *smaps,
                       unsigned char *smem_raw, long long bid, long long nblocks, int tid, int nthr)
 {
     const int n = P.n, T = 1 << P.tshift;
     const size_t tile_bytes = axis3_tile_bytes(n, P.tshift);
-    // 128-byte aligned ring of tiles, then the twiddle table, then the mbarriers
     unsigned char *base = (unsigned char *)(((size_t)smem_raw + 127) & ~(size_t)127);
     cplx *tw = (cplx *)(base + AXIS3_NBUF * tile_bytes);
-    unsigned long long *mbar = (unsigned long long *)(tw + n);
+    unsigned long long *full = (unsigned long long *)(tw + n);
+    unsigned long long *empty = full + AXIS3_NBUF;
     const long long per_array = P.outer * P.tiles;
     const long long total = per_array * P.narrays;
     const long long mine = bid < total ? (total - bid + nblocks - 1) / nblocks : 0;
@@ -347,77 +396,64 @@ HD void axis_tma_body(const AxisTmaParams &P, const void *const *lmaps, const vo
     for (int e = tid; e < n; e += nthr) tw[e] = ldg_c(P.tw + e);
 #if defined(__CUDA_ARCH__)
     if (tid == 0) {
-        for (int b = 0; b < AXIS3_NBUF; ++b)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(axis3_smem_u32(mbar + b)));
+        for (int b = 0; b < AXIS3_NBUF; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(axis3_smem_u32(full + b)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(axis3_smem_u32(empty + b)));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 #endif
     BLOCK_SYNC();
 
-    // issue the load of my i-th tile into ring slot i % NBUF
-    auto issue_load = [&](long long i) {
+#if defined(__CUDA_ARCH__)
+    const int group = tid / AXIS3_GROUP_THREADS;               // AXIS3_GROUPS = producer warp
+    if (group >= AXIS3_GROUPS) {
+        // ---------------- producer: one lane streams the tiles into the ring ----------------
+        if ((tid & 31) == 0) {
+            for (long long i = 0; i < mine; ++i) {
+                const int slot = (int)(i % AXIS3_NBUF);
+                if (i >= AXIS3_NBUF) mbar_wait(axis3_smem_u32(empty + slot), (unsigned)(((i / AXIS3_NBUF) - 1) & 1));
+                const long long t = bid + i * nblocks;
+                const int which = (int)(t / per_array);
+                const long long r = t - which * per_array;
+                const long long o = r / P.tiles, tile = r - o * P.tiles;
+                const unsigned bar = axis3_smem_u32(full + slot);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)tile_bytes) : "memory");
+                asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                             ::"r"(axis3_smem_u32(base + (size_t)slot * tile_bytes)), "l"(lmaps[which]),
+                               "r"((int)(tile << (P.tshift + 1))), "r"(0), "r"(0), "r"((int)o), "r"(bar)
+                             : "memory");
+            }
+        }
+        return;
+    }
+    // ---------------- consumers: group g takes my tiles g, g + GROUPS, ... ----------------------
+    const int gtid = tid - group * AXIS3_GROUP_THREADS;
+    const int gn = AXIS3_GROUP_THREADS;
+    const int bar_id = 1 + group;
+    for (long long i = group; i < mine; i += AXIS3_GROUPS) {
+        const int slot = (int)(i % AXIS3_NBUF);
         const long long t = bid + i * nblocks;
         const int which = (int)(t / per_array);
         const long long r = t - which * per_array;
         const long long o = r / P.tiles, tile = r - o * P.tiles;
-        cplx *dst = (cplx *)(base + (size_t)(i % AXIS3_NBUF) * tile_bytes);
-#if defined(__CUDA_ARCH__)
-        const unsigned bar = axis3_smem_u32(mbar + (i % AXIS3_NBUF));
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)tile_bytes) : "memory");
-        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                     ::"r"(axis3_smem_u32(dst)), "l"(lmaps[which]), "r"((int)(tile << (P.tshift + 1))), "r"(0), "r"(0), "r"((int)o), "r"(bar)
-                     : "memory");
-#else
-        (void)lmaps;
-        const cplx *src = P.in[which] + (size_t)o * n * P.inner + (tile << P.tshift);
-        const int tcount = (int)((P.inner - (tile << P.tshift)) < T ? (P.inner - (tile << P.tshift)) : T);
-        for (int row = 0; row < n; ++row)
-            for (int c = 0; c < T; ++c) dst[(size_t)row * T + c] = c < tcount ? src[(size_t)row * P.inner + c] : cmake(0.0, 0.0);
-#endif
-    };
-
-    if (tid == 0)
-        for (long long i = 0; i < AXIS3_NBUF - 1 && i < mine; ++i) issue_load(i);
-
-    for (long long i = 0; i < mine; ++i) {
-        const long long t = bid + i * nblocks;
-        const int which = (int)(t / per_array);
-        const long long r = t - which * per_array;
-        const long long o = r / P.tiles, tile = r - o * P.tiles;
-        cplx *s = (cplx *)(base + (size_t)(i % AXIS3_NBUF) * tile_bytes);
-        if (tid == 0 && i + AXIS3_NBUF - 1 < mine) {
-#if defined(__CUDA_ARCH__)
-            // the slot being refilled was stored in the previous iteration: wait until that store has read it
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-#endif
-            issue_load(i + AXIS3_NBUF - 1);
-        }
-#if defined(__CUDA_ARCH__)
-        {
-            const unsigned bar = axis3_smem_u32(mbar + (i % AXIS3_NBUF));
-            const unsigned parity = (unsigned)((i / AXIS3_NBUF) & 1);
-            unsigned done = 0;
-            while (!done)
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        }
-#endif
+        cplx *s = (cplx *)(base + (size_t)slot * tile_bytes);
+        mbar_wait(axis3_smem_u32(full + slot), (unsigned)((i / AXIS3_NBUF) & 1));
         const double alpha = P.alpha[which];
         if (P.use_pow && alpha != 1.0) {
             const int total_e = n << P.tshift;
-            for (int idx = tid; idx < total_e; idx += nthr) {
+            for (int idx = gtid; idx < total_e; idx += gn) {
                 cplx v = s[idx];
                 v.x = pow_nonneg(v.x, alpha);
                 v.y = pow_nonneg(v.y, alpha);
                 s[idx] = v;
             }
-            BLOCK_SYNC();
+            GROUP_SYNC(bar_id, gn);
         }
-        fft_stages_from<D>(s, T, P.tshift, P.plan, 0, tw, tid, nthr);  // ends with a block barrier
-#if defined(__CUDA_ARCH__)
+        fft_stages_group<D>(s, T, P.tshift, P.plan, tw, gtid, gn, bar_id);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA unit
-        BLOCK_SYNC();
-        if (tid == 0) {
+        GROUP_SYNC(bar_id, gn);
+        if (gtid == 0) {
             const int c0 = (int)(tile << (P.tshift + 1));
             const int ns = P.plan.nstages;
             const void *sm = smaps[which];
@@ -432,19 +468,32 @@ HD void axis_tma_body(const AxisTmaParams &P, const void *const *lmaps, const vo
                 asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
                              ::"l"(sm), "r"(c0), "r"(0), "r"(0), "r"(0), "r"((int)o), "r"(src) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the TMA unit has read the slot
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(axis3_smem_u32(empty + slot)) : "memory");
         }
-#else
-        (void)smaps;
-        {
-            cplx *dst = P.out[which] + (size_t)o * n * P.inner + (tile << P.tshift);
-            const int tcount = (int)((P.inner - (tile << P.tshift)) < T ? (P.inner - (tile << P.tshift)) : T);
-            for (int p = 0; p < n; ++p)
-                for (int c = 0; c < tcount; ++c) dst[(size_t)P.freq_of[p] * P.inner + c] = s[(size_t)p * T + c];
-        }
-#endif
     }
-#if defined(__CUDA_ARCH__)
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before the block exits
+    if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before the block exits
+#else
+    // ---------------- host emulation: the two TMA operations as plain copies --------------------
+    (void)lmaps; (void)smaps; (void)full; (void)empty;
+    for (long long i = 0; i < mine; ++i) {
+        const long long t = bid + i * nblocks;
+        const int which = (int)(t / per_array);
+        const long long r = t - which * per_array;
+        const long long o = r / P.tiles, tile = r - o * P.tiles;
+        cplx *s = (cplx *)(base + (size_t)(i % AXIS3_NBUF) * tile_bytes);
+        const cplx *src = P.in[which] + (size_t)o * n * P.inner + (tile << P.tshift);
+        const int tcount = (int)((P.inner - (tile << P.tshift)) < T ? (P.inner - (tile << P.tshift)) : T);
+        for (int row = 0; row < n; ++row)
+            for (int c = 0; c < T; ++c) s[(size_t)row * T + c] = c < tcount ? src[(size_t)row * P.inner + c] : cmake(0.0, 0.0);
+        const double alpha = P.alpha[which];
+        if (P.use_pow && alpha != 1.0)
+            for (int idx = 0; idx < (n << P.tshift); ++idx) { s[idx].x = pow_nonneg(s[idx].x, alpha); s[idx].y = pow_nonneg(s[idx].y, alpha); }
+        fft_stages_group<D>(s, T, P.tshift, P.plan, tw, tid, nthr, 0);
+        cplx *dst = P.out[which] + (size_t)o * n * P.inner + (tile << P.tshift);
+        for (int p = 0; p < n; ++p)
+            for (int c = 0; c < tcount; ++c) dst[(size_t)P.freq_of[p] * P.inner + c] = s[(size_t)p * T + c];
+    }
 #endif
 }
 

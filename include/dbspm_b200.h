@@ -47,9 +47,11 @@ extern "C" {
 /* flags for dbspm_corr3d_f64 */
 #define DBSPM_CORR_DEFAULT    0
 #define DBSPM_CORR_AXIS_V1    (1 << 1)   /* force the all-in-shared-memory axis pass (A/B timing) */
-#define DBSPM_CORR_USE_TMA    (1 << 2)   /* x/y passes through the TMA-fed persistent kernel (tensor-map load, digit-reversing
-                                            tensor-map store).  Measured on B200: equal to the default register-staged
-                                            kernel at n <= 384, 10-25 % slower at n = 1024 (FP64/shared-memory bound) */
+#define DBSPM_CORR_USE_TMA    (1 << 2)   /* force the TMA-fed persistent axis pass (tensor-map load, digit-reversing
+                                            tensor-map store, two consumer groups + producer warp) */
+#define DBSPM_CORR_NO_TMA     (1 << 3)   /* force the register-staged axis pass.  Default: picked per axis length --
+                                            TMA for 256 <= n <= 576 (27 % faster at n = 384 on B200), register-staged
+                                            otherwise (n = 1024 is FP64/shared-memory bound with 4-line tiles) */
 /* profiling aid: skip stages (results are then meaningless); bench.py times each launch alone */
 #define DBSPM_CORR_SKIP_XFWD  (1 << 8)
 #define DBSPM_CORR_SKIP_YFWD  (1 << 9)

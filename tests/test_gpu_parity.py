@@ -59,7 +59,7 @@ def test_overlap_edge_shapes(ops, shape, window):
     assert _rel(got, ref) <= 1e-9
 
 
-@pytest.mark.parametrize("flags", [0, 1 << 1, 1 << 2])
+@pytest.mark.parametrize("flags", [0, 1 << 1, 1 << 2, 1 << 3])
 def test_overlap_kernel_variants_agree(ops, overlap_golden, manifest, flags):
     """default (register-first/last) axis pass, all-in-shared-memory variant (1<<1) and the TMA-fed
     persistent variant (1<<2: tensor-map load + digit-reversing tensor-map store) give the reference's answer."""
@@ -72,7 +72,7 @@ def test_overlap_kernel_variants_agree(ops, overlap_golden, manifest, flags):
             win = ops.density_overlap_window(a, b, dr, z_lo, z_hi, alpha, alpha, flags=flags)
             assert np.abs(win - ref[:, :, z_lo:z_hi]).max() <= 1e-9 * np.abs(ref).max(), (case, flags)
     rng = np.random.default_rng(5)
-    for shape in [(196, 50, 24), (96, 120, 10), (1024, 6, 8)]:        # n = 196 (4*7*7), 120 (3*5*8), 1024 (16*8*8)
+    for shape in [(196, 50, 24), (96, 120, 10), (1024, 6, 8), (384, 320, 6)]:   # n = 196 (4*7*7), 120 (3*5*8), 1024, 384/320 (TMA by default)
         a, b = rng.random(shape), rng.random(shape) - 0.5
         ref = O.density_overlap_fft(a, b, np.ones(3))
         got = ops.density_overlap_window(a, b, np.ones(3), flags=flags)
