@@ -10,7 +10,7 @@
 #define RELAX_THREADS 128
 #endif
 #ifndef RELAX_MIN_BLOCKS
-#define RELAX_MIN_BLOCKS 3   /* measured on B200: 3 CTAs of 128 (168 regs) beat 2 (183) and 4 (128 + spills) */
+#define RELAX_MIN_BLOCKS 4   /* measured on B200 (1024x1024x24): 3 / 4 / 5 / 6 CTAs of 128 -> 139 / 129 / 141 / 146 ms; 4 = 128 registers, no spills */
 #endif
 
 __global__ void __launch_bounds__(256) relax_cart_kernel(const double *etp, double *cart, long long npos, double rpivot)
@@ -23,7 +23,8 @@ template <int LAYOUT>
 __global__ void __launch_bounds__(RELAX_THREADS, RELAX_MIN_BLOCKS) relax_kernel(const __grid_constant__ RelaxParams P, long long ncol)
 {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    relax_column_body<LAYOUT>(P, col, ncol);      // lanes past the end idle inside (warp barrier)
+    __shared__ double powell_sm[PS_COUNT * RELAX_THREADS];       // Powell-level state, one column per thread
+    relax_column_body<LAYOUT, RELAX_THREADS>(P, col, ncol, powell_sm, threadIdx.x);      // lanes past the end idle inside (warp barrier)
 }
 
 // (nx,ny,nz) -> (nx,nz,ny) so that the lanes of a warp (adjacent y columns) read adjacent addresses

@@ -169,293 +169,72 @@ HD double relax_objective(const RelaxParams &P, int oi, int oj, int ok, double t
 }
 
 // ---- Powell / Brent / bracket state machine -----------------------------------------------
-enum RelaxState {
-    RS_START = 0,      // begin a minimisation at the current guess
-    RS_INIT,           // f(x0) arrived
-    RS_ITER_BEGIN,
-    RS_LS_BEGIN,       // start line search `which`
-    RS_BR_FA, RS_BR_FB, RS_BR_FC,
-    RS_BR_LOOP,
-    RS_BR_A1, RS_BR_C1, RS_BR_GEN,
-    RS_BR_DONE,
-    RS_BT_LOOP,        // Brent loop head
-    RS_BT_U,           // f(u) arrived
-    RS_LS_FINISH,
-    RS_AFTER_LS,
-    RS_ITER_END,
-    RS_EXTRAP,         // f(x2) arrived
-    RS_FINISHED
+// A lane is always in one of the ENTRY states (a function value it asked for has arrived).  One
+// trip of the column loop runs, for the whole warp together, a short dispatch on the entry state
+// followed by a fixed sequence of blocks `if (pc == X) { ... }` in the order in which scipy's control
+// flow visits them (bracket loop -> bracket check -> Brent iteration -> line-search finish ->
+// direction bookkeeping -> iteration end -> store/next height -> iteration begin -> line-search
+// begin -> request).  Every block is entered once per trip by all the lanes that need it, whatever
+// state they came from, and the warp re-converges after each block; the rare backward edges (maxfev
+// exhausted, a zero search direction) repeat the sequence for the lanes concerned.
+enum RelaxPc {
+    PC_IDLE = 0,                   // column finished
+    // entry states
+    PC_INIT,                       // f(x0)
+    PC_BR_FA, PC_BR_FB, PC_BR_FC,  // bracket: f(xa), f(xb), f(xc)
+    PC_BR_A1, PC_BR_C1, PC_BR_GEN, // bracket loop: f(w) for the three kinds of trial point
+    PC_BT_U,                       // Brent: f(u)
+    PC_EXTRAP,                     // Powell: f(2x - x1)
+    // blocks
+    PC_BR_LOOP, PC_BR_DONE, PC_BT_LOOP, PC_LS_FINISH, PC_AFTER_LS, PC_ITER_END, PC_FINISHED,
+    PC_ITER_BEGIN, PC_LS_BEGIN, PC_REQUEST
 };
 
-struct PowellMachine {
-    // Powell
-    double x[2], x1[2], d0[2], d1[2], fval, fx, fx2, delta;
-    int bigind, iter, nfev, which, state;
-    // line search
-    double p[2], xi[2], alpha_min, fret;
-    // bracket
-    double xa, xb, xc, fa, fb, fc, w, fw;
-    int br_iter;
-    // Brent
-    double bx, bw, bv, bfx, bfw, bfv, a, b, deltax, rat, u;
-    int bt_iter;
-    // evaluation request
-    double ex[2];
+// Powell-level state, touched only at line-search boundaries: one shared-memory column per thread
+// (field-major, so a warp's accesses are conflict-free).  Keeps ~28 registers free for occupancy.
+enum RelaxShared {
+    PS_X_0, PS_X_1,                // current point (theta, phi)
+    PS_X1_0, PS_X1_1,              // point at the start of the iteration
+    PS_D0_0, PS_D0_1, PS_D1_0, PS_D1_1,   // direction set
+    PS_FVAL, PS_FX, PS_FX2, PS_DELTA,
+    PS_COUNT
 };
 
-HD void pm_request_alpha(PowellMachine &M, double alpha, int next)
-{
-    M.ex[0] = M.p[0] + alpha * M.xi[0];
-    M.ex[1] = M.p[1] + alpha * M.xi[1];
-    M.state = next;
-}
-
-// Advance until an objective value is needed (returns true, point in M.ex) or the
-// minimisation has finished (returns false; result in M.x, M.fval).  `fe` is the value of
-// the previously requested point.
-HDN inline bool powell_advance(PowellMachine &M, double fe, double xtol, double ftol, int maxiter, int maxfev)
-{
-    const double _gold = 1.618034, _verysmall_num = 1e-21, grow_limit = 110.0;
-    const double _mintol = 1.0e-11, _cg = 0.3819660;
-    const double tol = xtol * 100;
-    for (;;) {
-        switch (M.state) {
-        case RS_START:
-            M.nfev = 0; M.iter = 0;
-            M.d0[0] = 1.0; M.d0[1] = 0.0; M.d1[0] = 0.0; M.d1[1] = 1.0;
-            M.ex[0] = M.x[0]; M.ex[1] = M.x[1];
-            M.state = RS_INIT;
-            M.nfev += 1;
-            return true;
-        case RS_INIT:
-            M.fval = fe;
-            M.x1[0] = M.x[0]; M.x1[1] = M.x[1];
-            goto L_ITER_BEGIN;
-        case RS_ITER_BEGIN:
-        L_ITER_BEGIN:
-            M.fx = M.fval; M.bigind = 0; M.delta = 0.0;
-            M.which = 0;
-            goto L_LS_BEGIN;
-        case RS_LS_BEGIN:
-        L_LS_BEGIN:
-            if (M.which == 0) { M.xi[0] = M.d0[0]; M.xi[1] = M.d0[1]; }
-            else if (M.which == 1) { M.xi[0] = M.d1[0]; M.xi[1] = M.d1[1]; }
-            /* which == 2: xi already holds the extrapolation direction */
-            if (M.which < 2) M.fx2 = M.fval;
-            if (M.xi[0] == 0.0 && M.xi[1] == 0.0) { goto L_AFTER_LS; }
-            M.p[0] = M.x[0]; M.p[1] = M.x[1];
-            M.xa = 0.0; M.xb = 1.0;
-            pm_request_alpha(M, M.xa, RS_BR_FA);
-            goto request;
-        case RS_BR_FA:
-            M.fa = fe;
-            pm_request_alpha(M, M.xb, RS_BR_FB);
-            goto request;
-        case RS_BR_FB:
-            M.fb = fe;
-            if (M.fa < M.fb) {
-                double t = M.xa; M.xa = M.xb; M.xb = t;
-                t = M.fa; M.fa = M.fb; M.fb = t;
-            }
-            M.xc = M.xb + _gold * (M.xb - M.xa);
-            pm_request_alpha(M, M.xc, RS_BR_FC);
-            goto request;
-        case RS_BR_FC:
-            M.fc = fe;
-            M.br_iter = 0;
-            goto L_BR_LOOP;
-        case RS_BR_LOOP:
-        L_BR_LOOP: {
-            if (!(M.fc < M.fb)) { goto L_BR_DONE; }
-            const double tmp1 = (M.xb - M.xa) * (M.fb - M.fc);
-            const double tmp2 = (M.xb - M.xc) * (M.fb - M.fa);
-            const double val = tmp2 - tmp1;
-            double denom;
-            if (fabs(val) < _verysmall_num) denom = 2.0 * _verysmall_num;
-            else denom = 2.0 * val;
-            M.w = M.xb - ((M.xb - M.xc) * tmp2 - (M.xb - M.xa) * tmp1) / denom;
-            const double wlim = M.xb + grow_limit * (M.xc - M.xb);
-            if (M.br_iter > 1000) { goto L_BR_DONE; }
-            M.br_iter += 1;
-            if ((M.w - M.xc) * (M.xb - M.w) > 0.0) {
-                pm_request_alpha(M, M.w, RS_BR_A1);
-            } else if ((M.w - wlim) * (wlim - M.xc) >= 0.0) {
-                M.w = wlim;
-                pm_request_alpha(M, M.w, RS_BR_GEN);
-            } else if ((M.w - wlim) * (M.xc - M.w) > 0.0) {
-                pm_request_alpha(M, M.w, RS_BR_C1);
-            } else {
-                M.w = M.xc + _gold * (M.xc - M.xb);
-                pm_request_alpha(M, M.w, RS_BR_GEN);
-            }
-            goto request;
-        }
-        case RS_BR_A1:
-            M.fw = fe;
-            if (M.fw < M.fc) {
-                M.xa = M.xb; M.xb = M.w; M.fa = M.fb; M.fb = M.fw;
-                goto L_BR_DONE;
-            } else if (M.fw > M.fb) {
-                M.xc = M.w; M.fc = M.fw;
-                goto L_BR_DONE;
-            }
-            M.w = M.xc + _gold * (M.xc - M.xb);
-            pm_request_alpha(M, M.w, RS_BR_GEN);
-            goto request;
-        case RS_BR_C1:
-            M.fw = fe;
-            if (M.fw < M.fc) {
-                M.xb = M.xc; M.xc = M.w; M.w = M.xc + _gold * (M.xc - M.xb);
-                M.fb = M.fc; M.fc = M.fw;
-                pm_request_alpha(M, M.w, RS_BR_GEN);
-                goto request;
-            }
-            M.xa = M.xb; M.xb = M.xc; M.xc = M.w;
-            M.fa = M.fb; M.fb = M.fc; M.fc = M.fw;
-            goto L_BR_LOOP;
-        case RS_BR_GEN:
-            M.fw = fe;
-            M.xa = M.xb; M.xb = M.xc; M.xc = M.w;
-            M.fa = M.fb; M.fb = M.fc; M.fc = M.fw;
-            goto L_BR_LOOP;
-        case RS_BR_DONE:
-        L_BR_DONE: {
-            const bool cond1 = (M.fb < M.fc && M.fb <= M.fa) || (M.fb < M.fa && M.fb <= M.fc);
-            const bool cond2 = (M.xa < M.xb && M.xb < M.xc) || (M.xc < M.xb && M.xb < M.xa);
-            const bool cond3 = isfinite(M.xa) && isfinite(M.xb) && isfinite(M.xc);
-            if (!(cond1 && cond2 && cond3)) {
-                if (isnan(M.xa) || isnan(M.xb) || isnan(M.xc) || isnan(M.fa) || isnan(M.fb) || isnan(M.fc)) {
-                    M.alpha_min = NAN; M.fret = NAN;
-                } else {
-                    M.alpha_min = M.xa; M.fret = M.fa;                /* np.argmin: first minimum */
-                    if (M.fb < M.fret) { M.alpha_min = M.xb; M.fret = M.fb; }
-                    if (M.fc < M.fret) { M.alpha_min = M.xc; M.fret = M.fc; }
-                }
-                goto L_LS_FINISH;
-            }
-            M.bx = M.bw = M.bv = M.xb;
-            M.bfw = M.bfv = M.bfx = M.fb;
-            if (M.xa < M.xc) { M.a = M.xa; M.b = M.xc; } else { M.a = M.xc; M.b = M.xa; }
-            M.deltax = 0.0; M.rat = 0.0;
-            M.bt_iter = 0;
-            goto L_BT_LOOP;
-        }
-        case RS_BT_LOOP:
-        L_BT_LOOP: {
-            if (!(M.bt_iter < 500)) { M.alpha_min = M.bx; M.fret = M.bfx; goto L_LS_FINISH; }
-            const double x = M.bx;
-            const double tol1 = tol * fabs(x) + _mintol;
-            const double tol2 = 2.0 * tol1;
-            const double xmid = 0.5 * (M.a + M.b);
-            if (fabs(x - xmid) < (tol2 - 0.5 * (M.b - M.a))) {
-                M.alpha_min = M.bx; M.fret = M.bfx; goto L_LS_FINISH;
-            }
-            if (fabs(M.deltax) <= tol1) {
-                if (x >= xmid) M.deltax = M.a - x; else M.deltax = M.b - x;
-                M.rat = _cg * M.deltax;
-            } else {
-                double tmp1 = (x - M.bw) * (M.bfx - M.bfv);
-                double tmp2 = (x - M.bv) * (M.bfx - M.bfw);
-                double pp = (x - M.bv) * tmp2 - (x - M.bw) * tmp1;
-                tmp2 = 2.0 * (tmp2 - tmp1);
-                if (tmp2 > 0.0) pp = -pp;
-                tmp2 = fabs(tmp2);
-                const double dx_temp = M.deltax;
-                M.deltax = M.rat;
-                if ((pp > tmp2 * (M.a - x)) && (pp < tmp2 * (M.b - x)) && (fabs(pp) < fabs(0.5 * tmp2 * dx_temp))) {
-                    M.rat = pp * 1.0 / tmp2;
-                    const double uu = x + M.rat;
-                    if ((uu - M.a) < tol2 || (M.b - uu) < tol2) {
-                        if (xmid - x >= 0) M.rat = tol1; else M.rat = -tol1;
-                    }
-                } else {
-                    if (x >= xmid) M.deltax = M.a - x; else M.deltax = M.b - x;
-                    M.rat = _cg * M.deltax;
-                }
-            }
-            if (fabs(M.rat) < tol1) { if (M.rat >= 0) M.u = x + tol1; else M.u = x - tol1; }
-            else M.u = x + M.rat;
-            pm_request_alpha(M, M.u, RS_BT_U);
-            goto request;
-        }
-        case RS_BT_U: {
-            const double fu = fe, u = M.u;
-            if (fu > M.bfx) {
-                if (u < M.bx) M.a = u; else M.b = u;
-                if ((fu <= M.bfw) || (M.bw == M.bx)) { M.bv = M.bw; M.bw = u; M.bfv = M.bfw; M.bfw = fu; }
-                else if ((fu <= M.bfv) || (M.bv == M.bx) || (M.bv == M.bw)) { M.bv = u; M.bfv = fu; }
-            } else {
-                if (u >= M.bx) M.a = M.bx; else M.b = M.bx;
-                M.bv = M.bw; M.bw = M.bx; M.bx = u;
-                M.bfv = M.bfw; M.bfw = M.bfx; M.bfx = fu;
-            }
-            M.bt_iter += 1;
-            goto L_BT_LOOP;
-        }
-        case RS_LS_FINISH:
-        L_LS_FINISH:
-            M.xi[0] = M.alpha_min * M.xi[0]; M.xi[1] = M.alpha_min * M.xi[1];
-            M.x[0] = M.p[0] + M.xi[0]; M.x[1] = M.p[1] + M.xi[1];
-            M.fval = M.fret;
-            goto L_AFTER_LS;
-        case RS_AFTER_LS:
-        L_AFTER_LS:
-            if (M.which < 2) {
-                if ((M.fx2 - M.fval) > M.delta) { M.delta = M.fx2 - M.fval; M.bigind = M.which; }
-                if (M.which == 0) { M.which = 1; goto L_LS_BEGIN; }
-                goto L_ITER_END;
-            } else {
-                if (M.xi[0] != 0.0 || M.xi[1] != 0.0) {
-                    if (M.bigind == 0) { M.d0[0] = M.d1[0]; M.d0[1] = M.d1[1]; }
-                    M.d1[0] = M.xi[0]; M.d1[1] = M.xi[1];
-                }
-                goto L_ITER_BEGIN;
-            }
-        case RS_ITER_END:
-        L_ITER_END: {
-            M.iter += 1;
-            const double bnd = ftol * (fabs(M.fx) + fabs(M.fval)) + 1e-20;
-            if (2.0 * (M.fx - M.fval) <= bnd) { M.state = RS_FINISHED; return false; }
-            if (M.nfev >= maxfev) { M.state = RS_FINISHED; return false; }
-            if (M.iter >= maxiter) { M.state = RS_FINISHED; return false; }
-            if (isnan(M.fx) && isnan(M.fval)) { M.state = RS_FINISHED; return false; }
-            M.xi[0] = M.x[0] - M.x1[0]; M.xi[1] = M.x[1] - M.x1[1];     /* direc1 */
-            M.x1[0] = M.x[0]; M.x1[1] = M.x[1];
-            M.ex[0] = M.x[0] + 1 * M.xi[0]; M.ex[1] = M.x[1] + 1 * M.xi[1];
-            M.state = RS_EXTRAP;
-            goto request;
-        }
-        case RS_EXTRAP: {
-            M.fx2 = fe;
-            bool again = false;
-            if (M.fx > M.fx2) {
-                double t = 2.0 * (M.fx + M.fx2 - 2.0 * M.fval);
-                double temp = (M.fx - M.fval - M.delta);
-                t *= temp * temp;
-                temp = M.fx - M.fx2;
-                t -= M.delta * temp * temp;
-                if (t < 0.0) again = true;
-            }
-            if (again) { M.which = 2; goto L_LS_BEGIN; }
-            goto L_ITER_BEGIN;
-        }
-        default:
-            return false;
-        }
-        continue;
-    request:
-        /* maxfun wrapper: the call that would exceed maxfev raises instead (-> loop exit
-           with the x, fval of the last completed line search) */
-        if (M.nfev >= maxfev) { M.state = RS_FINISHED; return false; }
-        M.nfev += 1;
-        return true;
-    }
-}
+struct PowellRegs {
+    double p[2], xi[2];            // line search: origin and direction
+    double s[11];                  // bracket (xa xb xc fa fb fc w) and Brent (x w v fx fw fv a b deltax rat u) share storage
+    int pc, which, bigind, iter, nfev, it;
+};
+// bracket view
+#define BR_XA R.s[0]
+#define BR_XB R.s[1]
+#define BR_XC R.s[2]
+#define BR_FA R.s[3]
+#define BR_FB R.s[4]
+#define BR_FC R.s[5]
+#define BR_W  R.s[6]
+// Brent view
+#define BT_X   R.s[1]
+#define BT_FX  R.s[4]
+#define BT_W   R.s[0]
+#define BT_V   R.s[2]
+#define BT_FW  R.s[3]
+#define BT_FV  R.s[5]
+#define BT_A   R.s[6]
+#define BT_B   R.s[7]
+#define BT_DX  R.s[8]
+#define BT_RAT R.s[9]
+#define BT_U   R.s[10]
 
 // ---- one lateral column: sweep z from the top with warm start ------------------------------
-template <int LAYOUT>
-HDN inline void relax_column_body(const RelaxParams &P, long long col, long long ncol)
+// NTHR = threads per block (the stride of the shared-memory columns); sm = PS_COUNT*NTHR doubles.
+template <int LAYOUT, int NTHR>
+HDN inline void relax_column_body(const RelaxParams &P, long long col, long long ncol, double *sm, int tid)
 {
+#define PS(f) sm[(f) * NTHR + tid]
+    const double _gold = 1.618034, _verysmall_num = 1e-21, grow_limit = 110.0;
+    const double _mintol = 1.0e-11, _cg = 0.3819660;
+    const double tol = P.xtol * 100;
     // Every lane of the warp stays in the loop until all of them are finished (lanes past the
     // end of the tile start out finished), so the full-mask warp barrier below is legal.
     bool done = col >= ncol;
@@ -463,33 +242,284 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
     const long long c = done ? 0 : col;
     const int ci = (int)(c / nj), cj = (int)(c - (long long)ci * nj);
     const int oi = P.i_lo + ci, oj = P.j_lo + cj;
-    PowellMachine M;
-    M.x[0] = M_PI; M.x[1] = 0.0;
     int k = P.nz_relax - 1;
     int ok = (int)((double)k + P.npivot);                    // int64 store truncates
-    M.state = RS_START;
-    double fe = 0.0;
+    PowellRegs R;
+    // start of a minimisation at the current point (scipy: x = asarray(x0); fval = func(x)); the
+    // request "p + 0*0" is x itself
+    PS(PS_X_0) = M_PI; PS(PS_X_1) = 0.0;
+    PS(PS_D0_0) = 1.0; PS(PS_D0_1) = 0.0; PS(PS_D1_0) = 0.0; PS(PS_D1_1) = 1.0;
+    R.p[0] = M_PI; R.p[1] = 0.0; R.xi[0] = 0.0; R.xi[1] = 0.0;
+    R.nfev = 1; R.iter = 0; R.which = 0; R.bigind = 0; R.it = 0;
+    R.pc = done ? PC_IDLE : PC_INIT;
+#pragma unroll
+    for (int q = 0; q < 11; ++q) R.s[q] = 0.0;
+    double alpha = 0.0;
     for (;;) {
-        // cheap, divergent part: advance this lane's optimiser until it needs a function value.
-        // Finishing a height stores its row and immediately starts the next one, so lanes do not
-        // wait for the slowest lane at every height.
-        while (!done && !powell_advance(M, fe, P.xtol, P.ftol, P.maxiter, P.maxfev)) {
-            const size_t o = (size_t)col * P.nz_relax + k;
-            P.out_etp[3 * o + 0] = M.fval;
-            P.out_etp[3 * o + 1] = M.x[0];
-            P.out_etp[3 * o + 2] = M.x[1];
-            if (P.out_nfev) P.out_nfev[o] = M.nfev;
-            if (--k < 0) { done = true; break; }
-            ok = (int)((double)k + P.npivot);
-            M.state = RS_START;
-        }
-        // expensive part: re-converge the warp, then all unfinished lanes evaluate the 64-point
-        // stencil together (without the barrier the compiler threads the jump from each state
-        // straight into a private copy of the evaluation and the lanes run it one group at a time)
+        // expensive part: the warp is converged here and all unfinished lanes evaluate the 64-point
+        // stencil together
         WARP_SYNC();
         if (WARP_ALL(done)) break;
-        if (!done) fe = relax_objective<LAYOUT>(P, oi, oj, ok, M.ex[0], M.ex[1]);
+        double fe = 0.0;
+        if (!done) fe = relax_objective<LAYOUT>(P, oi, oj, ok, R.p[0] + alpha * R.xi[0], R.p[1] + alpha * R.xi[1]);
+        WARP_SYNC();
+
+        // ---- dispatch on the entry state (cheap, per state) ----
+        int pc = R.pc, next = PC_IDLE;
+        bool fresh = false;                  // request that starts a minimisation: no maxfev check
+        double alpha_min = 0.0, fret = 0.0;  // line-search result on its way to PC_LS_FINISH
+        if (pc == PC_BT_U) {
+            const double fu = fe, u = BT_U;
+            if (fu > BT_FX) {
+                if (u < BT_X) BT_A = u; else BT_B = u;
+                if ((fu <= BT_FW) || (BT_W == BT_X)) { BT_V = BT_W; BT_W = u; BT_FV = BT_FW; BT_FW = fu; }
+                else if ((fu <= BT_FV) || (BT_V == BT_X) || (BT_V == BT_W)) { BT_V = u; BT_FV = fu; }
+            } else {
+                if (u >= BT_X) BT_A = BT_X; else BT_B = BT_X;
+                BT_V = BT_W; BT_W = BT_X; BT_X = u;
+                BT_FV = BT_FW; BT_FW = BT_FX; BT_FX = fu;
+            }
+            R.it += 1;
+            pc = PC_BT_LOOP;
+        } else if (pc == PC_BR_FA) {
+            BR_FA = fe;
+            alpha = BR_XB; next = PC_BR_FB; pc = PC_REQUEST;
+        } else if (pc == PC_BR_FB) {
+            BR_FB = fe;
+            if (BR_FA < BR_FB) {
+                double t = BR_XA; BR_XA = BR_XB; BR_XB = t;
+                t = BR_FA; BR_FA = BR_FB; BR_FB = t;
+            }
+            BR_XC = BR_XB + _gold * (BR_XB - BR_XA);
+            alpha = BR_XC; next = PC_BR_FC; pc = PC_REQUEST;
+        } else if (pc == PC_BR_FC) {
+            BR_FC = fe;
+            R.it = 0;
+            pc = PC_BR_LOOP;
+        } else if (pc == PC_BR_GEN) {
+            BR_XA = BR_XB; BR_XB = BR_XC; BR_XC = BR_W;
+            BR_FA = BR_FB; BR_FB = BR_FC; BR_FC = fe;
+            pc = PC_BR_LOOP;
+        } else if (pc == PC_BR_A1) {
+            const double fw = fe;
+            if (fw < BR_FC) {
+                BR_XA = BR_XB; BR_XB = BR_W; BR_FA = BR_FB; BR_FB = fw;
+                pc = PC_BR_DONE;
+            } else if (fw > BR_FB) {
+                BR_XC = BR_W; BR_FC = fw;
+                pc = PC_BR_DONE;
+            } else {
+                BR_W = BR_XC + _gold * (BR_XC - BR_XB);
+                alpha = BR_W; next = PC_BR_GEN; pc = PC_REQUEST;
+            }
+        } else if (pc == PC_BR_C1) {
+            const double fw = fe;
+            if (fw < BR_FC) {
+                BR_XB = BR_XC; BR_XC = BR_W; BR_W = BR_XC + _gold * (BR_XC - BR_XB);
+                BR_FB = BR_FC; BR_FC = fw;
+                alpha = BR_W; next = PC_BR_GEN; pc = PC_REQUEST;
+            } else {
+                BR_XA = BR_XB; BR_XB = BR_XC; BR_XC = BR_W;
+                BR_FA = BR_FB; BR_FB = BR_FC; BR_FC = fw;
+                pc = PC_BR_LOOP;
+            }
+        } else if (pc == PC_EXTRAP) {
+            const double fx2 = fe, fx = PS(PS_FX);
+            PS(PS_FX2) = fx2;
+            bool again = false;
+            if (fx > fx2) {
+                const double fval = PS(PS_FVAL), delta = PS(PS_DELTA);
+                double t = 2.0 * (fx + fx2 - 2.0 * fval);
+                double temp = (fx - fval - delta);
+                t *= temp * temp;
+                temp = fx - fx2;
+                t -= delta * temp * temp;
+                if (t < 0.0) again = true;
+            }
+            if (again) { R.which = 2; pc = PC_LS_BEGIN; }
+            else pc = PC_ITER_BEGIN;
+        } else if (pc == PC_INIT) {
+            PS(PS_FVAL) = fe;
+            PS(PS_X1_0) = PS(PS_X_0); PS(PS_X1_1) = PS(PS_X_1);
+            pc = PC_ITER_BEGIN;
+        }
+
+        // ---- block sequence ----
+        bool repeat;
+        do {
+            repeat = false;
+            if (pc == PC_BR_LOOP) {
+                if (!(BR_FC < BR_FB)) {
+                    pc = PC_BR_DONE;
+                } else {
+                    const double tmp1 = (BR_XB - BR_XA) * (BR_FB - BR_FC);
+                    const double tmp2 = (BR_XB - BR_XC) * (BR_FB - BR_FA);
+                    const double val = tmp2 - tmp1;
+                    double denom;
+                    if (fabs(val) < _verysmall_num) denom = 2.0 * _verysmall_num;
+                    else denom = 2.0 * val;
+                    BR_W = BR_XB - ((BR_XB - BR_XC) * tmp2 - (BR_XB - BR_XA) * tmp1) / denom;
+                    const double wlim = BR_XB + grow_limit * (BR_XC - BR_XB);
+                    if (R.it > 1000) {
+                        pc = PC_BR_DONE;
+                    } else {
+                        R.it += 1;
+                        if ((BR_W - BR_XC) * (BR_XB - BR_W) > 0.0) {
+                            next = PC_BR_A1;
+                        } else if ((BR_W - wlim) * (wlim - BR_XC) >= 0.0) {
+                            BR_W = wlim;
+                            next = PC_BR_GEN;
+                        } else if ((BR_W - wlim) * (BR_XC - BR_W) > 0.0) {
+                            next = PC_BR_C1;
+                        } else {
+                            BR_W = BR_XC + _gold * (BR_XC - BR_XB);
+                            next = PC_BR_GEN;
+                        }
+                        alpha = BR_W; pc = PC_REQUEST;
+                    }
+                }
+            }
+            if (pc == PC_BR_DONE) {
+                const double xa = BR_XA, xb = BR_XB, xc = BR_XC, fa = BR_FA, fb = BR_FB, fc = BR_FC;
+                const bool cond1 = (fb < fc && fb <= fa) || (fb < fa && fb <= fc);
+                const bool cond2 = (xa < xb && xb < xc) || (xc < xb && xb < xa);
+                const bool cond3 = isfinite(xa) && isfinite(xb) && isfinite(xc);
+                if (!(cond1 && cond2 && cond3)) {
+                    if (isnan(xa) || isnan(xb) || isnan(xc) || isnan(fa) || isnan(fb) || isnan(fc)) {
+                        alpha_min = NAN; fret = NAN;
+                    } else {
+                        alpha_min = xa; fret = fa;                    /* np.argmin: first minimum */
+                        if (fb < fret) { alpha_min = xb; fret = fb; }
+                        if (fc < fret) { alpha_min = xc; fret = fc; }
+                    }
+                    pc = PC_LS_FINISH;
+                } else {
+                    BT_X = xb; BT_W = xb; BT_V = xb;
+                    BT_FX = fb; BT_FW = fb; BT_FV = fb;
+                    if (xa < xc) { BT_A = xa; BT_B = xc; } else { BT_A = xc; BT_B = xa; }
+                    BT_DX = 0.0; BT_RAT = 0.0;
+                    R.it = 0;
+                    pc = PC_BT_LOOP;
+                }
+            }
+            if (pc == PC_BT_LOOP) {
+                const double x = BT_X;
+                const double tol1 = tol * fabs(x) + _mintol;
+                const double tol2 = 2.0 * tol1;
+                const double xmid = 0.5 * (BT_A + BT_B);
+                if (!(R.it < 500) || fabs(x - xmid) < (tol2 - 0.5 * (BT_B - BT_A))) {
+                    alpha_min = x; fret = BT_FX;
+                    pc = PC_LS_FINISH;
+                } else {
+                    if (fabs(BT_DX) <= tol1) {
+                        if (x >= xmid) BT_DX = BT_A - x; else BT_DX = BT_B - x;
+                        BT_RAT = _cg * BT_DX;
+                    } else {
+                        double tmp1 = (x - BT_W) * (BT_FX - BT_FV);
+                        double tmp2 = (x - BT_V) * (BT_FX - BT_FW);
+                        double pp = (x - BT_V) * tmp2 - (x - BT_W) * tmp1;
+                        tmp2 = 2.0 * (tmp2 - tmp1);
+                        if (tmp2 > 0.0) pp = -pp;
+                        tmp2 = fabs(tmp2);
+                        const double dx_temp = BT_DX;
+                        BT_DX = BT_RAT;
+                        if ((pp > tmp2 * (BT_A - x)) && (pp < tmp2 * (BT_B - x)) && (fabs(pp) < fabs(0.5 * tmp2 * dx_temp))) {
+                            BT_RAT = pp * 1.0 / tmp2;
+                            const double uu = x + BT_RAT;
+                            if ((uu - BT_A) < tol2 || (BT_B - uu) < tol2) {
+                                if (xmid - x >= 0) BT_RAT = tol1; else BT_RAT = -tol1;
+                            }
+                        } else {
+                            if (x >= xmid) BT_DX = BT_A - x; else BT_DX = BT_B - x;
+                            BT_RAT = _cg * BT_DX;
+                        }
+                    }
+                    if (fabs(BT_RAT) < tol1) { if (BT_RAT >= 0) BT_U = x + tol1; else BT_U = x - tol1; }
+                    else BT_U = x + BT_RAT;
+                    alpha = BT_U; next = PC_BT_U; pc = PC_REQUEST;
+                }
+            }
+            if (pc == PC_LS_FINISH) {
+                R.xi[0] = alpha_min * R.xi[0]; R.xi[1] = alpha_min * R.xi[1];
+                PS(PS_X_0) = R.p[0] + R.xi[0]; PS(PS_X_1) = R.p[1] + R.xi[1];
+                PS(PS_FVAL) = fret;
+                pc = PC_AFTER_LS;
+            }
+            if (pc == PC_AFTER_LS) {
+                if (R.which < 2) {
+                    const double gain = PS(PS_FX2) - PS(PS_FVAL);
+                    if (gain > PS(PS_DELTA)) { PS(PS_DELTA) = gain; R.bigind = R.which; }
+                    if (R.which == 0) { R.which = 1; pc = PC_LS_BEGIN; }
+                    else pc = PC_ITER_END;
+                } else {
+                    if (R.xi[0] != 0.0 || R.xi[1] != 0.0) {
+                        if (R.bigind == 0) { PS(PS_D0_0) = PS(PS_D1_0); PS(PS_D0_1) = PS(PS_D1_1); }
+                        PS(PS_D1_0) = R.xi[0]; PS(PS_D1_1) = R.xi[1];
+                    }
+                    pc = PC_ITER_BEGIN;
+                }
+            }
+            if (pc == PC_ITER_END) {
+                R.iter += 1;
+                const double fx = PS(PS_FX), fval = PS(PS_FVAL);
+                const double bnd = P.ftol * (fabs(fx) + fabs(fval)) + 1e-20;
+                if (2.0 * (fx - fval) <= bnd || R.nfev >= P.maxfev || R.iter >= P.maxiter || (isnan(fx) && isnan(fval))) {
+                    pc = PC_FINISHED;
+                } else {
+                    const double x0 = PS(PS_X_0), x1 = PS(PS_X_1);
+                    R.xi[0] = x0 - PS(PS_X1_0); R.xi[1] = x1 - PS(PS_X1_1);         /* direc1 */
+                    PS(PS_X1_0) = x0; PS(PS_X1_1) = x1;
+                    R.p[0] = x0; R.p[1] = x1;
+                    alpha = 1.0; next = PC_EXTRAP; pc = PC_REQUEST;                   /* x + 1*direc1 */
+                }
+            }
+            if (pc == PC_FINISHED) {
+                // store this height's row and start the next one from the relaxed angles (warm
+                // start), so lanes do not wait for the slowest lane at every height
+                const size_t o = (size_t)col * P.nz_relax + k;
+                const double x0 = PS(PS_X_0), x1 = PS(PS_X_1);
+                P.out_etp[3 * o + 0] = PS(PS_FVAL);
+                P.out_etp[3 * o + 1] = x0;
+                P.out_etp[3 * o + 2] = x1;
+                if (P.out_nfev) P.out_nfev[o] = R.nfev;
+                if (--k < 0) {
+                    done = true; pc = PC_IDLE;
+                } else {
+                    ok = (int)((double)k + P.npivot);
+                    R.nfev = 0; R.iter = 0;
+                    PS(PS_D0_0) = 1.0; PS(PS_D0_1) = 0.0; PS(PS_D1_0) = 0.0; PS(PS_D1_1) = 1.0;
+                    R.p[0] = x0; R.p[1] = x1; R.xi[0] = 0.0; R.xi[1] = 0.0;
+                    alpha = 0.0; next = PC_INIT; fresh = true; pc = PC_REQUEST;
+                }
+            }
+            if (pc == PC_ITER_BEGIN) {
+                PS(PS_FX) = PS(PS_FVAL); R.bigind = 0; PS(PS_DELTA) = 0.0;
+                R.which = 0;
+                pc = PC_LS_BEGIN;
+            }
+            if (pc == PC_LS_BEGIN) {
+                if (R.which == 0) { R.xi[0] = PS(PS_D0_0); R.xi[1] = PS(PS_D0_1); }
+                else if (R.which == 1) { R.xi[0] = PS(PS_D1_0); R.xi[1] = PS(PS_D1_1); }
+                /* which == 2: xi already holds the extrapolation direction */
+                if (R.which < 2) PS(PS_FX2) = PS(PS_FVAL);
+                if (R.xi[0] == 0.0 && R.xi[1] == 0.0) {
+                    pc = PC_AFTER_LS; repeat = true;
+                } else {
+                    R.p[0] = PS(PS_X_0); R.p[1] = PS(PS_X_1);
+                    BR_XA = 0.0; BR_XB = 1.0;
+                    alpha = 0.0; next = PC_BR_FA; pc = PC_REQUEST;
+                }
+            }
+            if (pc == PC_REQUEST) {
+                /* maxfun wrapper: the call that would exceed maxfev raises instead (-> exit with
+                   the x, fval of the last completed line search) */
+                if (!fresh && R.nfev >= P.maxfev) { pc = PC_FINISHED; repeat = true; }
+                else { R.nfev += 1; pc = next; }
+            }
+        } while (repeat);
+        R.pc = pc;
     }
+#undef PS
 }
 
 // sph2cart of every relaxed position (dbspm:603-605), one converged pass instead of divergent

@@ -171,6 +171,7 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
                                     double xtol, double ftol, int maxfev,
                                     double *out_etp, double *out_cart, int *out_nfev, int transposed)
 {
+    double powell_sm[PS_COUNT];
     RelaxParams P;
     P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc;
     P.i_lo = i_lo; P.i_hi = i_hi; P.j_lo = j_lo; P.j_hi = j_hi; P.nz_relax = nz_relax;
@@ -209,9 +210,9 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
                         }
                 }
         P.grid = tr.data();
-        for (long long c = 0; c < ncol; ++c) relax_column_body<1>(P, c, ncol);
+        for (long long c = 0; c < ncol; ++c) relax_column_body<1, 1>(P, c, ncol, powell_sm, 0);
     } else {
-        for (long long c = 0; c < ncol; ++c) relax_column_body<0>(P, c, ncol);
+        for (long long c = 0; c < ncol; ++c) relax_column_body<0, 1>(P, c, ncol, powell_sm, 0);
     }
     if (out_cart) relax_cart_body(out_etp, out_cart, ncol * nz_relax, rpivot, 0, 1);
     return 0;
