@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(RELAX_THREADS, RELAX_MIN_BLOCKS) relax_kernel(
     relax_column_body<LAYOUT, RELAX_THREADS>(P, col, ncol, powell_sm, threadIdx.x);      // lanes past the end idle inside (warp barrier)
 }
 
-// (nx,ny,nz) -> (nx,nz,ny) so that the lanes of a warp (adjacent y columns) read adjacent addresses
+// (nx,ny,nz) -> (nx,nz,ny+3) so that the lanes of a warp (adjacent y columns) read adjacent addresses
+// and the y neighbours of a stencil row are contiguous across the periodic boundary
 __global__ void __launch_bounds__(256) transpose_yz_kernel(const double *in, double *out, int ny, int nz)
 {
     __shared__ double tile[32 * 33];
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const double *data, int nx,
     const double inv_n[3] = {1.0 / nx, 1.0 / ny, 1.0 / nz};
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += stride)
-        out[i] = tricubic_eval<0>(data, nx, ny, nz, inv_n, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+        out[i] = tricubic_eval<0>(data, nx, ny, nz, 0, inv_n, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
 }
 
 // np.gradient(E, -dz, axis=2): central differences inside, one-sided first order at the ends
@@ -121,7 +122,7 @@ extern "C" int dbspm_static_accumulate_f64(double *acc, const double *comp, doub
 extern "C" size_t dbspm_relax_workspace_bytes(int nx, int ny, int nzc)
 {
     if (nx < 1 || ny < 1 || nzc < 1) return 0;
-    return (size_t)nx * ny * nzc * sizeof(double);
+    return (size_t)nx * (ny + 3) * nzc * sizeof(double);       // y-fastest copy with a 3-plane periodic halo
 }
 
 extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
@@ -136,15 +137,16 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
     DBSPM_REQUIRE(i_lo <= i_hi && j_lo <= j_hi && nz_relax >= 0, DBSPM_EINVAL, "bad tile");
     DBSPM_REQUIRE(dr[0] > 0 && dr[1] > 0 && dr[2] > 0, DBSPM_EINVAL, "grid spacings must be positive");
     DBSPM_REQUIRE(maxfev >= 1, DBSPM_EINVAL, "maxfev must be >= 1");
-    DBSPM_REQUIRE((long long)nx * ny * nzc < 2147483647LL, DBSPM_EUNSUPPORTED,
+    DBSPM_REQUIRE((long long)nx * (ny + 3) * nzc < 2147483647LL, DBSPM_EUNSUPPORTED,
                   "potential grid too large for 32-bit element offsets (%d x %d x %d)", nx, ny, nzc);
     RelaxParams P;
-    P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc;
+    P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc; P.nyp = ny + 3;
     P.i_lo = i_lo; P.i_hi = i_hi; P.j_lo = j_lo; P.j_hi = j_hi; P.nz_relax = nz_relax;
     P.kappa = kappa; P.rpivot = rpivot;
     P.npivot = rpivot / dr[2];
     P.rpivot_rt = P.npivot * dr[2];
     P.dr[0] = dr[0]; P.dr[1] = dr[1]; P.dr[2] = dr[2];
+    for (int q = 0; q < 3; ++q) P.inv_dr[q] = 1.0 / dr[q];
     P.inv_n[0] = 1.0 / nx; P.inv_n[1] = 1.0 / ny; P.inv_n[2] = 1.0 / nzc;
     P.noortho = dR != nullptr;
     for (int q = 0; q < 9; ++q) P.Minv[q] = 0.0;
@@ -164,7 +166,7 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
                       DBSPM_EWORKSPACE, "relax workspace needs %zu bytes (got %zu)",
                       dbspm_relax_workspace_bytes(nx, ny, nzc), workspace_bytes);
         DBSPM_REQUIRE(nx <= 65535, DBSPM_EUNSUPPORTED, "nx too large for the transpose grid");
-        dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 31) / 32), (unsigned)nx);
+        dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 3 + 31) / 32), (unsigned)nx);
         transpose_yz_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_win, (double *)workspace, ny, nzc);
         DBSPM_CUDA_TRY(cudaGetLastError());
         P.grid = (const double *)workspace;

@@ -24,8 +24,9 @@
 #endif
 
 struct RelaxParams {
-    const double *grid;       // static potential: (nx,ny,nzc) z fastest [LAYOUT 0] or (nx,nzc,ny) [LAYOUT 1]
+    const double *grid;       // static potential: (nx,ny,nzc) z fastest [LAYOUT 0] or (nx,nzc,nyp) [LAYOUT 1]
     int nx, ny, nzc;
+    int nyp;                  // LAYOUT 1: row length ny + 3 (periodic halo: stored index t holds y = t - 1)
     int i_lo, i_hi, j_lo, j_hi;
     int nz_relax;
     double kappa;
@@ -33,6 +34,7 @@ struct RelaxParams {
     double npivot;            // rpivot / dr[2]                     (dbspm:558)
     double rpivot_rt;         // npivot * dr[2]                     (interactions.py:73)
     double dr[3];
+    double inv_dr[3];         // RN(1/dr): division by dr as multiply + two fused corrections (div_by)
     double inv_n[3];          // 1/nx, 1/ny, 1/nzc
     int noortho;
     double Minv[9];           // inv(dR^T), row-major
@@ -57,14 +59,31 @@ HD double wrap_coord(double p, double n, double inv_n)
     return (p >= 0.0) ? pos : neg;
 }
 
+// x / d for a divisor known in advance, correctly rounded (Markstein): with y = RN(1/d), q = RN(x*y) is
+// within one ulp of x/d, r = x - q*d is exact in one fma, and RN(q + r*y) is the correctly rounded quotient
+// (finite, non-extreme operands -- offsets of a few grid spacings here).  3 instructions instead of
+// the ~20 of the general division; tests/test_emulation.py compares it with `/` on 10^7 random pairs.
+HD double div_by(double x, double d, double inv_d)
+{
+    const double q = x * inv_d;
+    const double r = fma(-q, d, x);
+    return fma(r, inv_d, q);
+}
+
+// indices of the four stencil planes around floor(coordinate) = i0 in [0, n] (n itself when the
+// reference's `+= n` rounds up), periodic; chained selects, valid for every n >= 1
+HD void stencil_idx(int i0, int n, int *idx)
+{
+    const int i1 = (i0 >= n) ? i0 - n : i0;
+    idx[1] = i1;
+    idx[0] = (i1 == 0) ? n - 1 : i1 - 1;
+    idx[2] = (i1 + 1 == n) ? 0 : i1 + 1;
+    idx[3] = (idx[2] + 1 == n) ? 0 : idx[2] + 1;
+}
+
 HD void cr_axis(double p, int n, double inv_n, int *i0, double *w)
 {
-#if defined(RELAX_OLD_WRAP)
-    double d = fmod(p, (double)n);
-    if (d < 0) d += (double)n;
-#else
     const double d = wrap_coord(p, (double)n, inv_n);
-#endif
     const double fl = floor(d);
     const double u = d - fl, u2 = u * u, u3 = u2 * u;
     *i0 = (int)fl;
@@ -74,56 +93,54 @@ HD void cr_axis(double p, int n, double inv_n, int *i0, double *w)
     w[3] = 0.5 * u3 - 0.5 * u2;
 }
 
-HD int wrap_idx(int i, int n)
-{   // i in [-1, n+2] (stencil around a wrapped coordinate): selects instead of integer division;
-    // tiny grids (n < 4) can need more than one correction and take the modulo (uniform branch)
-#if defined(RELAX_OLD_WRAP)
-    i %= n;
-    return i < 0 ? i + n : i;
-#else
-    if (n < 4) {
-        i %= n;
-        return i < 0 ? i + n : i;
-    }
-    i = (i < 0) ? i + n : i;
-    return (i >= n) ? i - n : i;
-#endif
-}
-
 // LAYOUT 0: g[(x*ny + y)*nz + z] (the caller's array, z fastest)
-// LAYOUT 1: g[(x*nz + z)*ny + y] (y fastest: the 32 lanes of a warp, which own adjacent y columns,
-//           read adjacent addresses -> 2-3 L1 wavefronts per load instead of ~8 and a 5x smaller
-//           per-warp cache footprint)
+// LAYOUT 1: g[(x*nz + z)*nyp + (y + 1)], nyp = ny + 3 (y fastest with a periodic halo: the 32 lanes of a
+//           warp, which own adjacent y columns, read adjacent addresses -> 2-3 L1 wavefronts per load
+//           instead of ~8, and the four y neighbours of a stencil row are four consecutive doubles at
+//           immediate offsets from one base address, wrap or no wrap)
 template <int LAYOUT>
-HD double tricubic_eval(const double *g, int nx, int ny, int nz, const double *inv_n, double x, double y, double z)
+HD double tricubic_eval(const double *g, int nx, int ny, int nz, int nyp, const double *inv_n, double x, double y, double z)
 {
     int ix, iy, iz;
     double wx[4], wy[4], wz[4];
     cr_axis(x, nx, inv_n[0], &ix, wx);
     cr_axis(y, ny, inv_n[1], &iy, wy);
     cr_axis(z, nz, inv_n[2], &iz, wz);
-    // 32-bit element offsets (the C ABI guarantees nx*ny*nz < 2^31): one 3-input add and one
-    // widening multiply-add per load instead of 64-bit pointer arithmetic
+    // 32-bit element offsets (the C ABI guarantees the element count < 2^31)
     int xo[4], yo[4], zo[4];
+    stencil_idx(ix, nx, xo);
+    stencil_idx(iz, nz, zo);
+    if (LAYOUT == 0) {
+        stencil_idx(iy, ny, yo);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        xo[c] = wrap_idx(ix - 1 + c, nx) * (ny * nz);
-        yo[c] = wrap_idx(iy - 1 + c, ny) * (LAYOUT == 0 ? nz : 1);
-        zo[c] = wrap_idx(iz - 1 + c, nz) * (LAYOUT == 0 ? 1 : ny);
+        for (int c = 0; c < 4; ++c) { xo[c] *= ny * nz; yo[c] *= nz; }
+    } else {
+        const int y1 = (iy >= ny) ? iy - ny : iy;          // stored index of plane y1 - 1
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { xo[c] *= nyp * nz; zo[c] *= nyp; yo[c] = y1 + c; }
     }
     double r = 0.0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         double rx = 0.0;
         // same summation order for both layouts (y innermost), so the result does not depend on
-        // whether the caller supplied the transposition workspace
+        // whether the caller supplied the re-layout workspace
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int o = xo[a] + zo[c];
-            double ry = wy[0] * LDG(g + (o + yo[0]));
-            ry = fma(wy[1], LDG(g + (o + yo[1])), ry);
-            ry = fma(wy[2], LDG(g + (o + yo[2])), ry);
-            ry = fma(wy[3], LDG(g + (o + yo[3])), ry);
+            double ry;
+            if (LAYOUT == 0) {
+                const int o = xo[a] + zo[c];
+                ry = wy[0] * LDG(g + (o + yo[0]));
+                ry = fma(wy[1], LDG(g + (o + yo[1])), ry);
+                ry = fma(wy[2], LDG(g + (o + yo[2])), ry);
+                ry = fma(wy[3], LDG(g + (o + yo[3])), ry);
+            } else {
+                const double *row = g + (xo[a] + zo[c] + yo[0]);
+                ry = wy[0] * LDG(row);
+                ry = fma(wy[1], LDG(row + 1), ry);
+                ry = fma(wy[2], LDG(row + 2), ry);
+                ry = fma(wy[3], LDG(row + 3), ry);
+            }
             rx = fma(wz[c], ry, rx);
         }
         r = fma(wx[a], rx, r);
@@ -150,9 +167,9 @@ HD double relax_objective(const RelaxParams &P, int oi, int oj, int ok, double t
 #endif
     double ox, oy, oz;
     if (!P.noortho) {
-        ox = P.rpivot_rt * sth * caz / P.dr[0];
-        oy = P.rpivot_rt * sth * saz / P.dr[1];
-        oz = P.rpivot_rt * cth / P.dr[2];
+        ox = div_by(P.rpivot_rt * sth * caz, P.dr[0], P.inv_dr[0]);
+        oy = div_by(P.rpivot_rt * sth * saz, P.dr[1], P.inv_dr[1]);
+        oz = div_by(P.rpivot_rt * cth, P.dr[2], P.inv_dr[2]);
     } else {
         const double X = P.rpivot_rt * sth * caz, Y = P.rpivot_rt * sth * saz, Z = P.rpivot_rt * cth;
         ox = P.Minv[0] * X + P.Minv[1] * Y + P.Minv[2] * Z;
@@ -165,7 +182,7 @@ HD double relax_objective(const RelaxParams &P, int oi, int oj, int ok, double t
     if (dbspm_emu_interp_hook)
         return dbspm_emu_interp_hook((double)oi + ox, (double)oj + oy, (double)ok + oz) + spr;
 #endif
-    return tricubic_eval<LAYOUT>(P.grid, P.nx, P.ny, P.nzc, P.inv_n, (double)oi + ox, (double)oj + oy, (double)ok + oz) + spr;
+    return tricubic_eval<LAYOUT>(P.grid, P.nx, P.ny, P.nzc, P.nyp, P.inv_n, (double)oi + ox, (double)oj + oy, (double)ok + oz) + spr;
 }
 
 // ---- Powell / Brent / bracket state machine -----------------------------------------------
@@ -181,7 +198,7 @@ enum RelaxPc {
     PC_IDLE = 0,                   // column finished
     // entry states
     PC_INIT,                       // f(x0)
-    PC_BR_FA, PC_BR_FB, PC_BR_FC,  // bracket: f(xa), f(xb), f(xc)
+    PC_BR_FB, PC_BR_FC,            // bracket: f(xb), f(xc)   (f(xa) is never requested, see PC_LS_BEGIN)
     PC_BR_A1, PC_BR_C1, PC_BR_GEN, // bracket loop: f(w) for the three kinds of trial point
     PC_BT_U,                       // Brent: f(u)
     PC_EXTRAP,                     // Powell: f(2x - x1)
@@ -281,9 +298,6 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
             }
             R.it += 1;
             pc = PC_BT_LOOP;
-        } else if (pc == PC_BR_FA) {
-            BR_FA = fe;
-            alpha = BR_XB; next = PC_BR_FB; pc = PC_REQUEST;
         } else if (pc == PC_BR_FB) {
             BR_FB = fe;
             if (BR_FA < BR_FB) {
@@ -507,7 +521,15 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
                 } else {
                     R.p[0] = PS(PS_X_0); R.p[1] = PS(PS_X_1);
                     BR_XA = 0.0; BR_XB = 1.0;
-                    alpha = 0.0; next = PC_BR_FA; pc = PC_REQUEST;
+                    // bracket's first call is f(p + 0*xi) = f(x), the point whose value is fval: the
+                    // objective is a pure function, so the call is counted (the maxfun wrapper may
+                    // raise on it) but not recomputed -- one evaluation in ten saved, same bits
+                    if (R.nfev >= P.maxfev) { pc = PC_FINISHED; repeat = true; }
+                    else {
+                        R.nfev += 1;
+                        BR_FA = PS(PS_FVAL);
+                        alpha = 1.0; next = PC_BR_FB; pc = PC_REQUEST;
+                    }
                 }
             }
             if (pc == PC_REQUEST) {
@@ -534,19 +556,21 @@ HD void relax_cart_body(const double *etp, double *cart, long long npos, double 
     }
 }
 
-// (nx, ny, nz) -> (nx, nz, ny): 32x32 tiles through shared memory (tile[32][33]), one x-slab per blockIdx.z
+// (nx, ny, nz) -> (nx, nz, nyp = ny + 3) with stored index t holding y = (t - 1) mod ny: 32x32 tiles
+// through shared memory (tile[32][33]), one x-slab per blockIdx.z; `by` tiles the stored index t
 HD void transpose_yz_tile(const double *in, double *out, int ny, int nz, double *tile /* 32*33 */,
-                          int bx /* z tile */, int by /* y tile */, long long slab, int tx, int ty, int nty)
+                          int bx /* z tile */, int by /* t tile */, long long slab, int tx, int ty, int nty)
 {
+    const int nyp = ny + 3;
     const double *src = in + (size_t)slab * ny * nz;
-    double *dst = out + (size_t)slab * ny * nz;
+    double *dst = out + (size_t)slab * nyp * nz;
     for (int r = ty; r < 32; r += nty) {
-        const int y = by * 32 + r, z = bx * 32 + tx;
-        if (y < ny && z < nz) tile[r * 33 + tx] = src[(size_t)y * nz + z];
+        const int t = by * 32 + r, z = bx * 32 + tx;
+        if (t < nyp && z < nz) tile[r * 33 + tx] = src[(size_t)((t - 1 + ny) % ny) * nz + z];
     }
     BLOCK_SYNC();
     for (int r = ty; r < 32; r += nty) {
-        const int z = bx * 32 + r, y = by * 32 + tx;
-        if (y < ny && z < nz) dst[(size_t)z * ny + y] = tile[tx * 33 + r];
+        const int z = bx * 32 + r, t = by * 32 + tx;
+        if (t < nyp && z < nz) dst[(size_t)z * nyp + t] = tile[tx * 33 + r];
     }
 }

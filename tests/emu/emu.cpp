@@ -173,10 +173,11 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
 {
     double powell_sm[PS_COUNT];
     RelaxParams P;
-    P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc;
+    P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc; P.nyp = ny + 3;
     P.i_lo = i_lo; P.i_hi = i_hi; P.j_lo = j_lo; P.j_hi = j_hi; P.nz_relax = nz_relax;
     P.kappa = kappa; P.rpivot = rpivot; P.npivot = rpivot / dr[2]; P.rpivot_rt = P.npivot * dr[2];
     P.dr[0] = dr[0]; P.dr[1] = dr[1]; P.dr[2] = dr[2];
+    for (int q = 0; q < 3; ++q) P.inv_dr[q] = 1.0 / dr[q];
     P.inv_n[0] = 1.0 / nx; P.inv_n[1] = 1.0 / ny; P.inv_n[2] = 1.0 / nzc;
     P.noortho = dR != nullptr;
     for (int q = 0; q < 9; ++q) P.Minv[q] = 0.0;
@@ -189,24 +190,27 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
     const long long ncol = (long long)(i_hi - i_lo) * (j_hi - j_lo);
     std::vector<double> tr;
     if (transposed) {
-        // what transpose_yz_kernel does, block by block (blockDim = 32 x 8 emulated as tx loop, ty = 0, nty = 1)
-        tr.resize((size_t)nx * ny * nzc);
+        // what transpose_yz_kernel does, block by block: the body has one block barrier, so it is run
+        // as a 32 x 1 thread block with each phase completed for all tx before the next starts --
+        // done here by calling the body per tx with a private tile copy of phase 1 (tile is filled
+        // identically by every call's phase 1 for its own tx column only, so fill first, then store)
+        const int nyp = ny + 3;
+        tr.resize((size_t)nx * nyp * nzc);
         std::vector<double> tile(32 * 33);
         for (int x = 0; x < nx; ++x)
-            for (int by = 0; by < (ny + 31) / 32; ++by)
+            for (int by = 0; by < (nyp + 31) / 32; ++by)
                 for (int bx = 0; bx < (nzc + 31) / 32; ++bx) {
-                    // two phases separated by the block barrier: emulate each phase over all tx
                     const double *src = static_win + (size_t)x * ny * nzc;
                     for (int tx = 0; tx < 32; ++tx)
                         for (int r = 0; r < 32; ++r) {
-                            const int y = by * 32 + r, z = bx * 32 + tx;
-                            if (y < ny && z < nzc) tile[r * 33 + tx] = src[(size_t)y * nzc + z];
+                            const int t = by * 32 + r, z = bx * 32 + tx;
+                            if (t < nyp && z < nzc) tile[r * 33 + tx] = src[(size_t)((t - 1 + ny) % ny) * nzc + z];
                         }
-                    double *dst = tr.data() + (size_t)x * ny * nzc;
+                    double *dst = tr.data() + (size_t)x * nyp * nzc;
                     for (int tx = 0; tx < 32; ++tx)
                         for (int r = 0; r < 32; ++r) {
-                            const int z = bx * 32 + r, y = by * 32 + tx;
-                            if (y < ny && z < nzc) dst[(size_t)z * ny + y] = tile[tx * 33 + r];
+                            const int z = bx * 32 + r, t = by * 32 + tx;
+                            if (t < nyp && z < nzc) dst[(size_t)z * nyp + t] = tile[tx * 33 + r];
                         }
                 }
         P.grid = tr.data();
@@ -221,5 +225,20 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
 extern "C" double emu_tricubic(const double *g, int nx, int ny, int nz, double x, double y, double z)
 {
     const double inv_n[3] = {1.0 / nx, 1.0 / ny, 1.0 / nz};
-    return tricubic_eval<0>(g, nx, ny, nz, inv_n, x, y, z);
+    return tricubic_eval<0>(g, nx, ny, nz, 0, inv_n, x, y, z);
+}
+
+// div_by(x, d, RN(1/d)) against x / d on random operands: returns the number of mismatching bit patterns
+extern "C" long long emu_check_div_by(long long n, unsigned long long seed)
+{
+    unsigned long long st = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+    auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(st >> 11) / 9007199254740992.0; };
+    long long bad = 0;
+    for (long long i = 0; i < n; ++i) {
+        const double d = 0.01 + rnd() * 2.0;                       // grid spacings (Angstrom)
+        const double x = (rnd() - 0.5) * 20.0 * pow(10.0, (int)(rnd() * 12) - 8);
+        const double got = div_by(x, d, 1.0 / d), want = x / d;
+        if (memcmp(&got, &want, sizeof got) != 0 && !(got == 0.0 && want == 0.0)) ++bad;
+    }
+    return bad;
 }

@@ -167,3 +167,12 @@ def test_relax_empty_tile_and_periodic_wrap(emu, relax_golden):
     a, _, _ = emu.relax(static, (0, 1, 0, 1), 6, 0.2, 3.02, dr)
     b, _, _ = emu.relax(rolled, (1, 2, 1, 2), 6, 0.2, 3.02, dr)
     assert np.abs(a[..., 0] - b[..., 0]).max() < 1e-12
+
+
+def test_division_by_known_spacing_is_correctly_rounded(emu):
+    """relax_objective divides the tip offset by dr with `div_by` (multiply + two fused corrections);
+    it must give the bits of the IEEE quotient the reference's numpy computes."""
+    import ctypes as C
+    f = emu.L.emu_check_div_by
+    f.restype, f.argtypes = C.c_longlong, [C.c_longlong, C.c_ulonglong]
+    assert f(10_000_000, 1234) == 0
