@@ -99,9 +99,14 @@ def main(argv=None) -> int:
         z_lo, z_hi = calc.z_window
         nx, ny, _ = calc.rhoS.shape
         a, b = calc.device_array(a_name), calc.device_array(b_name)
+        # a tip array that is exactly zero outside a z-range (a cut-off or synthetic tip) takes the pruned
+        # transform; a CHGCAR tip has a noise floor everywhere and the support comes back as the whole cell
+        support = ops.tip_zsupport(b) if b.shape[2] % 2 == 0 else None
+        if support is not None and support[1] >= b.shape[2]:
+            support = None
 
         def slab(zl, zh):
-            return ops.density_overlap_window(a, b, calc.gridS.dr, zl, zh, alpha, alpha)
+            return ops.density_overlap_window(a, b, calc.gridS.dr, zl, zh, alpha, alpha, tip_support=support)
 
         win = parallel.corr3d_sharded(slab, nx, ny, z_lo, z_hi, device)
         if rank == 0:

@@ -76,6 +76,25 @@ __global__ void __launch_bounds__(DBSPM_THREADS) compact_kernel(const double *W,
                  (long long)gridDim.x * blockDim.x);
 }
 
+// which z-planes of a (nlines, nz) array hold a nonzero value: flags[z] = 1 (flags zeroed by the caller).
+// Streaming 128-bit reads, per-block flags in shared memory, one global store per set plane and block.
+__global__ void __launch_bounds__(256) zsupport_kernel(const double2 *B2, size_t npairs, int nzh, int *flags)
+{
+    extern __shared__ unsigned char seen[];               // 2*nzh
+    for (int i = threadIdx.x; i < 2 * nzh; i += blockDim.x) seen[i] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
+        const double2 v = __ldcs(B2 + i);
+        const int zp = (int)(i % (size_t)nzh);
+        if (v.x != 0.0) seen[2 * zp] = 1;
+        if (v.y != 0.0) seen[2 * zp + 1] = 1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * nzh; i += blockDim.x)
+        if (seen[i]) flags[i] = 1;
+}
+
 // ---- device-resident plan cache (twiddle + position tables; a few KB per distinct length) --
 struct DevPlan {
     HostPlan host;
@@ -224,10 +243,16 @@ static int launch_axis_tma(const cplx *in0, cplx *out0, const cplx *in1, cplx *o
     return DBSPM_OK;
 }
 
+// z-range cut of the caller's arrays read by the first pass of the pruned correlation (planes)
+struct GatherSpec {
+    int src_nz, dst_nz;
+    int z0[2], valid[2];
+};
+
 template <int D>
 static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, int narrays,
                        double alpha0, double alpha1, int use_pow, int n, long long inner, long long outer,
-                       cudaStream_t st, int flags)
+                       cudaStream_t st, int flags, const GatherSpec *g = nullptr)
 {
     DevPlan *pl = nullptr;
     int rc = get_plan(n, st, &pl);
@@ -241,13 +266,22 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     // (256 <= n <= 576: measured 27 % faster at n = 384); the register-staged kernel wins at n = 1024
     // (4-line tiles, FP64/shared-memory bound) and ties below 256
     const bool tma_auto = n >= 256 && axis3_config(n, inner) == 3;
-    if (((flags & DBSPM_CORR_USE_TMA) || (tma_auto && !(flags & DBSPM_CORR_NO_TMA))) && !(flags & DBSPM_CORR_AXIS_V1)) {
+    P.gather = 0;
+    if (g) {
+        // only the register-staged body can remap its loads
+        DBSPM_REQUIRE(axis_v2_ok(pl->host.dev), DBSPM_EUNSUPPORTED, "pruned first pass needs an all-fast-radix plan (n=%d)", n);
+        P.gather = 1;
+        P.g_src_nzh = g->src_nz / 2; P.g_dst_nzh = g->dst_nz / 2;
+        P.g_src_inner = inner / P.g_dst_nzh * P.g_src_nzh;
+        for (int w = 0; w < 2; ++w) { P.g_zp0[w] = g->z0[w] / 2; P.g_valid[w] = g->valid[w] / 2; }
+    }
+    if (!g && ((flags & DBSPM_CORR_USE_TMA) || (tma_auto && !(flags & DBSPM_CORR_NO_TMA))) && !(flags & DBSPM_CORR_AXIS_V1)) {
         bool done = false;
         rc = launch_axis_tma<D>(in0, out0, in1, out1, narrays, alpha0, alpha1, use_pow, n, inner, outer, pl, st, &done);
         if (rc || done) return rc;
     }
     P.plan = pl->host.dev; P.tw = pl->tw; P.pos_of = pl->pos_of; P.freq_of = pl->freq_of;
-    P.v2 = axis_v2_ok(P.plan) && !(flags & DBSPM_CORR_AXIS_V1);
+    P.v2 = axis_v2_ok(P.plan) && (g || !(flags & DBSPM_CORR_AXIS_V1));
     P.tw_smem = 0;
     size_t smem;
     if (P.v2) {
@@ -285,21 +319,11 @@ extern "C" size_t dbspm_corr3d_workspace_bytes(int nx, int ny, int nz, int z_lo,
     return bytes;
 }
 
-extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
-                                int nx, int ny, int nz, int z_lo, int z_hi, double *E_win,
-                                void *workspace, size_t workspace_bytes, int flags, void *stream)
+// the five launches on a problem of z length nz (the caller's, or the pruned length when g != null)
+static int corr3d_core(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                       int nx, int ny, int nz, int z_lo, int z_hi, double *E_win,
+                       void *workspace, int flags, cudaStream_t st, const GatherSpec *g)
 {
-    cudaStream_t st = (cudaStream_t)stream;
-    DBSPM_REQUIRE(A && B && E_win && workspace, DBSPM_EINVAL, "null pointer argument");
-    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 2, DBSPM_EINVAL, "bad shape (%d,%d,%d)", nx, ny, nz);
-    DBSPM_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= nz, DBSPM_EINVAL, "bad window [%d,%d) for nz=%d", z_lo, z_hi, nz);
-    DBSPM_REQUIRE((nz & 1) == 0, DBSPM_EUNSUPPORTED, "nz=%d is odd: the packed real transform needs an even z length", nz);
-    DBSPM_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)E_win & 15) == 0,
-                  DBSPM_EINVAL, "A, B and E_win must be 16-byte aligned");
-    const size_t need = dbspm_corr3d_workspace_bytes(nx, ny, nz, z_lo, z_hi, flags);
-    DBSPM_REQUIRE(workspace_bytes >= need && ((uintptr_t)workspace & 255) == 0, DBSPM_EWORKSPACE,
-                  "workspace needs %zu bytes, 256-byte aligned (got %zu)", need, workspace_bytes);
-
     const int n = nz / 2, nzw = z_hi - z_lo, nwh = (nzw + 1) / 2;
     const size_t N = (size_t)nx * ny * nz;
     unsigned char *ws = (unsigned char *)workspace;
@@ -310,7 +334,7 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
     int rc;
     // forward x (out of place, power fused into the load), then y in place
     if (!(flags & DBSPM_CORR_SKIP_XFWD)) {
-        rc = launch_axis<-1>((const cplx *)A, WA, (const cplx *)B, WB, 2, alphaA, alphaB, 1, nx, (long long)ny * n, 1, st, flags);
+        rc = launch_axis<-1>((const cplx *)A, WA, (const cplx *)B, WB, 2, alphaA, alphaB, 1, nx, (long long)ny * n, 1, st, flags, g);
         if (rc) return rc;
     }
     if (!(flags & DBSPM_CORR_SKIP_YFWD)) {
@@ -373,5 +397,84 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
         compact_kernel<<<(unsigned)blocks, DBSPM_THREADS, 0, st>>>((const double *)W, E_win, ncol, nzw, 2 * nwh);
         DBSPM_CUDA_TRY(cudaGetLastError());
     }
+    return DBSPM_OK;
+}
+
+extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                                int nx, int ny, int nz, int z_lo, int z_hi, double *E_win,
+                                void *workspace, size_t workspace_bytes, int flags, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    DBSPM_REQUIRE(A && B && E_win && workspace, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 2, DBSPM_EINVAL, "bad shape (%d,%d,%d)", nx, ny, nz);
+    DBSPM_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= nz, DBSPM_EINVAL, "bad window [%d,%d) for nz=%d", z_lo, z_hi, nz);
+    DBSPM_REQUIRE((nz & 1) == 0, DBSPM_EUNSUPPORTED, "nz=%d is odd: the packed real transform needs an even z length", nz);
+    DBSPM_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)E_win & 15) == 0,
+                  DBSPM_EINVAL, "A, B and E_win must be 16-byte aligned");
+    const size_t need = dbspm_corr3d_workspace_bytes(nx, ny, nz, z_lo, z_hi, flags);
+    DBSPM_REQUIRE(workspace_bytes >= need && ((uintptr_t)workspace & 255) == 0, DBSPM_EWORKSPACE,
+                  "workspace needs %zu bytes, 256-byte aligned (got %zu)", need, workspace_bytes);
+
+    return corr3d_core(A, B, alphaA, alphaB, dV, nx, ny, nz, z_lo, z_hi, E_win, workspace, flags, st, nullptr);
+}
+
+// ---- z-pruned correlation for a tip that is exactly zero outside s_len planes -----------------
+extern "C" size_t dbspm_corr3d_pruned_workspace_bytes(int nx, int ny, int nz, int z_lo, int z_hi, int s_lo, int s_len, int flags)
+{
+    if (nx < 1 || ny < 1 || nz < 2 || z_lo < 0 || z_hi <= z_lo || z_hi > nz) return 0;
+    const PrunedGeom G = pruned_geometry(nz, z_lo, z_hi, s_lo, s_len);
+    if (!G.use) return dbspm_corr3d_workspace_bytes(nx, ny, nz, z_lo, z_hi, flags);
+    return dbspm_corr3d_workspace_bytes(nx, ny, G.Mp, G.w_lo, G.w_lo + (z_hi - z_lo), flags);
+}
+
+extern "C" int dbspm_corr3d_pruned_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                                       int nx, int ny, int nz, int z_lo, int z_hi, int s_lo, int s_len,
+                                       double *E_win, void *workspace, size_t workspace_bytes, int flags, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    DBSPM_REQUIRE(A && B && E_win && workspace, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 2, DBSPM_EINVAL, "bad shape (%d,%d,%d)", nx, ny, nz);
+    DBSPM_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= nz, DBSPM_EINVAL, "bad window [%d,%d) for nz=%d", z_lo, z_hi, nz);
+    DBSPM_REQUIRE(s_len >= 1 && s_len <= nz, DBSPM_EINVAL, "bad tip support length %d for nz=%d", s_len, nz);
+    DBSPM_REQUIRE((nz & 1) == 0, DBSPM_EUNSUPPORTED, "nz=%d is odd: the packed real transform needs an even z length", nz);
+    DBSPM_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)E_win & 15) == 0,
+                  DBSPM_EINVAL, "A, B and E_win must be 16-byte aligned");
+    const size_t need = dbspm_corr3d_pruned_workspace_bytes(nx, ny, nz, z_lo, z_hi, s_lo, s_len, flags);
+    DBSPM_REQUIRE(workspace_bytes >= need && ((uintptr_t)workspace & 255) == 0, DBSPM_EWORKSPACE,
+                  "workspace needs %zu bytes, 256-byte aligned (got %zu)", need, workspace_bytes);
+    PrunedGeom G = pruned_geometry(nz, z_lo, z_hi, s_lo, s_len);
+    if (G.use) {
+        // the remapped first pass exists in the register-staged body only (all radices of nx fast)
+        DevPlan *pl = nullptr;
+        int rc = get_plan(nx, st, &pl);
+        if (rc) return rc;
+        if (!axis_v2_ok(pl->host.dev)) G.use = 0;
+    }
+    if (!G.use) {
+        DBSPM_REQUIRE(workspace_bytes >= dbspm_corr3d_workspace_bytes(nx, ny, nz, z_lo, z_hi, flags), DBSPM_EWORKSPACE,
+                      "workspace too small for the full-length path");
+        return corr3d_core(A, B, alphaA, alphaB, dV, nx, ny, nz, z_lo, z_hi, E_win, workspace, flags, st, nullptr);
+    }
+    GatherSpec g;
+    g.src_nz = nz; g.dst_nz = G.Mp;
+    g.z0[0] = G.zA0; g.z0[1] = G.zB0; g.valid[0] = G.validA; g.valid[1] = G.validB;
+    return corr3d_core(A, B, alphaA, alphaB, dV, nx, ny, G.Mp, G.w_lo, G.w_lo + (z_hi - z_lo), E_win, workspace, flags, st, &g);
+}
+
+extern "C" int dbspm_zsupport_f64(const double *B, int nx, int ny, int nz, int *plane_nonzero, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    DBSPM_REQUIRE(B && plane_nonzero, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 2, DBSPM_EINVAL, "bad shape (%d,%d,%d)", nx, ny, nz);
+    DBSPM_REQUIRE((nz & 1) == 0 && nz <= 65536, DBSPM_EUNSUPPORTED, "nz=%d: need an even z length <= 65536", nz);
+    DBSPM_REQUIRE(((uintptr_t)B & 15) == 0, DBSPM_EINVAL, "B must be 16-byte aligned");
+    DBSPM_CUDA_TRY(cudaMemsetAsync(plane_nonzero, 0, sizeof(int) * (size_t)nz, st));
+    const size_t npairs = (size_t)nx * ny * (nz / 2);
+    size_t blocks = (npairs + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if ((size_t)nz > 48 * 1024)
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(zsupport_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nz));
+    zsupport_kernel<<<(unsigned)blocks, 256, (size_t)nz, st>>>((const double2 *)B, npairs, nz / 2, plane_nonzero);
+    DBSPM_CUDA_TRY(cudaGetLastError());
     return DBSPM_OK;
 }

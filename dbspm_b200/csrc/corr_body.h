@@ -43,7 +43,57 @@ struct AxisParams {
     const int *freq_of;       // in-place position -> frequency
     int v2;                   // 1: register-first/last body (axis_pass_body_v2)
     int tw_smem;              // v2: stage the twiddle table in shared memory (else read it through L1)
+    // z-pruned correlation (v2 body, first pass only): the pass reads a z-range of the caller's arrays
+    // instead of a packed copy.  Destination line (y, zp) with zp < g_valid[w] comes from source column
+    // y*g_src_nzh + (g_zp0[w] + zp) mod g_src_nzh, row stride g_src_inner; zp >= g_valid[w] reads as zero.
+    int gather;
+    long long g_src_inner;
+    int g_dst_nzh, g_src_nzh;
+    int g_zp0[2], g_valid[2];
 };
+
+// ---- z-pruned correlation: geometry ---------------------------------------------------------
+// When the tip array B is exactly zero outside the planes (s_lo + m) mod nz, m in [0, s_len), the window
+// planes [z_lo, z_hi) of the periodic correlation only see the planes z_lo + s_lo ... z_hi - 1 + s_lo +
+// s_len - 1 of A.  Both ranges are cut out (starting on even planes, the packed transform pairs z = 2k,
+// 2k+1), zero-padded to a common FFT-friendly length Mp >= their linear-correlation length, and
+// correlated periodically over Mp: no wrap-around term reaches the window, which sits at [w_lo, w_lo+nzw).
+struct PrunedGeom {
+    int use;                  // 0: no gain (support too wide) -> full-length path
+    int Mp;                   // pruned z length (even, Mp/2 is 2-3-5-7 smooth)
+    int zA0, zB0;             // first source plane of the A / B cut (even)
+    int validA, validB;       // planes taken from the source (even); the rest of Mp is zero
+    int w_lo;                 // window start inside the pruned problem (0 or 1)
+};
+
+HD bool pruned_smooth(int m)
+{
+    const int pr[4] = {2, 3, 5, 7};
+    for (int i = 0; i < 4; ++i) while (m % pr[i] == 0) m /= pr[i];
+    return m == 1;
+}
+
+HD PrunedGeom pruned_geometry(int nz, int z_lo, int z_hi, int s_lo, int s_len)
+{
+    PrunedGeom g;
+    g.use = 0; g.Mp = nz; g.zA0 = g.zB0 = 0; g.validA = g.validB = nz; g.w_lo = z_lo;
+    if (s_len < 1 || s_len >= nz || (nz & 1)) return g;
+    s_lo = ((s_lo % nz) + nz) % nz;
+    const int nzw = z_hi - z_lo;
+    g.zB0 = s_lo & ~1;
+    const int Lb = s_lo - g.zB0 + s_len;
+    const int a0 = (z_lo + g.zB0) % nz;
+    g.zA0 = a0 & ~1;
+    g.w_lo = a0 - g.zA0;
+    const int Ma = g.w_lo + nzw + Lb - 1;
+    g.validB = (Lb + 1) & ~1;
+    g.validA = (Ma + 1) & ~1;
+    int Mp = g.validA > g.validB ? g.validA : g.validB;
+    while (!pruned_smooth(Mp / 2)) Mp += 2;
+    g.Mp = Mp;
+    g.use = (Mp < nz && 10 * (long long)Mp <= 9 * (long long)nz) ? 1 : 0;     // worth it only below 90 % of the full length
+    return g;
+}
 
 HD size_t axis_smem_bytes(int n, int tshift)
 {
@@ -152,7 +202,7 @@ HD void axis2_config(int n, long long inner, int nstages, int *tshift, int *tw_s
 
 template <int D, int R>
 HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gin, cplx *gout, int tcount,
-                    bool do_pow, double alpha, int tid, int nthr)
+                    bool do_pow, double alpha, int which, long long i0, int tid, int nthr)
 {
     const int n = P.n, q = n / R, tmask = (1 << P.tshift) - 1;
     const bool single = P.plan.nstages == 1;
@@ -160,10 +210,21 @@ HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gi
     for (int idx = tid; idx < total; idx += nthr) {
         const int t = idx & tmask, j = idx >> P.tshift;
         cplx v[R];
-        if (t < tcount) {
-            const cplx *src = gin + (size_t)j * P.inner + t;
+        bool have = t < tcount;
+        const cplx *src = gin + (size_t)j * P.inner + t;
+        size_t rstride = (size_t)P.inner;
+        if (P.gather && have) {
+            const long long i = i0 + t, y = i / P.g_dst_nzh;
+            const int zp = (int)(i - y * P.g_dst_nzh);
+            int zs = P.g_zp0[which] + zp;
+            zs = zs >= P.g_src_nzh ? zs - P.g_src_nzh : zs;
+            have = zp < P.g_valid[which];
+            rstride = (size_t)P.g_src_inner;
+            src = P.in[which] + ((size_t)y * P.g_src_nzh + zs) + (size_t)j * rstride;
+        }
+        if (have) {
 #pragma unroll
-            for (int k = 0; k < R; ++k) v[k] = ld_stream(src + (size_t)k * q * P.inner);
+            for (int k = 0; k < R; ++k) v[k] = ld_stream(src + (size_t)k * q * rstride);
             if (do_pow) {
 #pragma unroll
                 for (int k = 0; k < R; ++k) { v[k].x = pow_nonneg(v[k].x, alpha); v[k].y = pow_nonneg(v[k].y, alpha); }
@@ -235,13 +296,13 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
         BLOCK_SYNC();
     }
     switch (pl.radix[0]) {
-    case 2: axis2_first<D, 2>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
-    case 3: axis2_first<D, 3>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
-    case 4: axis2_first<D, 4>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
-    case 5: axis2_first<D, 5>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
-    case 7: axis2_first<D, 7>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
-    case 8: axis2_first<D, 8>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
-    default: axis2_first<D, 16>(P, s, tw, gin, gout, tcount, do_pow, alpha, tid, nthr); break;
+    case 2: axis2_first<D, 2>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
+    case 3: axis2_first<D, 3>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
+    case 4: axis2_first<D, 4>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
+    case 5: axis2_first<D, 5>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
+    case 7: axis2_first<D, 7>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
+    case 8: axis2_first<D, 8>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
+    default: axis2_first<D, 16>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
     }
     if (pl.nstages == 1) return;
     BLOCK_SYNC();

@@ -67,13 +67,48 @@ def release_workspace() -> None:
 
 
 # ------------------------------------------------------------------------------------ sr / es
+def circular_support(nonzero) -> tuple[int, int]:
+    """Smallest circular interval (start, length) of plane indices that covers every True of `nonzero`
+    (a tip centred on the cell origin occupies planes [0, h] and [nz-h, nz): start = nz-h, length 2h+1).
+    All False -> (0, 1); no False -> (0, nz)."""
+    f = np.asarray(nonzero, dtype=bool)
+    nz = f.size
+    if not f.any():
+        return 0, 1
+    if f.all():
+        return 0, nz
+    # longest circular run of empty planes; the support is its complement
+    z = np.flatnonzero(f)
+    gaps = np.diff(np.concatenate([z, [z[0] + nz]])) - 1          # empty planes after each occupied one
+    g = int(np.argmax(gaps))
+    start = int(z[(g + 1) % z.size])
+    return start, nz - int(gaps[g])
+
+
+def tip_zsupport(rho1, device=None) -> tuple[int, int]:
+    """(s_lo, s_len): the z-planes (s_lo + m) mod nz, m < s_len, outside which the tip array is exactly
+    zero (one streaming read of the array on the device, then a synchronising copy of nz flags)."""
+    on_device = isinstance(rho1, torch.Tensor) and rho1.is_cuda
+    dev = rho1.device if on_device else _device(device)
+    b = _to_dev(rho1, dev)
+    nx, ny, nz = (int(v) for v in b.shape)
+    with torch.cuda.device(dev):
+        flags = torch.empty(nz, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().dbspm_zsupport_f64(b.data_ptr(), nx, ny, nz, flags.data_ptr(), _stream_ptr(dev)))
+        return circular_support(flags.cpu().numpy() != 0)
+
+
 def density_overlap_window(rho0, rho1, dr, z_lo=0, z_hi=None, alpha0=1.0, alpha1=1.0, out=None, device=None,
-                           flags=0):
+                           flags=0, tip_support=None):
     """dV * sum_r rho0[r]^alpha0 * rho1[(r-R) mod N]^alpha1 for R on planes z_lo..z_hi-1.
 
     Fuses what dbspm:329-330 / :348-349 do in three passes (`**ALPHA`, get_density_overlap,
     `[nidx]`).  Returns (Nx,Ny,z_hi-z_lo): a CUDA tensor if the inputs were CUDA tensors,
-    else a numpy array."""
+    else a numpy array.
+
+    tip_support: None -> full-length transform; "auto" -> find the z-support of rho1 (tip_zsupport)
+    and take the z-pruned path when it pays; (s_lo, s_len) -> the caller's claim that rho1 is exactly
+    zero outside those planes (e.g. found once for a tip that is used for many samples)."""
     on_device = isinstance(rho0, torch.Tensor) and rho0.is_cuda
     dev = rho0.device if on_device else _device(device)
     a = _to_dev(rho0, dev)
@@ -84,8 +119,16 @@ def density_overlap_window(rho0, rho1, dr, z_lo=0, z_hi=None, alpha0=1.0, alpha1
     z_hi = nz if z_hi is None else int(z_hi)
     z_lo = int(z_lo)
     L = _lib.lib()
+    if isinstance(tip_support, str):
+        if tip_support != "auto":
+            raise ValueError("tip_support must be None, 'auto' or (s_lo, s_len)")
+        tip_support = tip_zsupport(b) if nz % 2 == 0 else None
     with torch.cuda.device(dev):
-        need = L.dbspm_corr3d_workspace_bytes(nx, ny, nz, z_lo, z_hi, 0)
+        if tip_support is None:
+            need = L.dbspm_corr3d_workspace_bytes(nx, ny, nz, z_lo, z_hi, 0)
+        else:
+            s_lo, s_len = (int(v) for v in tip_support)
+            need = L.dbspm_corr3d_pruned_workspace_bytes(nx, ny, nz, z_lo, z_hi, s_lo, s_len, 0)
         if need == 0:
             raise ValueError(f"bad window [{z_lo},{z_hi}) for shape {(nx, ny, nz)}")
         ws = _workspace(need, dev)
@@ -95,9 +138,14 @@ def density_overlap_window(rho0, rho1, dr, z_lo=0, z_hi=None, alpha0=1.0, alpha1
                   and tuple(out.shape) == (nx, ny, z_hi - z_lo)):
             raise ValueError("out must be a contiguous float64 CUDA tensor of the window shape")
         dV = float(np.prod(np.asarray(dr, dtype=np.float64)))
-        _lib.check(L.dbspm_corr3d_f64(a.data_ptr(), b.data_ptr(), float(alpha0), float(alpha1), dV,
-                                      nx, ny, nz, z_lo, z_hi, out.data_ptr(), ws.data_ptr(), ws.numel(), int(flags),
-                                      _stream_ptr(dev)))
+        if tip_support is None:
+            _lib.check(L.dbspm_corr3d_f64(a.data_ptr(), b.data_ptr(), float(alpha0), float(alpha1), dV,
+                                          nx, ny, nz, z_lo, z_hi, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          int(flags), _stream_ptr(dev)))
+        else:
+            _lib.check(L.dbspm_corr3d_pruned_f64(a.data_ptr(), b.data_ptr(), float(alpha0), float(alpha1), dV,
+                                                 nx, ny, nz, z_lo, z_hi, s_lo, s_len, out.data_ptr(), ws.data_ptr(),
+                                                 ws.numel(), int(flags), _stream_ptr(dev)))
     return out if on_device else out.cpu().numpy()
 
 

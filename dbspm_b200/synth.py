@@ -144,6 +144,7 @@ def make_tip(cfg: Config, device="cpu", variant="noisy"):
         rc = min(3.5, 0.45 * min(lx, ly, lz))
         t = torch.clamp(rmin / rc, max=1.0)
         rho = rho * (1 - t * t) ** 2          # C^1 at the cutoff, exact zero beyond it
+        cores = cores * (1 - t * t) ** 2      # so that nrhoT is compact too (es takes the pruned path as well)
     elif variant == "noisy":
         gdev = device if torch.device(device).type == "cuda" else "cpu"   # big grids: draw on the GPU
         g = torch.Generator(device=gdev).manual_seed(cfg.seed + 7)

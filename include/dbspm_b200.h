@@ -73,6 +73,21 @@ int dbspm_corr3d_f64(const double *A, const double *B, double alphaA, double alp
                      int nx, int ny, int nz, int z_lo, int z_hi, double *E_win,
                      void *workspace, size_t workspace_bytes, int flags, void *stream);
 
+/* ---- sr / es with a tip that is exactly zero outside a z-range ("compact tip") ----
+ * Same result as dbspm_corr3d_f64 when B[x,y,z] == 0 for every z outside the s_len planes
+ * (s_lo + m) mod nz, m in [0, s_len): only the planes of A the window can see are transformed, on a
+ * z length Mp ~ (z_hi - z_lo) + s_len instead of nz (all five passes shrink by Mp/nz; the first pass
+ * reads the z-ranges of A and B in place, no packed copy).  Falls back to the full-length path when
+ * Mp > 0.9 nz or nx has a prime factor > 7.  The support is the caller's claim: find it with
+ * dbspm_zsupport_f64 (plane_nonzero: device int[nz], 1 where a plane of B holds a nonzero value;
+ * the smallest circular interval covering the ones is (s_lo, s_len)).  Replaces the same reference
+ * lines as dbspm_corr3d_f64; the reference always pays the full transform.                      */
+size_t dbspm_corr3d_pruned_workspace_bytes(int nx, int ny, int nz, int z_lo, int z_hi, int s_lo, int s_len, int flags);
+int dbspm_corr3d_pruned_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                            int nx, int ny, int nz, int z_lo, int z_hi, int s_lo, int s_len, double *E_win,
+                            void *workspace, size_t workspace_bytes, int flags, void *stream);
+int dbspm_zsupport_f64(const double *B, int nx, int ny, int nz, int *plane_nonzero, void *stream);
+
 /* ---- static potential assembly: acc = (init ? 0 : acc) + comp*scale  (separate mul, add) -- */
 int dbspm_static_accumulate_f64(double *acc, const double *comp, double scale, size_t n,
                                 int init, void *stream);

@@ -27,15 +27,26 @@ static int pick_tshift(int n, long long inner)
     return 0;
 }
 
+struct EmuGather { int src_nz, dst_nz, z0[2], valid[2]; };
+
 template <int D>
 static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, int narrays, double a0, double a1,
-                    int use_pow, int n, long long inner, long long outer, int force_tshift)
+                    int use_pow, int n, long long inner, long long outer, int force_tshift, const EmuGather *g = nullptr)
 {
     HostPlan hp;
     if (!dbspm_make_plan(n, hp)) return -2;
     AxisParams P;
     P.in[0] = in0; P.in[1] = in1; P.out[0] = out0; P.out[1] = out1;
     P.alpha[0] = a0; P.alpha[1] = a1; P.use_pow = use_pow; P.narrays = narrays;
+    P.gather = 0;
+    if (g) {   // as launch_axis(): the remapped first pass exists in the register-staged body only
+        if (!axis_v2_ok(hp.dev)) return -2;
+        if (force_tshift >= 100) force_tshift = -1;
+        P.gather = 1;
+        P.g_src_nzh = g->src_nz / 2; P.g_dst_nzh = g->dst_nz / 2;
+        P.g_src_inner = inner / P.g_dst_nzh * P.g_src_nzh;
+        for (int w = 0; w < 2; ++w) { P.g_zp0[w] = g->z0[w] / 2; P.g_valid[w] = g->valid[w] / 2; }
+    }
     if (force_tshift >= 200 && (!axis_v2_ok(hp.dev) || hp.dev.nstages > 3)) force_tshift = -1;   // launcher falls back too
     if (force_tshift >= 200) {
         // TMA-fed persistent body (axis_tma_body) with the two TMA operations emulated by copies;
@@ -88,8 +99,8 @@ extern "C" size_t emu_corr3d_workspace_bytes(int nx, int ny, int nz, int z_lo, i
     return bytes;
 }
 
-extern "C" int emu_corr3d_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
-                              int nx, int ny, int nz, int z_lo, int z_hi, double *E_win, int force_tshift)
+static int emu_corr3d_core(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                           int nx, int ny, int nz, int z_lo, int z_hi, double *E_win, int force_tshift, const EmuGather *g)
 {
     if (nz & 1) return -2;
     const int n = nz / 2, nzw = z_hi - z_lo, nwh = (nzw + 1) / 2;
@@ -98,7 +109,7 @@ extern "C" int emu_corr3d_f64(const double *A, const double *B, double alphaA, d
     cplx *W = (cplx *)E_win;
     if (nzw & 1) { Wodd.resize((size_t)nx * ny * nwh); W = Wodd.data(); }
     int rc;
-    if ((rc = run_axis<-1>((const cplx *)A, WA.data(), (const cplx *)B, WB.data(), 2, alphaA, alphaB, 1, nx, (long long)ny * n, 1, force_tshift))) return rc;
+    if ((rc = run_axis<-1>((const cplx *)A, WA.data(), (const cplx *)B, WB.data(), 2, alphaA, alphaB, 1, nx, (long long)ny * n, 1, force_tshift, g))) return rc;
     if ((rc = run_axis<-1>(WA.data(), WA.data(), WB.data(), WB.data(), 2, 1.0, 1.0, 0, ny, n, nx, force_tshift))) return rc;
     {
         HostPlan hp, hpN;
@@ -120,6 +131,30 @@ extern "C" int emu_corr3d_f64(const double *A, const double *B, double alphaA, d
     if ((rc = run_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)ny * nwh, 1, force_tshift))) return rc;
     if (nzw & 1) compact_body((const double *)W, E_win, (long long)nx * ny, nzw, 2 * nwh, 0, 1);
     return 0;
+}
+
+extern "C" int emu_corr3d_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                              int nx, int ny, int nz, int z_lo, int z_hi, double *E_win, int force_tshift)
+{
+    return emu_corr3d_core(A, B, alphaA, alphaB, dV, nx, ny, nz, z_lo, z_hi, E_win, force_tshift, nullptr);
+}
+
+// what dbspm_corr3d_pruned_f64 does; returns the pruned z length (or nz when the full path was taken), < 0 on error
+extern "C" int emu_corr3d_pruned_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                                     int nx, int ny, int nz, int z_lo, int z_hi, int s_lo, int s_len, double *E_win, int force_tshift)
+{
+    PrunedGeom G = pruned_geometry(nz, z_lo, z_hi, s_lo, s_len);
+    HostPlan hp;
+    if (!dbspm_make_plan(nx, hp)) return -2;
+    if (G.use && !axis_v2_ok(hp.dev)) G.use = 0;
+    if (!G.use) {
+        const int rc = emu_corr3d_core(A, B, alphaA, alphaB, dV, nx, ny, nz, z_lo, z_hi, E_win, force_tshift, nullptr);
+        return rc ? rc : nz;
+    }
+    EmuGather g;
+    g.src_nz = nz; g.dst_nz = G.Mp; g.z0[0] = G.zA0; g.z0[1] = G.zB0; g.valid[0] = G.validA; g.valid[1] = G.validB;
+    const int rc = emu_corr3d_core(A, B, alphaA, alphaB, dV, nx, ny, G.Mp, G.w_lo, G.w_lo + (z_hi - z_lo), E_win, force_tshift, &g);
+    return rc ? rc : G.Mp;
 }
 
 // plain 1-D FFT of T interleaved lines through the tile routine (plan / butterfly unit test)

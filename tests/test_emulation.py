@@ -176,3 +176,33 @@ def test_division_by_known_spacing_is_correctly_rounded(emu):
     f = emu.L.emu_check_div_by
     f.restype, f.argtypes = C.c_longlong, [C.c_longlong, C.c_ulonglong]
     assert f(10_000_000, 1234) == 0
+
+
+@pytest.mark.parametrize("shape,window,support", [
+    ((8, 6, 40), (10, 16), (36, 9)),      # support wraps through z = 0, even start
+    ((8, 6, 40), (11, 18), (37, 8)),      # odd start of both cuts, odd window
+    ((6, 10, 48), (0, 5), (45, 7)),       # window at the bottom: the A cut wraps
+    ((6, 10, 48), (40, 48), (2, 5)),      # window at the top: the A cut wraps upwards
+    ((12, 4, 64), (20, 21), (0, 1)),      # single-plane tip
+    ((4, 4, 32), (3, 30), (30, 6)),       # window + support > 0.9 nz -> full-length path
+    ((22, 4, 40), (10, 16), (36, 9)),     # nx = 2*11: remapped first pass unavailable -> full-length path
+])
+def test_corr3d_pruned_equals_full_correlation(emu, shape, window, support):
+    """Tip exactly zero outside `support` planes: the z-pruned path (cut, zero-pad, shorter transform)
+    gives the window of the full periodic correlation."""
+    rng = np.random.default_rng(sum(shape) + window[0])
+    nz = shape[2]
+    a = rng.random(shape)
+    b = np.zeros(shape)
+    s_lo, s_len = support
+    planes = (s_lo + np.arange(s_len)) % nz
+    b[:, :, planes] = rng.random(shape[:2] + (s_len,)) - 0.3
+    dr = np.array([0.1, 0.2, 0.3])
+    ref = O.density_overlap_fft(a ** 1.08, b, dr)[:, :, window[0]:window[1]]
+    got, used = emu.corr3d_pruned(a, b, dr, window[0], window[1], s_lo, s_len, alpha0=1.08)
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    expect_full = shape in [(4, 4, 32), (22, 4, 40)]
+    assert (used == nz) == expect_full, used
+    # a support claim wider than the real one is harmless
+    got2, _ = emu.corr3d_pruned(a, b, dr, window[0], window[1], s_lo - 2, s_len + 3, alpha0=1.08)
+    assert np.abs(got2 - ref).max() <= 1e-12 * np.abs(ref).max()

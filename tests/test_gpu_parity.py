@@ -410,3 +410,45 @@ def test_batched_parameter_sweep(ops):
         assert (dE > 1e-6).mean() < 1e-2, (dE > 1e-6).mean()
         dev_pos = _dev_positions(r, ref, cfg.rpivot)
         assert (dev_pos > 1e-6).mean() < 2e-2, (dev_pos > 1e-6).mean()
+
+
+# ------------------------------------------------------------------------------------ compact tip
+@pytest.mark.parametrize("name", ["pyridine", "tma_cu111"])
+def test_compact_tip_takes_pruned_path_and_matches_full(ops, name):
+    """Compact synthetic tip (exactly zero beyond 3.5 A): support detection on the device, the z-pruned
+    transform, and agreement with the full-length transform (and the numpy oracle at pyridine size)."""
+    from dbspm_b200 import synth
+    cfg = synth.CONFIGS[name]
+    dev = torch.device("cuda", 0)
+    nx, ny, nz = cfg.shape
+    dr = np.array(cfg.cell) / np.array(cfg.shape)
+    rhoS, potS, _ = synth.make_sample(cfg, device=dev)
+    rhoT, nrhoT = synth.make_tip(cfg, device=dev, variant="compact")
+    s_lo, s_len = ops.tip_zsupport(rhoT)
+    flags = (rhoT != 0).any(dim=0).any(dim=0).cpu().numpy()
+    assert (s_lo, s_len) == ops.circular_support(flags)
+    assert s_len < nz and (s_lo + s_len) % nz <= s_len               # wraps through z = 0
+    z_lo, z_hi = (76, 130) if name == "pyridine" else (76, 92)       # tma_cu111 (nz = 160): a rank's slab of the window
+    for a, b, al in ((rhoS, rhoT, cfg.alpha), (potS, nrhoT, 1.0)):
+        full = ops.density_overlap_window(a, b, dr, z_lo, z_hi, al, al)
+        auto = ops.density_overlap_window(a, b, dr, z_lo, z_hi, al, al, tip_support="auto")
+        scale = float(full.abs().max())
+        assert float((auto - full).abs().max()) <= 1e-12 * scale
+        odd = ops.density_overlap_window(a, b, dr, z_lo + 1, z_hi - 2, al, al, tip_support=ops.tip_zsupport(b))
+        assert float((odd - full[:, :, 1:-2]).abs().max()) <= 1e-12 * scale
+    if name == "pyridine":
+        ref = O.density_overlap_fft(potS.cpu().numpy(), nrhoT.cpu().numpy(), dr)[:, :, z_lo:z_hi]
+        assert _rel(auto.cpu().numpy(), ref) <= 1e-9
+
+
+def test_pruned_entry_argument_checks(ops):
+    from dbspm_b200._lib import DbspmError, EINVAL
+    a = np.ones((4, 4, 8))
+    with pytest.raises(DbspmError) as e:
+        ops.density_overlap_window(a, a, np.ones(3), 0, 4, tip_support=(0, 0))
+    assert e.value.code == EINVAL
+    with pytest.raises(ValueError):
+        ops.density_overlap_window(a, a, np.ones(3), 0, 4, tip_support="always")
+    # a tip that fills the cell: "auto" silently takes the full-length path
+    out = ops.density_overlap_window(a, a, np.ones(3), 0, 4, tip_support="auto")
+    assert np.allclose(out, 4 * 4 * 8)

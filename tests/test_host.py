@@ -226,3 +226,15 @@ def test_sph2cart_matches_definition():
     x, y, z = sph2cart(th, az, 3.02)
     assert np.allclose(x ** 2 + y ** 2 + z ** 2, 3.02 ** 2)
     assert np.allclose(z, 3.02 * np.cos(th))
+
+
+def test_circular_support_host_logic():
+    from dbspm_b200.interactions import circular_support
+    f = np.zeros(40, bool); f[[0, 1, 2, 37, 38, 39]] = True
+    assert circular_support(f) == (37, 6)
+    f = np.zeros(40, bool); f[[5, 9]] = True
+    assert circular_support(f) == (5, 5)
+    assert circular_support(np.zeros(8, bool)) == (0, 1)
+    assert circular_support(np.ones(8, bool)) == (0, 8)
+    f = np.zeros(10, bool); f[[9]] = True
+    assert circular_support(f) == (9, 1)
