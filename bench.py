@@ -254,11 +254,12 @@ def run_gpu_arm(args):
         e.record()
         return e
 
-    def corr_phase(src, marks=None):
+    def corr_phase(src, marks=None, supports=None):
         for (which, zl, zh), buf in zip(jobs, bufs):
             a, b, al = src[which]
             if zh > zl:
-                ops.density_overlap_window(a, b, dr, zl, zh, al, al, out=buf)
+                ops.density_overlap_window(a, b, dr, zl, zh, al, al, out=buf,
+                                           tip_support=supports[which] if supports else None)
                 launches["n"] += 5 + (1 if (zh - zl) & 1 else 0)
             if marks is not None:
                 marks.append(ev())
@@ -354,6 +355,31 @@ def run_gpu_arm(args):
     relax_ms = float(np.mean(ts))
     relax_ms_max, = max_over_ranks([relax_ms])
 
+    # ---- the same sr+es with the compact tip variant (exactly zero beyond 3.5 A): z-pruned path ----
+    compact = None
+    if not args.no_compact:
+        rhoTc, nrhoTc = synth.make_tip(cfg, dev, "compact")
+        sup = {0: ops.tip_zsupport(rhoTc), 1: ops.tip_zsupport(nrhoTc)}
+        src_c = {0: (rhoS, rhoTc, cfg.alpha), 1: (potS, nrhoTc, 1.0)}
+        for _ in range(2):
+            corr_phase(src_c, None, sup)
+        barrier()
+        ts = []
+        for _ in range(args.steps):
+            a = ev()
+            corr_phase(src_c, None, sup)
+            b = ev(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        barrier()
+        t_c, = max_over_ranks([float(np.mean(ts))])
+        compact = {"value": 2 * N / (t_c * 1e-3), "unit": UNIT, "ms_sr_plus_es": t_c,
+                   "tip_support_planes": {"rhoT": list(sup[0]), "nrhoT": list(sup[1])},
+                   "note": "tip arrays exactly zero outside the listed (start, length) z-planes: only the planes of the "
+                           "sample the window can see are transformed (dbspm_corr3d_pruned_f64); support scan not timed "
+                           "(once per tip)"}
+        del rhoTc, nrhoTc, src_c
+        torch.cuda.empty_cache()
+
     # ---- end to end: pinned host inputs in, results out, inside the timed region -----------
     e2e = None
     if not args.no_e2e:
@@ -442,7 +468,7 @@ def run_gpu_arm(args):
                                    f"x-tile x{world} (relax), gather to rank 0") if world > 1 else "single GPU"},
         "relax": {"value": nx * ny * nz_relax / (relax_ms_max * 1e-3), "unit": "tip positions/s",
                   "ms": relax_ms_max, "mean_nfev": nfev_mean, "in_step_ms_static_relax_gather": t_rest},
-        "stages_ms": stages, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+        "stages_ms": stages, "compact_tip": compact, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": n_launch, "clocks": clk.summary(), "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line), flush=True)
@@ -460,6 +486,7 @@ def main():
     ap.add_argument("--workload", default="large_slab", choices=sorted(WORKLOAD_DESC))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-compact", action="store_true", help="skip the compact-tip (z-pruned path) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -150,3 +150,43 @@ def relax_sharded(compute_tile, nx, device):
         if rank == 0:
             out[key] = torch.cat(parts, dim=0)
     return out if rank == 0 else None
+
+
+def sweep_assignment(param_sets, world: int):
+    """Which parameter sets (indices into `param_sets`, each (alpha, V0, kappa)) a rank relaxes in a
+    multi-GPU sweep.  Sets are dealt in contiguous blocks after sorting by alpha,
+    so that a rank needs as few distinct sr grids (one forward correlation per alpha) as possible;
+    block sizes differ by at most one."""
+    order = sorted(range(len(param_sets)), key=lambda i: (float(param_sets[i][0]), i))
+    return [[order[k] for k in range(lo, hi)] for lo, hi in split_range(0, len(order), world)]
+
+
+def gather_sweep(results, assignment, keys=("E", "theta", "phi", "tip_x", "tip_y", "tip_z"), dst: int = 0):
+    """results: this rank's relax dicts in the order of assignment[rank].  Rank `dst` returns the dicts
+    of every set in the original order of the parameter list (tensors only for `keys`), others None."""
+    rank, world = _world()
+    if world == 1:
+        out = [None] * sum(len(a) for a in assignment)
+        for i, r in zip(assignment[0], results):
+            out[i] = r
+        return out
+    shape = None
+    for r in results:
+        shape = tuple(r[keys[0]].shape)
+    meta = [None] * world
+    dist.all_gather_object(meta, shape)
+    shape = next(m for m in meta if m is not None)
+    dev = results[0][keys[0]].device if results else torch.device("cuda", torch.cuda.current_device()) \
+        if torch.cuda.is_available() else torch.device("cpu")
+    if results:
+        mine = torch.stack([torch.stack([r[k] for k in keys]) for r in results])
+    else:
+        mine = torch.empty((0, len(keys)) + shape, dtype=torch.float64, device=dev)
+    parts = _gather_padded(mine.contiguous(), [len(a) for a in assignment], dst=dst)
+    if rank != dst:
+        return None
+    out = [None] * sum(len(a) for a in assignment)
+    for a, part in zip(assignment, parts):
+        for j, i in enumerate(a):
+            out[i] = {k: part[j, q] for q, k in enumerate(keys)}
+    return out

@@ -27,6 +27,16 @@ for name in sys.argv[1:] or ["pyridine", "tma_cu111", "large_slab"]:
         res[label] = float(np.median(ts))
         if label == "full": ref = o.clone()
         if label == "pruned": err = float((o - ref).abs().max() / ref.abs().max())
+    SKIP = {"x_fwd": 1 << 8, "y_fwd": 1 << 9, "z": 1 << 10, "y_inv": 1 << 11, "x_inv": 1 << 12}
+    st = {}
+    for nm, bit in SKIP.items():
+        ts = []
+        for it in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); ops.density_overlap_window(potS, nrhoT, dr, z_lo, z_hi, out=out, flags=sum(SKIP.values()) & ~bit, tip_support=sup); b.record(); torch.cuda.synchronize()
+            if it: ts.append(a.elapsed_time(b))
+        st[nm] = round(float(np.mean(ts)), 3)
+    print("   pruned stages", st)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); ops.tip_zsupport(nrhoT); b.record(); torch.cuda.synchronize()
     print(f"{name}: support {sup} of nz={cfg.shape[2]} | es full {res['full']:.3f} ms, pruned {res['pruned']:.3f} ms "

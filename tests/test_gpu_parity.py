@@ -452,3 +452,16 @@ def test_pruned_entry_argument_checks(ops):
     # a tip that fills the cell: "auto" silently takes the full-length path
     out = ops.density_overlap_window(a, a, np.ones(3), 0, 4, tip_support="auto")
     assert np.allclose(out, 4 * 4 * 8)
+
+
+def test_npz_reader_pins_and_uploads(tmp_path):
+    from dbspm_b200.npzio import read_npz
+    rng = np.random.default_rng(11)
+    a = rng.random((128, 128, 40))
+    f = tmp_path / "tip.npz"
+    np.savez(f, rhoT=a, nrhoT=a - a.mean(), cell=np.eye(3))
+    host = read_npz(f)
+    assert host["rhoT"].is_pinned() and np.array_equal(host["rhoT"].numpy(), a)
+    dev = read_npz(f, keys=["rhoT", "nrhoT", "cell"], device=torch.device("cuda", 0), dtype=torch.float64)
+    assert dev["rhoT"].is_cuda and torch.equal(dev["rhoT"].cpu(), torch.from_numpy(a))
+    assert isinstance(dev["cell"], np.ndarray)

@@ -196,6 +196,17 @@ if rank == 0:
     assert torch.equal(wins[0], full2[0]) and torch.equal(wins[1], full2[1]), "interaction gather"
 else:
     assert wins is None
+# parameter sweep: sets dealt by alpha, results back on rank 0 in the caller's order
+sets = [(1.08, 40.0, 0.2), (1.0, 40.0, 0.2), (1.08, 50.0, 0.2), (1.0, 50.0, 0.24), (1.12, 35.0, 0.2)]
+asg = parallel.sweep_assignment(sets, 2)
+assert asg == [[1, 3], [0, 2, 4]], asg
+mine = [{{"E": torch.full((2, 3), float(i)), "tip_x": torch.full((2, 3), 10.0 + i)}} for i in asg[rank]]
+got = parallel.gather_sweep(mine, asg, keys=("E", "tip_x"))
+if rank == 0:
+    assert [float(g["E"][0, 0]) for g in got] == [0.0, 1.0, 2.0, 3.0, 4.0]
+    assert [float(g["tip_x"][1, 2]) for g in got] == [10.0, 11.0, 12.0, 13.0, 14.0]
+else:
+    assert got is None
 t = torch.arange(3.0) if rank == 0 else torch.zeros(3)
 parallel.broadcast_(t)
 assert torch.equal(t, torch.arange(3.0))
@@ -238,3 +249,39 @@ def test_circular_support_host_logic():
     assert circular_support(np.ones(8, bool)) == (0, 8)
     f = np.zeros(10, bool); f[[9]] = True
     assert circular_support(f) == (9, 1)
+
+
+def test_sweep_assignment_balances_and_groups_alphas():
+    from dbspm_b200.parallel import sweep_assignment
+    sets = [(a, v, 0.2) for a in (1.0, 1.04, 1.08, 1.12) for v in (35.0, 42.9, 50.0, 60.0)]
+    for world in (1, 2, 3, 4, 8, 16, 20):
+        asg = sweep_assignment(sets, world)
+        assert sorted(i for a in asg for i in a) == list(range(16))
+        assert max(len(a) for a in asg) - min(len(a) for a in asg) <= 1
+    asg = sweep_assignment(sets, 4)
+    assert all(len({sets[i][0] for i in a}) == 1 for a in asg)       # one sr grid per rank
+
+
+def test_npz_reader_matches_numpy_load(tmp_path):
+    """dbspm_b200.npzio.read_npz (direct payload reads, pinned when a GPU is present) returns what np.load
+    returns, for stored and compressed files, big and small members, and object members."""
+    import torch
+    from dbspm_b200.npzio import read_npz
+    rng = np.random.default_rng(3)
+    a = rng.random((96, 96, 64)); b = (rng.random((300, 300, 8)) * 10).astype(np.int32)
+    f = tmp_path / "sample.npz"
+    np.savez(f, rhoS=a, potS=-a, big=b, cell=np.eye(3), numbers=np.array([1, 6]), zref=np.array(None, dtype=object))
+    r = read_npz(f)
+    with np.load(f, allow_pickle=True) as ref:
+        assert set(r) == set(ref.files)
+        for k in ref.files:
+            got = r[k].numpy() if isinstance(r[k], torch.Tensor) else r[k]
+            assert got.dtype == ref[k].dtype and got.shape == ref[k].shape
+            assert (got == ref[k]).all() if got.dtype != object else got.item() is None
+    assert isinstance(r["rhoS"], torch.Tensor) and isinstance(r["cell"], np.ndarray)
+    assert list(read_npz(f, keys=["potS"])) == ["potS"]
+    with pytest.raises(KeyError):
+        read_npz(f, keys=["nope"])
+    fc = tmp_path / "c.npz"
+    np.savez_compressed(fc, rhoS=a)
+    assert np.array_equal(read_npz(fc)["rhoS"], a)
