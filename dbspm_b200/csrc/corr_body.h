@@ -178,7 +178,7 @@ HD bool axis_v2_ok(const FftPlanDev &pl)
     if (pl.nstages < 1) return false;
     for (int i = 0; i < pl.nstages; ++i) {
         const int r = pl.radix[i];
-        if (!(r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16)) return false;
+        if (!fast_radix(r)) return false;
     }
     return true;
 }
@@ -295,41 +295,23 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
         for (int e = tid; e < n; e += nthr) twbuf[e] = ldg_c(P.tw + e);
         BLOCK_SYNC();
     }
-    switch (pl.radix[0]) {
-    case 2: axis2_first<D, 2>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
-    case 3: axis2_first<D, 3>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
-    case 4: axis2_first<D, 4>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
-    case 5: axis2_first<D, 5>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
-    case 7: axis2_first<D, 7>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
-    case 8: axis2_first<D, 8>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
-    default: axis2_first<D, 16>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr); break;
-    }
+#define CALL_(R) axis2_first<D, R>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr)
+    DBSPM_FAST_RADIX_SWITCH(pl.radix[0], CALL_)
+#undef CALL_
     if (pl.nstages == 1) return;
     BLOCK_SYNC();
     int m = n / pl.radix[0];
     for (int st = 1; st + 1 < pl.nstages; ++st) {
         const int r = pl.radix[st];
-        switch (r) {
-        case 2: fft_stage<2, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
-        case 3: fft_stage<3, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
-        case 4: fft_stage<4, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
-        case 5: fft_stage<5, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
-        case 7: fft_stage<7, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
-        case 8: fft_stage<8, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
-        default: fft_stage<16, D>(s, T, P.tshift, n, m, tw, tid, nthr); break;
-        }
+#define CALL_(R) fft_stage<R, D>(s, T, P.tshift, n, m, tw, tid, nthr)
+        DBSPM_FAST_RADIX_SWITCH(r, CALL_)
+#undef CALL_
         m /= r;
         BLOCK_SYNC();
     }
-    switch (pl.radix[pl.nstages - 1]) {
-    case 2: axis2_last<D, 2>(P, s, gout, tcount, tid, nthr); break;
-    case 3: axis2_last<D, 3>(P, s, gout, tcount, tid, nthr); break;
-    case 4: axis2_last<D, 4>(P, s, gout, tcount, tid, nthr); break;
-    case 5: axis2_last<D, 5>(P, s, gout, tcount, tid, nthr); break;
-    case 7: axis2_last<D, 7>(P, s, gout, tcount, tid, nthr); break;
-    case 8: axis2_last<D, 8>(P, s, gout, tcount, tid, nthr); break;
-    default: axis2_last<D, 16>(P, s, gout, tcount, tid, nthr); break;
-    }
+#define CALL_(R) axis2_last<D, R>(P, s, gout, tcount, tid, nthr)
+    DBSPM_FAST_RADIX_SWITCH(pl.radix[pl.nstages - 1], CALL_)
+#undef CALL_
 }
 
 // ------------------------------------------------------------------------------------------
@@ -414,15 +396,9 @@ HD void fft_stages_group(cplx *s, int ld, int tshift, const FftPlanDev &pl, cons
     int m = pl.n;
     for (int st = 0; st < pl.nstages; ++st) {
         const int r = pl.radix[st];
-        switch (r) {
-        case 2: fft_stage<2, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 3: fft_stage<3, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 4: fft_stage<4, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 5: fft_stage<5, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 7: fft_stage<7, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 8: fft_stage<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        default: fft_stage<16, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        }
+#define CALL_(R) fft_stage<R, D>(s, ld, tshift, pl.n, m, tw, tid, nthr)
+        DBSPM_FAST_RADIX_SWITCH(r, CALL_)
+#undef CALL_
         m /= r;
         GROUP_SYNC(bar_id, nthr);
     }
@@ -750,19 +726,9 @@ HD void fft_stages_from(cplx *s, int ld, int tshift, const FftPlanDev &pl, int f
     for (int st = 0; st < first; ++st) m /= pl.radix[st];
     for (int st = first; st < pl.nstages; ++st) {
         const int r = pl.radix[st];
-        switch (r) {
-        case 2: fft_stage<2, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 3: fft_stage<3, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 4: fft_stage<4, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 5: fft_stage<5, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 7: fft_stage<7, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-#if ZF2_MAX_RADIX >= 16
-        case 8: fft_stage<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        default: fft_stage<16, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-#else
-        default: fft_stage<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-#endif
-        }
+#define CALL_(R) fft_stage<R, D>(s, ld, tshift, pl.n, m, tw, tid, nthr)
+        DBSPM_FAST_RADIX_SWITCH(r, CALL_)
+#undef CALL_
         m /= r;
         BLOCK_SYNC();
     }
@@ -799,19 +765,9 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
         pi[0] = z.kx; pi[1] = z.ky; pi[2] = z.mx; pi[3] = z.my; pi[4] = z.valid; pi[5] = z.self;
     }
     BLOCK_SYNC();
-    switch (P.plan.radix[0]) {
-    case 2: zfused2_first<-1, 2, ZLV>(P, U, tw, pinfo, tid, nthr); break;
-    case 3: zfused2_first<-1, 3, ZLV>(P, U, tw, pinfo, tid, nthr); break;
-    case 4: zfused2_first<-1, 4, ZLV>(P, U, tw, pinfo, tid, nthr); break;
-    case 5: zfused2_first<-1, 5, ZLV>(P, U, tw, pinfo, tid, nthr); break;
-    case 7: zfused2_first<-1, 7, ZLV>(P, U, tw, pinfo, tid, nthr); break;
-#if ZF2_MAX_RADIX >= 16
-    case 8: zfused2_first<-1, 8, ZLV>(P, U, tw, pinfo, tid, nthr); break;
-    default: zfused2_first<-1, 16, ZLV>(P, U, tw, pinfo, tid, nthr); break;
-#else
-    default: zfused2_first<-1, 8, ZLV>(P, U, tw, pinfo, tid, nthr); break;
-#endif
-    }
+#define CALL_(R) zfused2_first<-1, R, ZLV>(P, U, tw, pinfo, tid, nthr)
+    DBSPM_FAST_RADIX_SWITCH(P.plan.radix[0], CALL_)
+#undef CALL_
     BLOCK_SYNC();
     fft_stages_from<-1>(U, LDF, TSF, P.plan, 1, tw, tid, nthr);
 

@@ -136,16 +136,99 @@ template <int P, int D> HD void bfly_odd(cplx *v)
     }
 }
 
+template <int R, int D> HD void bfly(cplx *v);
+
+// ---- composite radices: fewer shared-memory stages for lengths like 120 = 12*10, 196 = 14*14 ----
+HD constexpr int mod_inverse(int a, int m)
+{
+    int r = 0;
+    for (int x = 1; x < m; ++x) if ((a * x) % m == 1) r = x;
+    return m == 1 ? 0 : r;
+}
+
+// R = R1*R2 with gcd(R1,R2) = 1, Good-Thomas: no twiddles between the two passes, only index maps
+//   input  n = (R2*n1 + R1*n2) mod R,   output k = k1 (mod R1), k2 (mod R2)  (Chinese remainder)
+template <int R1, int R2, int D> HD void bfly_pfa(cplx *v)
+{
+    constexpr int R = R1 * R2;
+    constexpr int A = R2 * mod_inverse(R2 % R1, R1), B = R1 * mod_inverse(R1 % R2, R2);
+    cplx t[R2][R1];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) {
+#pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1) t[n2][n1] = v[(R2 * n1 + R1 * n2) % R];
+        bfly<R1, D>(t[n2]);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+        cplx c[R2];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) c[n2] = t[n2][k1];
+        bfly<R2, D>(c);
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) v[(k1 * A + k2 * B) % R] = c[k2];
+    }
+}
+
+// radix 9 = 3 x 3: X[k1 + 3 k2] = sum_b W9^{b k1} W3^{b k2} sum_a x[3a + b] W3^{a k1}
+template <int D> HD void bfly9(cplx *v)
+{
+    const double c1 = 0.766044443118978, s1 = 0.6427876096865393;      // cos, sin of 2 pi / 9
+    const double c2 = 0.17364817766693036, s2 = 0.984807753012208;     // 4 pi / 9
+    const double c4 = -0.9396926207859084, s4 = 0.3420201433256687;    // 8 pi / 9
+    cplx t[3][3];                                     // t[b][k1]
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        cplx col[3] = {v[b], v[3 + b], v[6 + b]};
+        bfly_odd<3, D>(col);
+#pragma unroll
+        for (int k1 = 0; k1 < 3; ++k1) t[b][k1] = col[k1];
+    }
+    t[1][1] = cmul_cD<D>(t[1][1], c1, s1);            // W9^1
+    t[1][2] = cmul_cD<D>(t[1][2], c2, s2);            // W9^2
+    t[2][1] = cmul_cD<D>(t[2][1], c2, s2);            // W9^2
+    t[2][2] = cmul_cD<D>(t[2][2], c4, s4);            // W9^4
+#pragma unroll
+    for (int k1 = 0; k1 < 3; ++k1) {
+        cplx row[3] = {t[0][k1], t[1][k1], t[2][k1]};
+        bfly_odd<3, D>(row);
+#pragma unroll
+        for (int k2 = 0; k2 < 3; ++k2) v[k1 + 3 * k2] = row[k2];
+    }
+}
+
 template <int R, int D> HD void bfly(cplx *v)
 {
     if (R == 2) bfly2<D>(v);
     else if (R == 3) bfly_odd<3, D>(v);
     else if (R == 4) bfly4<D>(v);
     else if (R == 5) bfly_odd<5, D>(v);
+    else if (R == 6) bfly_pfa<2, 3, D>(v);
     else if (R == 7) bfly_odd<7, D>(v);
     else if (R == 8) bfly8<D>(v);
+    else if (R == 9) bfly9<D>(v);
+    else if (R == 10) bfly_pfa<2, 5, D>(v);
+    else if (R == 12) bfly_pfa<4, 3, D>(v);
+    else if (R == 14) bfly_pfa<2, 7, D>(v);
+    else if (R == 15) bfly_pfa<3, 5, D>(v);
     else if (R == 16) bfly16<D>(v);
 }
+
+// the radices with a register butterfly above ("fast" radices); every other radix (primes 11..31)
+// goes through fft_stage_generic
+HD bool fast_radix(int r)
+{
+    return (r >= 2 && r <= 10) || r == 12 || r == 14 || r == 15 || r == 16;
+}
+
+// runtime radix -> template instantiation; CALL(R) is a statement that uses the constant R
+#define DBSPM_FAST_RADIX_SWITCH(r, CALL)                                                            \
+    switch (r) {                                                                                    \
+    case 2: CALL(2); break;   case 3: CALL(3); break;   case 4: CALL(4); break;   case 5: CALL(5); break;   \
+    case 6: CALL(6); break;   case 7: CALL(7); break;   case 8: CALL(8); break;   case 9: CALL(9); break;   \
+    case 10: CALL(10); break; case 12: CALL(12); break; case 14: CALL(14); break; case 15: CALL(15); break; \
+    default: CALL(16); break;                                                                       \
+    }
 
 // ---- one DIF stage over the whole tile ----------------------------------------------------
 // m = current sub-transform length, R | m.  tw[e] = exp(-2 pi i e / n), e in [0,n).
@@ -261,19 +344,9 @@ HD void fft_tile_t(cplx *s, int ld, int tshift, const FftPlanDev &pl, const cplx
     for (int st = pl.nstages - 1; st >= 0; --st) {
         const int r = pl.radix[st];
         m *= r;
-        switch (r) {
-        case 2: fft_stage_t<2, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 3: fft_stage_t<3, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 4: fft_stage_t<4, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 5: fft_stage_t<5, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 7: fft_stage_t<7, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-#if !defined(ZF2_MAX_RADIX) || ZF2_MAX_RADIX >= 16
-        case 8: fft_stage_t<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        default: fft_stage_t<16, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-#else
-        default: fft_stage_t<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-#endif
-        }
+#define CALL_(R) fft_stage_t<R, D>(s, ld, tshift, pl.n, m, tw, tid, nthr)
+        DBSPM_FAST_RADIX_SWITCH(r, CALL_)
+#undef CALL_
         BLOCK_SYNC();
     }
 }
@@ -286,15 +359,12 @@ HD void fft_tile(cplx *s, int ld, int tshift, const FftPlanDev &pl, const cplx *
     int m = pl.n;
     for (int st = 0; st < pl.nstages; ++st) {
         const int r = pl.radix[st];
-        switch (r) {
-        case 2: fft_stage<2, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 3: fft_stage<3, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 4: fft_stage<4, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 5: fft_stage<5, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 7: fft_stage<7, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 8: fft_stage<8, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        case 16: fft_stage<16, D>(s, ld, tshift, pl.n, m, tw, tid, nthr); break;
-        default: fft_stage_generic<D>(s, ld, tshift, pl.n, m, r, tw, tid, nthr); break;
+        if (fast_radix(r)) {
+#define CALL_(R) fft_stage<R, D>(s, ld, tshift, pl.n, m, tw, tid, nthr)
+            DBSPM_FAST_RADIX_SWITCH(r, CALL_)
+#undef CALL_
+        } else {
+            fft_stage_generic<D>(s, ld, tshift, pl.n, m, r, tw, tid, nthr);
         }
         m /= r;
         BLOCK_SYNC();

@@ -2,6 +2,44 @@
 // into the CPU emulation used by the tests).
 #include "plan.h"
 #include <math.h>
+#include <vector>
+
+// estimated real additions + multiplications per point of each register butterfly (fft_core.h); only
+// used to choose between factorisations with the same number of stages
+static double radix_cost(int r)
+{
+    switch (r) {
+    case 2: return 2.0;   case 3: return 5.3;   case 4: return 4.0;   case 5: return 9.6;
+    case 6: return 7.3;   case 7: return 13.7;  case 8: return 6.5;   case 9: return 13.3;
+    case 10: return 11.6; case 12: return 9.3;  case 14: return 19.0; case 15: return 14.9;   // 14: measured (n = 112: [7,16] beats [14,8])
+    case 16: return 11.4;
+    default: return 2.0 * r;                       // generic O(r^2) stage
+    }
+}
+
+// Fewest stages first (every stage is a shared-memory round trip and a block barrier), then the
+// cheapest butterflies.  Radices: the fast set of fft_core.h capped at max_radix, plus the primes
+// 11..31 (generic stage) when n needs them.  Non-increasing sequences only; the order is fixed below.
+static void search_split(int rem, int max_r, int cap, std::vector<int> &cur, double cost,
+                         std::vector<int> &best, double &best_cost)
+{
+    if (rem == 1) {
+        if (best.empty() || cur.size() < best.size() || (cur.size() == best.size() && cost < best_cost - 1e-9)) {
+            best = cur; best_cost = cost;
+        }
+        return;
+    }
+    if (!best.empty() && cur.size() + 1 > best.size()) return;
+    for (int r = max_r; r >= 2; --r) {
+        if (rem % r) continue;
+        const bool prime_big = r > 16 || r == 11 || r == 13;
+        if (!prime_big && (!fast_radix(r) || r > cap)) continue;
+        if (prime_big) { bool pr = true; for (int d = 2; d * d <= r; ++d) if (r % d == 0) pr = false; if (!pr) continue; }
+        cur.push_back(r);
+        search_split(rem / r, r, cap, cur, cost + radix_cost(r), best, best_cost);
+        cur.pop_back();
+    }
+}
 
 bool dbspm_make_plan(int n, HostPlan &out, int max_pow2_radix)
 {
@@ -9,31 +47,18 @@ bool dbspm_make_plan(int n, HostPlan &out, int max_pow2_radix)
     FftPlanDev &d = out.dev;
     d.n = n;
     d.nstages = 0;
-    int rem = n;
-    auto push = [&](int r) -> bool {
-        if (d.nstages >= DBSPM_MAX_STAGES) return false;
-        d.radix[d.nstages++] = r;
-        return true;
-    };
-    // odd prime factors first (large strides, twiddle-heavy stages early), then the 2-power
-    for (int p = 3; p <= DBSPM_MAX_RADIX; p += 2)
-        while (rem % p == 0) {
-            if (!push(p)) return false;
-            rem /= p;
-        }
-    int twos = 0;
-    while (rem % 2 == 0) { rem /= 2; ++twos; }
-    if (rem != 1) return false;                    // prime factor > DBSPM_MAX_RADIX
-    // 2^twos over ceil(twos/maxbits) stages of radix <= max_pow2_radix, bits spread evenly, larger radices first
-    if (twos > 0) {
-        const int maxbits = max_pow2_radix >= 16 ? 4 : (max_pow2_radix >= 8 ? 3 : (max_pow2_radix >= 4 ? 2 : 1));
-        const int ns = (twos + maxbits - 1) / maxbits;
-        for (int i = 0; i < ns; ++i) {
-            const int bits = twos / ns + (i < twos % ns ? 1 : 0);
-            if (!push(1 << bits)) return false;
-        }
+    if (n > 1) {
+        std::vector<int> cur, best;
+        double best_cost = 0.0;
+        search_split(n, DBSPM_MAX_RADIX - 1, max_pow2_radix < 2 ? 2 : max_pow2_radix, cur, 0.0, best, best_cost);
+        if (best.empty() || (int)best.size() > DBSPM_MAX_STAGES) return false;   // prime factor > 31 or too many stages
+        // stage order: radices that are not powers of two first (large strides, twiddle-heavy stages early),
+        // then the powers of two, each group in descending order
+        auto pow2 = [](int r) { return (r & (r - 1)) == 0; };
+        for (int pass = 0; pass < 2; ++pass)
+            for (int r : best)
+                if ((pass == 1) == pow2(r)) d.radix[d.nstages++] = r;
     }
-    if (n == 1) { d.nstages = 0; }
 
     out.tw.resize(n);
     const long double two_pi = 6.283185307179586476925286766559005768L;

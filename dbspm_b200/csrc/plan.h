@@ -10,6 +10,7 @@ struct HostPlan {
     std::vector<int> freq_of;   // inverse table: freq_of[pos_of[K]] = K
 };
 
-// returns false if n has a prime factor > DBSPM_MAX_RADIX or needs too many stages
-// max_pow2_radix (16, 8, 4 or 2) caps the power-of-two radices: smaller radices need fewer registers
+// returns false if n has a prime factor > DBSPM_MAX_RADIX or needs too many stages.  The schedule has the
+// fewest stages possible with radices {2..10,12,14,15,16} (and generic primes 11..31), ties broken by
+// butterfly cost; max_pow2_radix caps the fast radices (smaller radices need fewer registers)
 bool dbspm_make_plan(int n, HostPlan &out, int max_pow2_radix = 16);

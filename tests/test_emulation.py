@@ -6,8 +6,8 @@ import pytest
 
 from oracle import oracle as O
 
-LENGTHS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 20, 21, 27, 28, 30, 32, 49, 64, 77, 80, 96, 98, 120,
-           128, 160, 196, 240, 256, 320, 384, 512, 1024, 11, 13, 22, 26, 33, 62, 169]
+LENGTHS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 20, 21, 27, 28, 30, 32, 49, 54, 64, 72, 77, 80, 84, 90, 96, 98,
+           100, 108, 112, 120, 128, 160, 196, 240, 256, 320, 384, 512, 576, 1024, 11, 13, 22, 26, 33, 62, 169]
 
 
 def _factors(n):
