@@ -243,6 +243,10 @@ struct PowellRegs {
 #define BT_RAT R.s[9]
 #define BT_U   R.s[10]
 
+#ifndef RELAX_DRIFT
+#define RELAX_DRIFT 0
+#endif
+
 // ---- one lateral column: sweep z from the top with warm start ------------------------------
 // NTHR = threads per block (the stride of the shared-memory columns); sm = PS_COUNT*NTHR doubles.
 template <int LAYOUT, int NTHR>
@@ -278,11 +282,21 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
         WARP_SYNC();
         if (WARP_ALL(done)) break;
         double fe = 0.0;
-        if (!done) fe = relax_objective<LAYOUT>(P, oi, oj, ok, R.p[0] + alpha * R.xi[0], R.p[1] + alpha * R.xi[1]);
+#if defined(__CUDA_ARCH__)
+        // A lane that has finished a height waits for the slowest lane of its warp before it starts the
+        // next one (RELAX_DRIFT = heights it may run ahead).  The kernel is bound by L1 wavefronts: lanes on
+        // the same height read the same z rows of the potential, which more than pays for the idle lanes
+        // (B200, 1024x1024x24: no limit 118 ms, 2 heights 115 ms, 1 height 107 ms, lockstep 89.5 ms).
+        const int kmax = __reduce_max_sync(0xffffffffu, done ? -1 : k);
+        const bool hold = !done && R.pc == PC_INIT && k < kmax - RELAX_DRIFT;
+#else
+        const bool hold = false;
+#endif
+        if (!done && !hold) fe = relax_objective<LAYOUT>(P, oi, oj, ok, R.p[0] + alpha * R.xi[0], R.p[1] + alpha * R.xi[1]);
         WARP_SYNC();
 
         // ---- dispatch on the entry state (cheap, per state) ----
-        int pc = R.pc, next = PC_IDLE;
+        int pc = hold ? PC_IDLE : R.pc, next = PC_IDLE;
         bool fresh = false;                  // request that starts a minimisation: no maxfev check
         double alpha_min = 0.0, fret = 0.0;  // line-search result on its way to PC_LS_FINISH
         if (pc == PC_BT_U) {
@@ -539,7 +553,7 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
                 else { R.nfev += 1; pc = next; }
             }
         } while (repeat);
-        R.pc = pc;
+        if (!hold) R.pc = pc;
     }
 #undef PS
 }
