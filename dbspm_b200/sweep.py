@@ -13,9 +13,10 @@ from . import parallel
 
 
 def fdbm_sweep(rhoS, potS, rhoT, nrhoT, dr, z_window, nz_relax, param_sets, rpivot, vdw=None, dR=None,
-               keep_static=False):
+               keep_static=False, streams=4):
     """param_sets: iterable of (alpha, V0, kappa).  Inputs: CUDA tensors (or numpy, uploaded once).
     Returns {"es": window, "sr": {alpha: window}, "relax": [dict per set]} with CUDA tensors.
+    streams: how many CUDA streams the independent relax runs are spread over (1 = serial).
 
     Under torchrun (torch.distributed initialised, one process per GPU) the sets are dealt over the
     ranks (parallel.sweep_assignment); es is computed on rank 0 and broadcast, every rank computes the
@@ -31,18 +32,32 @@ def fdbm_sweep(rhoS, potS, rhoT, nrhoT, dr, z_window, nz_relax, param_sets, rpiv
     es = ops.density_overlap_window(P, NT, dr, z_lo, z_hi)
     vd = ops._to_dev(vdw, dev) if vdw is not None else None
     sr = {}
-    out = []
-    for alpha, V0, kappa in param_sets:
+    for alpha, _, _ in param_sets:
         a = float(alpha)
         if a not in sr:
             sr[a] = ops.density_overlap_window(A, T, dr, z_lo, z_hi, a, a)
-        comps = [(sr[a], float(V0)), (es, 1.0)] + ([(vd, 1.0)] if vd is not None else [])
-        static = ops.build_static(comps)
-        r = ops.relax_grid(static, float(kappa), rpivot, dr, nz_relax, dR=dR)
+    # The relax of a small scan grid does not fill the GPU (pyridine: 300 blocks for 592 resident slots)
+    # and the sets are independent: run them on a few streams so that their kernels overlap.
+    main = torch.cuda.current_stream(dev)
+    nstreams = max(1, min(int(streams), len(param_sets)))
+    side = [torch.cuda.Stream(device=dev) for _ in range(nstreams)] if nstreams > 1 else [main]
+    out = []
+    for i, (alpha, V0, kappa) in enumerate(param_sets):
+        a = float(alpha)
+        st = side[i % nstreams]
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            comps = [(sr[a], float(V0)), (es, 1.0)] + ([(vd, 1.0)] if vd is not None else [])
+            static = ops.build_static(comps)
+            r = ops.relax_grid(static, float(kappa), rpivot, dr, nz_relax, dR=dR)
         r.update(alpha=a, V=float(V0), kappa=float(kappa))
         if keep_static:
             r["static"] = static
         out.append(r)
+    for st in side:
+        main.wait_stream(st)
+    if nstreams > 1:
+        torch.cuda.synchronize(dev)     # results were allocated on side streams: make them safe for any consumer
     return {"es": es, "sr": sr, "relax": out}
 
 
