@@ -76,6 +76,22 @@ __global__ void __launch_bounds__(DBSPM_THREADS) compact_kernel(const double *W,
                  (long long)gridDim.x * blockDim.x);
 }
 
+__global__ void __launch_bounds__(256) r2c_kernel(const double *in, cplx *out, size_t n, double alpha)
+{
+    r2c_body(in, out, n, alpha, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+}
+
+__global__ void __launch_bounds__(256) cmulconj_kernel(cplx *a, const cplx *b, size_t n, double scale)
+{
+    cmulconj_body(a, b, n, scale, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+}
+
+__global__ void __launch_bounds__(256) c2r_window_kernel(const cplx *W, double *E, long long ncol, int nz, int z_lo, int nzw)
+{
+    c2r_window_body(W, E, ncol, nz, z_lo, nzw, (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                    (long long)gridDim.x * blockDim.x);
+}
+
 // which z-planes of a (nlines, nz) array hold a nonzero value: flags[z] = 1 (flags zeroed by the caller).
 // Streaming 128-bit reads, per-block flags in shared memory, one global store per set plane and block.
 __global__ void __launch_bounds__(256) zsupport_kernel(const double2 *B2, size_t npairs, int nzh, int *flags)
@@ -311,12 +327,41 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
 extern "C" size_t dbspm_corr3d_workspace_bytes(int nx, int ny, int nz, int z_lo, int z_hi, int flags)
 {
     (void)flags;
-    if (nx < 1 || ny < 1 || nz < 2 || z_lo < 0 || z_hi <= z_lo || z_hi > nz) return 0;
+    if (nx < 1 || ny < 1 || nz < 1 || z_lo < 0 || z_hi <= z_lo || z_hi > nz) return 0;
     const size_t N = (size_t)nx * ny * nz;
     const int nzw = z_hi - z_lo, nwh = (nzw + 1) / 2;
+    if (nz & 1) return 2 * align_up(N * 16, 256);         // odd nz: two full complex arrays
     size_t bytes = 2 * align_up(N * 8, 256);
     if (nzw & 1) bytes += align_up((size_t)nx * ny * nwh * 16, 256);
     return bytes;
+}
+
+// odd nz: real -> complex, three forward passes on both arrays, product, three inverse passes, real window
+static int corr3d_complex(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                          int nx, int ny, int nz, int z_lo, int z_hi, double *E_win, void *workspace, int flags, cudaStream_t st)
+{
+    const size_t N = (size_t)nx * ny * nz;
+    cplx *WA = (cplx *)workspace;
+    cplx *WB = (cplx *)((unsigned char *)workspace + align_up(N * 16, 256));
+    size_t blocks = (N + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    r2c_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, WA, N, alphaA);
+    r2c_kernel<<<(unsigned)blocks, 256, 0, st>>>(B, WB, N, alphaB);
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    const int f = (flags | DBSPM_CORR_NO_TMA) & ~DBSPM_CORR_USE_TMA;
+    int rc;
+    if ((rc = launch_axis<-1>(WA, WA, WB, WB, 2, 1.0, 1.0, 0, nx, (long long)ny * nz, 1, st, f))) return rc;
+    if ((rc = launch_axis<-1>(WA, WA, WB, WB, 2, 1.0, 1.0, 0, ny, nz, nx, st, f))) return rc;
+    if ((rc = launch_axis<-1>(WA, WA, WB, WB, 2, 1.0, 1.0, 0, nz, 1, (long long)nx * ny, st, f))) return rc;
+    cmulconj_kernel<<<(unsigned)blocks, 256, 0, st>>>(WA, WB, N, dV / ((double)nx * (double)ny * (double)nz));
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    if ((rc = launch_axis<1>(WA, WA, nullptr, nullptr, 1, 1.0, 1.0, 0, nz, 1, (long long)nx * ny, st, f))) return rc;
+    if ((rc = launch_axis<1>(WA, WA, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nz, nx, st, f))) return rc;
+    if ((rc = launch_axis<1>(WA, WA, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)ny * nz, 1, st, f))) return rc;
+    const long long ncol = (long long)nx * ny;
+    c2r_window_kernel<<<(unsigned)blocks, 256, 0, st>>>(WA, E_win, ncol, nz, z_lo, z_hi - z_lo);
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    return DBSPM_OK;
 }
 
 // the five launches on a problem of z length nz (the caller's, or the pruned length when g != null)
@@ -406,14 +451,15 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
 {
     cudaStream_t st = (cudaStream_t)stream;
     DBSPM_REQUIRE(A && B && E_win && workspace, DBSPM_EINVAL, "null pointer argument");
-    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 2, DBSPM_EINVAL, "bad shape (%d,%d,%d)", nx, ny, nz);
+    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1, DBSPM_EINVAL, "bad shape (%d,%d,%d)", nx, ny, nz);
     DBSPM_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= nz, DBSPM_EINVAL, "bad window [%d,%d) for nz=%d", z_lo, z_hi, nz);
-    DBSPM_REQUIRE((nz & 1) == 0, DBSPM_EUNSUPPORTED, "nz=%d is odd: the packed real transform needs an even z length", nz);
     DBSPM_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)E_win & 15) == 0,
                   DBSPM_EINVAL, "A, B and E_win must be 16-byte aligned");
     const size_t need = dbspm_corr3d_workspace_bytes(nx, ny, nz, z_lo, z_hi, flags);
     DBSPM_REQUIRE(workspace_bytes >= need && ((uintptr_t)workspace & 255) == 0, DBSPM_EWORKSPACE,
                   "workspace needs %zu bytes, 256-byte aligned (got %zu)", need, workspace_bytes);
+    if (nz & 1)      // the packed real transform needs an even z length: plain complex transforms instead
+        return corr3d_complex(A, B, alphaA, alphaB, dV, nx, ny, nz, z_lo, z_hi, E_win, workspace, flags, st);
 
     return corr3d_core(A, B, alphaA, alphaB, dV, nx, ny, nz, z_lo, z_hi, E_win, workspace, flags, st, nullptr);
 }
@@ -421,7 +467,7 @@ extern "C" int dbspm_corr3d_f64(const double *A, const double *B, double alphaA,
 // ---- z-pruned correlation for a tip that is exactly zero outside s_len planes -----------------
 extern "C" size_t dbspm_corr3d_pruned_workspace_bytes(int nx, int ny, int nz, int z_lo, int z_hi, int s_lo, int s_len, int flags)
 {
-    if (nx < 1 || ny < 1 || nz < 2 || z_lo < 0 || z_hi <= z_lo || z_hi > nz) return 0;
+    if (nx < 1 || ny < 1 || nz < 1 || z_lo < 0 || z_hi <= z_lo || z_hi > nz) return 0;
     const PrunedGeom G = pruned_geometry(nz, z_lo, z_hi, s_lo, s_len);
     if (!G.use) return dbspm_corr3d_workspace_bytes(nx, ny, nz, z_lo, z_hi, flags);
     return dbspm_corr3d_workspace_bytes(nx, ny, G.Mp, G.w_lo, G.w_lo + (z_hi - z_lo), flags);
@@ -433,10 +479,9 @@ extern "C" int dbspm_corr3d_pruned_f64(const double *A, const double *B, double 
 {
     cudaStream_t st = (cudaStream_t)stream;
     DBSPM_REQUIRE(A && B && E_win && workspace, DBSPM_EINVAL, "null pointer argument");
-    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 2, DBSPM_EINVAL, "bad shape (%d,%d,%d)", nx, ny, nz);
+    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1, DBSPM_EINVAL, "bad shape (%d,%d,%d)", nx, ny, nz);
     DBSPM_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= nz, DBSPM_EINVAL, "bad window [%d,%d) for nz=%d", z_lo, z_hi, nz);
     DBSPM_REQUIRE(s_len >= 1 && s_len <= nz, DBSPM_EINVAL, "bad tip support length %d for nz=%d", s_len, nz);
-    DBSPM_REQUIRE((nz & 1) == 0, DBSPM_EUNSUPPORTED, "nz=%d is odd: the packed real transform needs an even z length", nz);
     DBSPM_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)E_win & 15) == 0,
                   DBSPM_EINVAL, "A, B and E_win must be 16-byte aligned");
     const size_t need = dbspm_corr3d_pruned_workspace_bytes(nx, ny, nz, z_lo, z_hi, s_lo, s_len, flags);
@@ -453,6 +498,8 @@ extern "C" int dbspm_corr3d_pruned_f64(const double *A, const double *B, double 
     if (!G.use) {
         DBSPM_REQUIRE(workspace_bytes >= dbspm_corr3d_workspace_bytes(nx, ny, nz, z_lo, z_hi, flags), DBSPM_EWORKSPACE,
                       "workspace too small for the full-length path");
+        if (nz & 1)
+            return corr3d_complex(A, B, alphaA, alphaB, dV, nx, ny, nz, z_lo, z_hi, E_win, workspace, flags, st);
         return corr3d_core(A, B, alphaA, alphaB, dV, nx, ny, nz, z_lo, z_hi, E_win, workspace, flags, st, nullptr);
     }
     GatherSpec g;

@@ -822,6 +822,34 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
 // ------------------------------------------------------------------------------------------
 // compaction when the window has an odd number of planes: W (nx*ny, 2*nwh) -> E (nx*ny, nzw)
 // ------------------------------------------------------------------------------------------
+// ---- odd nz: plain complex transforms (the packed real transform needs an even z length) --------
+// Elementwise bodies around six ordinary axis passes: real -> complex (power fused), spectrum product
+// A * conj(B) * scale, real part of the window planes.  Twice the traffic of the packed path; VASP FFT
+// grids are even, so this only keeps get_density_overlap() total over shapes like the reference's.
+HD void r2c_body(const double *in, cplx *out, size_t n, double alpha, size_t gid, size_t gstride)
+{
+    const bool do_pow = alpha != 1.0;
+    for (size_t i = gid; i < n; i += gstride) {
+        const double v = in[i];
+        out[i] = cmake(do_pow ? pow_nonneg(v, alpha) : v, 0.0);
+    }
+}
+
+HD void cmulconj_body(cplx *a, const cplx *b, size_t n, double scale, size_t gid, size_t gstride)
+{
+    for (size_t i = gid; i < n; i += gstride) a[i] = cscale(cmulc(a[i], b[i]), scale);
+}
+
+HD void c2r_window_body(const cplx *W, double *E, long long ncol, int nz, int z_lo, int nzw, long long gid, long long gstride)
+{
+    const long long total = ncol * nzw;
+    for (long long i = gid; i < total; i += gstride) {
+        const long long c = i / nzw;
+        const int z = (int)(i - c * nzw);
+        E[i] = W[c * nz + z_lo + z].x;
+    }
+}
+
 HD void compact_body(const double *W, double *E, long long ncol, int nzw, int ldw, long long gid, long long gstride)
 {
     const long long total = ncol * nzw;

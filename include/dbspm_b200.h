@@ -40,7 +40,7 @@ extern "C" {
 
 #define DBSPM_OK              0
 #define DBSPM_EINVAL         -1   /* bad argument (NULL pointer, non-positive size, bad window) */
-#define DBSPM_EUNSUPPORTED   -2   /* shape not supported (odd nz, prime factor > 31 in a length) */
+#define DBSPM_EUNSUPPORTED   -2   /* shape not supported (prime factor > 31 in a length, grid too large) */
 #define DBSPM_EWORKSPACE     -3   /* workspace too small or misaligned */
 #define DBSPM_ECUDA          -4   /* a CUDA runtime call / kernel launch failed */
 
@@ -66,7 +66,8 @@ const char *dbspm_last_error(void);
 /* ---- sr / es: periodic 3-D cross-correlation, output restricted to a z-window ------------
  * E_win[x,y,z-z_lo] = dV * sum_r A[r]^alphaA * B[(r - R) mod N]^alphaB ,  R = (x,y,z), z in [z_lo,z_hi)
  * A, B: (nx,ny,nz); E_win: (nx,ny,z_hi-z_lo).  alpha == 1.0 skips the power.
- * Requires nz even, 0 <= z_lo < z_hi <= nz, and nx, ny, nz/2 with prime factors <= 31.
+ * Requires 0 <= z_lo < z_hi <= nz and nx, ny, nz (nz/2 for even nz) with prime factors <= 31.  An odd nz
+ * takes plain complex transforms (twice the traffic of the packed real path; VASP grids are even).
  * workspace: at least dbspm_corr3d_workspace_bytes(...) bytes, 256-byte aligned.           */
 size_t dbspm_corr3d_workspace_bytes(int nx, int ny, int nz, int z_lo, int z_hi, int flags);
 int dbspm_corr3d_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,

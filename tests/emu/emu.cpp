@@ -102,7 +102,24 @@ extern "C" size_t emu_corr3d_workspace_bytes(int nx, int ny, int nz, int z_lo, i
 static int emu_corr3d_core(const double *A, const double *B, double alphaA, double alphaB, double dV,
                            int nx, int ny, int nz, int z_lo, int z_hi, double *E_win, int force_tshift, const EmuGather *g)
 {
-    if (nz & 1) return -2;
+    if (nz & 1) {
+        // odd nz: corr3d_complex() of corr3d.cu
+        const size_t N = (size_t)nx * ny * nz;
+        std::vector<cplx> WA(N), WB(N);
+        int rc;
+        r2c_body(A, WA.data(), N, alphaA, 0, 1);
+        r2c_body(B, WB.data(), N, alphaB, 0, 1);
+        if (force_tshift >= 200) force_tshift = -1;
+        if ((rc = run_axis<-1>(WA.data(), WA.data(), WB.data(), WB.data(), 2, 1.0, 1.0, 0, nx, (long long)ny * nz, 1, force_tshift))) return rc;
+        if ((rc = run_axis<-1>(WA.data(), WA.data(), WB.data(), WB.data(), 2, 1.0, 1.0, 0, ny, nz, nx, force_tshift))) return rc;
+        if ((rc = run_axis<-1>(WA.data(), WA.data(), WB.data(), WB.data(), 2, 1.0, 1.0, 0, nz, 1, (long long)nx * ny, force_tshift))) return rc;
+        cmulconj_body(WA.data(), WB.data(), N, dV / ((double)nx * (double)ny * (double)nz), 0, 1);
+        if ((rc = run_axis<1>(WA.data(), WA.data(), nullptr, nullptr, 1, 1.0, 1.0, 0, nz, 1, (long long)nx * ny, force_tshift))) return rc;
+        if ((rc = run_axis<1>(WA.data(), WA.data(), nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nz, nx, force_tshift))) return rc;
+        if ((rc = run_axis<1>(WA.data(), WA.data(), nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)ny * nz, 1, force_tshift))) return rc;
+        c2r_window_body(WA.data(), E_win, (long long)nx * ny, nz, z_lo, z_hi - z_lo, 0, 1);
+        return 0;
+    }
     const int n = nz / 2, nzw = z_hi - z_lo, nwh = (nzw + 1) / 2;
     const size_t N = (size_t)nx * ny * nz;
     std::vector<cplx> WA(N / 2), WB(N / 2), Wodd;

@@ -88,9 +88,18 @@ def test_corr3d_tiny_config_window(emu, overlap_golden):
     assert np.isfinite(out).all() and abs(out[0, 0, 0] - np.prod(dr) * (2.0 ** 1.08) ** 2) < 1e-12
 
 
-def test_odd_nz_is_refused(emu):
-    with pytest.raises(RuntimeError):
-        emu.corr3d(np.zeros((4, 4, 5)), np.zeros((4, 4, 5)), np.ones(3))
+@pytest.mark.parametrize("shape,window", [((4, 4, 5), (0, 5)), ((6, 5, 9), (2, 7)), ((3, 8, 15), (14, 15)),
+                                          ((1, 1, 1), (0, 1)), ((7, 1, 3), (1, 2)), ((10, 12, 21), (0, 21))])
+def test_odd_nz_takes_the_complex_path(emu, shape, window):
+    """The packed real transform needs an even z length; odd lengths go through plain complex transforms
+    (get_density_overlap of the reference accepts any shape)."""
+    rng = np.random.default_rng(sum(shape))
+    a, b = rng.random(shape), rng.random(shape) - 0.3
+    dr = np.array([0.2, 0.1, 0.3])
+    ref = O.density_overlap_fft(a ** 1.08, b, dr)[:, :, window[0]:window[1]]
+    for ts in (-1, 101, 200):
+        got = emu.corr3d(a, b, dr, window[0], window[1], alpha0=1.08, tshift=ts)
+        assert np.abs(got - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-300), (shape, ts)
 
 
 def test_tricubic_stencil_equals_oracle(emu, relax_golden):

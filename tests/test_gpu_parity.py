@@ -95,9 +95,12 @@ def test_overlap_tiny_config_sr_es(ops, overlap_golden):
 
 def test_overlap_errors(ops):
     from dbspm_b200._lib import DbspmError, EUNSUPPORTED
-    with pytest.raises(DbspmError) as e:
-        ops.get_density_overlap(np.ones((4, 4, 5)), np.ones((4, 4, 5)), np.ones(3))    # odd nz
-    assert e.value.code == EUNSUPPORTED
+    rng = np.random.default_rng(9)
+    for shape in [(4, 4, 5), (12, 10, 27), (196, 6, 55)]:                               # odd nz: complex path
+        a, b = rng.random(shape), rng.random(shape) - 0.4
+        ref = O.density_overlap_fft(a ** 1.08, b, np.ones(3))
+        assert _rel(ops.density_overlap_window(a, b, np.ones(3), alpha0=1.08), ref) <= 1e-9
+        assert _rel(ops.density_overlap_window(a, b, np.ones(3), 1, shape[2] - 1, alpha0=1.08), ref[:, :, 1:-1]) <= 1e-9
     with pytest.raises(DbspmError) as e:
         ops.get_density_overlap(np.ones((37, 4, 4)), np.ones((37, 4, 4)), np.ones(3))  # prime 37 > 31
     assert e.value.code == EUNSUPPORTED
