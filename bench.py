@@ -467,7 +467,13 @@ def run_gpu_arm(args):
                    "parallelism": (f"sr | es on disjoint rank groups, z-slab within a group ({world} ranks), "
                                    f"x-tile x{world} (relax), gather to rank 0") if world > 1 else "single GPU"},
         "relax": {"value": nx * ny * nz_relax / (relax_ms_max * 1e-3), "unit": "tip positions/s",
-                  "ms": relax_ms_max, "mean_nfev": nfev_mean, "in_step_ms_static_relax_gather": t_rest},
+                  "ms": relax_ms_max, "mean_nfev": nfev_mean, "in_step_ms_static_relax_gather": t_rest,
+                  # the kernel is bound by L1 wavefronts, not HBM (compulsory HBM bytes are ~50 B/position):
+                  # algorithmic stencil traffic = scipy's nfev x 64 points x 8 B per position, against the
+                  # nominal L1 load bandwidth (SMs x 128 B/clk x max SM clock)
+                  "stencil_gbs": nx * ny * nz_relax * nfev_mean * 512 / (relax_ms_max * 1e-3) / 1e9,
+                  "l1_nominal_gbs": world * 148 * 128 * 1.965,
+                  "hbm_bytes_per_position": 8.0 * nzw / nz_relax + 56.0},
         "stages_ms": stages, "compact_tip": compact, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": n_launch, "clocks": clk.summary(), "wall_s_timed_region": t_wall,
     }
