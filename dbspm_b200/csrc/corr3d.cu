@@ -30,6 +30,15 @@ __global__ void __launch_bounds__(AXIS2_THREADS, AXIS2_MIN_BLOCKS) axis_pass2_ke
     axis_pass_body_v2<D>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
 }
 
+// wide variant for the slowest axis at long lengths (n ~ 1024): one CTA of 512 threads per SM with an 8-line
+// tile, so that every row segment is a full 128-byte line (rows of the x pass are megabytes apart)
+template <int D>
+__global__ void __launch_bounds__(512, 1) axis_pass2w_kernel(const __grid_constant__ AxisParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    axis_pass_body_v2<D>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
+}
+
 __global__ void __launch_bounds__(DBSPM_THREADS) zfused_kernel(const __grid_constant__ ZFusedParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -300,10 +309,22 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     P.v2 = axis_v2_ok(P.plan) && (g || !(flags & DBSPM_CORR_AXIS_V1));
     P.tw_smem = 0;
     size_t smem;
+    bool wide = false;
     if (P.v2) {
         axis2_config(n, inner, P.plan.nstages, &P.tshift, &P.tw_smem);
         smem = axis2_smem_bytes(n, P.tshift, P.plan.nstages, P.tw_smem);
         if (smem > 227 * 1024) P.v2 = 0;
+#if !defined(AXIS2_NO_WIDE)
+        // slowest axis (outer == 1: rows inner*16 bytes apart) and a tile budget that only allows 4-line tiles:
+        // measured on B200 at n = 1024, 2 CTAs x 256 threads x T=4 -> 1 CTA x 512 threads x T=8: 2.60 -> 2.32 ms
+        // (the same change slows the y pass, whose rows are 2 KB apart, 2.20 -> 2.36 ms)
+        else if (outer == 1 && P.tshift == 2 && inner >= 65536 && P.plan.nstages > 1 &&
+                 axis2_smem_bytes(n, 3, P.plan.nstages, 0) <= 200 * 1024) {
+            wide = true;
+            P.tshift = 3; P.tw_smem = 0;
+            smem = axis2_smem_bytes(n, 3, P.plan.nstages, 0);
+        }
+#endif
     }
     if (!P.v2) {
         P.tshift = pick_tshift(n, inner);
@@ -313,7 +334,10 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     P.tiles = (inner + (1LL << P.tshift) - 1) >> P.tshift;
     const long long nblocks = outer * P.tiles;
     DBSPM_REQUIRE(nblocks > 0 && nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large (%lld blocks)", nblocks);
-    if (P.v2) {
+    if (P.v2 && wide) {
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2w_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        axis_pass2w_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), 512, smem, st>>>(P);
+    } else if (P.v2) {
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         axis_pass2_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), AXIS2_THREADS, smem, st>>>(P);
     } else {
