@@ -318,7 +318,10 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
         // slowest axis (outer == 1: rows inner*16 bytes apart) and a tile budget that only allows 4-line tiles:
         // measured on B200 at n = 1024, 2 CTAs x 256 threads x T=4 -> 1 CTA x 512 threads x T=8: 2.60 -> 2.32 ms
         // (the same change slows the y pass, whose rows are 2 KB apart, 2.20 -> 2.36 ms)
+        // With the power fused into the load the pass is FP64-issue bound and two CTAs hide it better:
+        // 4.21 ms (2 x 256) against 4.87 ms (1 x 512).
         else if (outer == 1 && P.tshift == 2 && inner >= 65536 && P.plan.nstages > 1 &&
+                 !(use_pow && (alpha0 != 1.0 || alpha1 != 1.0)) &&
                  axis2_smem_bytes(n, 3, P.plan.nstages, 0) <= 200 * 1024) {
             wide = true;
             P.tshift = 3; P.tw_smem = 0;
