@@ -36,6 +36,14 @@ _SIGNATURES = {
     "dbspm_corr3d_pruned_workspace_bytes": (C.c_size_t, [C.c_int] * 8),
     "dbspm_corr3d_pruned_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "dbspm_corr3d_dist_supported": (C.c_int, [C.c_int] * 4),
+    "dbspm_corr3d_dist_fwd_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            _vp, _vp, C.c_int, _vp]),
+    "dbspm_corr3d_dist_mid_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, _vp, C.c_int, _vp]),
+    "dbspm_corr3d_dist_fin_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "dbspm_corr3d_dist_fin_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t,
+                                            C.c_int, _vp]),
     "dbspm_zsupport_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "dbspm_static_accumulate_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_size_t, C.c_int, _vp]),
     "dbspm_relax_powell_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <map>
 #include <mutex>
+#include <tuple>
+#include <vector>
 #include "capi_common.h"
 #include "corr_body.h"
 #include "plan.h"
@@ -37,6 +39,14 @@ __global__ void __launch_bounds__(512, 1) axis_pass2w_kernel(const __grid_consta
 {
     extern __shared__ __align__(16) unsigned char smem[];
     axis_pass_body_v2<D>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
+}
+
+// row-mapped variant (distributed correlation): rows of the transform axis are read / written through a table
+template <int D>
+__global__ void __launch_bounds__(AXIS2_THREADS, AXIS2_MIN_BLOCKS) axis_pass2m_kernel(const __grid_constant__ AxisParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    axis_pass_body_v2<D, 1>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
 }
 
 __global__ void __launch_bounds__(DBSPM_THREADS) zfused_kernel(const __grid_constant__ ZFusedParams P)
@@ -159,6 +169,29 @@ static int get_plan(int n, cudaStream_t st, DevPlan **out, int max_radix = 16)
     return DBSPM_OK;
 }
 
+// device-resident row tables of the distributed correlation: map[K] = dist_row_of(K, n, G, blockrows)
+static std::map<std::tuple<int, int, int, long long>, int *> g_rowmaps;
+
+static int get_rowmap(int n, int G, long long blockrows, cudaStream_t st, const int **out)
+{
+    int dev = 0;
+    DBSPM_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    const auto key = std::make_tuple(dev, n, G, blockrows);
+    auto it = g_rowmaps.find(key);
+    if (it != g_rowmaps.end()) { *out = it->second; return DBSPM_OK; }
+    DBSPM_REQUIRE((long long)G * blockrows < 2147483647LL, DBSPM_EUNSUPPORTED, "row table overflows 32 bits");
+    std::vector<int> h((size_t)n);
+    for (int K = 0; K < n; ++K) h[K] = dist_row_of(K, n, G, blockrows);
+    int *d = nullptr;
+    DBSPM_CUDA_TRY(cudaMalloc((void **)&d, sizeof(int) * (size_t)n));
+    DBSPM_CUDA_TRY(cudaMemcpyAsync(d, h.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    DBSPM_CUDA_TRY(cudaStreamSynchronize(st));
+    g_rowmaps[key] = d;
+    *out = d;
+    return DBSPM_OK;
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // tile width for an axis pass: widest of 8,4,2,1 lines whose tile leaves room for 2 CTAs/SM
@@ -274,10 +307,16 @@ struct GatherSpec {
     int z0[2], valid[2];
 };
 
+// row tables of a mapped pass (distributed correlation); null table = natural rows
+struct AxisMap {
+    const int *in_map, *out_map;
+    long long in_ostride, out_ostride;      // elements between consecutive slabs (0 = n * inner)
+};
+
 template <int D>
 static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, int narrays,
                        double alpha0, double alpha1, int use_pow, int n, long long inner, long long outer,
-                       cudaStream_t st, int flags, const GatherSpec *g = nullptr)
+                       cudaStream_t st, int flags, const GatherSpec *g = nullptr, const AxisMap *mp = nullptr)
 {
     DevPlan *pl = nullptr;
     int rc = get_plan(n, st, &pl);
@@ -292,6 +331,14 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     // (4-line tiles, FP64/shared-memory bound) and ties below 256
     const bool tma_auto = n >= 256 && axis3_config(n, inner) == 3;
     P.gather = 0;
+    P.in_map = P.out_map = nullptr;
+    P.in_ostride = P.out_ostride = (long long)n * inner;
+    if (mp) {
+        DBSPM_REQUIRE(!g && axis_v2_ok(pl->host.dev), DBSPM_EUNSUPPORTED, "row-mapped pass needs an all-fast-radix plan (n=%d)", n);
+        P.in_map = mp->in_map; P.out_map = mp->out_map;
+        if (mp->in_ostride) P.in_ostride = mp->in_ostride;
+        if (mp->out_ostride) P.out_ostride = mp->out_ostride;
+    }
     if (g) {
         // only the register-staged body can remap its loads
         DBSPM_REQUIRE(axis_v2_ok(pl->host.dev), DBSPM_EUNSUPPORTED, "pruned first pass needs an all-fast-radix plan (n=%d)", n);
@@ -300,13 +347,13 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
         P.g_src_inner = inner / P.g_dst_nzh * P.g_src_nzh;
         for (int w = 0; w < 2; ++w) { P.g_zp0[w] = g->z0[w] / 2; P.g_valid[w] = g->valid[w] / 2; }
     }
-    if (!g && ((flags & DBSPM_CORR_USE_TMA) || (tma_auto && !(flags & DBSPM_CORR_NO_TMA))) && !(flags & DBSPM_CORR_AXIS_V1)) {
+    if (!g && !mp && ((flags & DBSPM_CORR_USE_TMA) || (tma_auto && !(flags & DBSPM_CORR_NO_TMA))) && !(flags & DBSPM_CORR_AXIS_V1)) {
         bool done = false;
         rc = launch_axis_tma<D>(in0, out0, in1, out1, narrays, alpha0, alpha1, use_pow, n, inner, outer, pl, st, &done);
         if (rc || done) return rc;
     }
     P.plan = pl->host.dev; P.tw = pl->tw; P.pos_of = pl->pos_of; P.freq_of = pl->freq_of;
-    P.v2 = axis_v2_ok(P.plan) && (g || !(flags & DBSPM_CORR_AXIS_V1));
+    P.v2 = axis_v2_ok(P.plan) && (g || mp || !(flags & DBSPM_CORR_AXIS_V1));
     P.tw_smem = 0;
     size_t smem;
     bool wide = false;
@@ -320,7 +367,7 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
         // (the same change slows the y pass, whose rows are 2 KB apart, 2.20 -> 2.36 ms)
         // With the power fused into the load the pass is FP64-issue bound and two CTAs hide it better:
         // 4.21 ms (2 x 256) against 4.87 ms (1 x 512).
-        else if (outer == 1 && P.tshift == 2 && inner >= 65536 && P.plan.nstages > 1 &&
+        else if (!mp && outer == 1 && P.tshift == 2 && inner >= 65536 && P.plan.nstages > 1 &&
                  !(use_pow && (alpha0 != 1.0 || alpha1 != 1.0)) &&
                  axis2_smem_bytes(n, 3, P.plan.nstages, 0) <= 200 * 1024) {
             wide = true;
@@ -329,6 +376,7 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
         }
 #endif
     }
+    DBSPM_REQUIRE(P.v2 || !mp, DBSPM_EUNSUPPORTED, "row-mapped pass: axis length %d does not fit in shared memory", n);
     if (!P.v2) {
         P.tshift = pick_tshift(n, inner);
         DBSPM_REQUIRE(P.tshift >= 0, DBSPM_EUNSUPPORTED, "axis length %d does not fit in shared memory", n);
@@ -337,7 +385,10 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     P.tiles = (inner + (1LL << P.tshift) - 1) >> P.tshift;
     const long long nblocks = outer * P.tiles;
     DBSPM_REQUIRE(nblocks > 0 && nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large (%lld blocks)", nblocks);
-    if (P.v2 && wide) {
+    if (P.v2 && mp) {
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2m_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        axis_pass2m_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), AXIS2_THREADS, smem, st>>>(P);
+    } else if (P.v2 && wide) {
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2w_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         axis_pass2w_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), 512, smem, st>>>(P);
     } else if (P.v2) {
@@ -391,6 +442,50 @@ static int corr3d_complex(const double *A, const double *B, double alphaA, doubl
     return DBSPM_OK;
 }
 
+// fused z kernel on (nx, ny_rows, nz/2) spectra -> packed window (nx, ny_rows, nwh).  slot_mode: the rows are
+// slots [slot_base, slot_base + ny_rows) of a distributed y axis (corr_body.h, dist_slot_of)
+static int launch_zfused(const cplx *WA, const cplx *WB, cplx *W, int nx, int ny_rows, int nz, int z_lo, int nwh,
+                         double scale, int slot_mode, int slot_base, int flags, cudaStream_t st)
+{
+    const int n = nz / 2;
+    DevPlan *pl = nullptr, *plN = nullptr;
+    int rc = get_plan(n, st, &pl, ZF2_MAX_RADIX);
+    if (rc) return rc;
+    rc = get_plan(nz, st, &plN);
+    if (rc) return rc;
+    ZFusedParams P;
+    P.ZA = WA; P.ZB = WB; P.W = W;
+    P.nx = nx; P.ny = ny_rows; P.n = n; P.nwh = nwh; P.z_lo = z_lo;
+    P.scale = scale;
+    P.plan = pl->host.dev; P.tw = pl->tw; P.pos_of = pl->pos_of; P.freq_of = pl->freq_of; P.twN = plN->tw;
+    P.npairs = (long long)(nx / 2 + 1) * ny_rows;
+    P.slot_mode = slot_mode; P.slot_base = slot_base;
+    const bool v2 = axis_v2_ok(P.plan) && zfused2_smem_bytes<ZF2_PAIRS>(n) <= 113 * 1024 &&
+                    !(flags & DBSPM_CORR_AXIS_V1);
+    if (v2) {
+        const long long ngroups = (P.npairs + ZF2_PAIRS - 1) / ZF2_PAIRS;
+        const size_t smem = zfused2_smem_bytes<ZF2_PAIRS>(n);
+        // persistent blocks: a few per SM (148 SMs), each walking over its share of the pair groups
+        int per_sm = (int)((220 * 1024) / (smem + 1024));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+        long long nblocks = 148LL * per_sm * 2;
+        if (nblocks > ngroups) nblocks = ngroups;
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        zfused2_kernel<<<(unsigned)nblocks, ZF2_THREADS, smem, st>>>(P);
+    } else {
+        const long long nblocks = (P.npairs + ZL - 1) / ZL;
+        const size_t smem = zfused_smem_bytes(n);
+        DBSPM_REQUIRE(smem <= 227 * 1024, DBSPM_EUNSUPPORTED, "nz=%d too long for the fused z kernel", nz);
+        DBSPM_REQUIRE(nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large");
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        zfused_kernel<<<(unsigned)nblocks, DBSPM_THREADS, smem, st>>>(P);
+    }
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    return DBSPM_OK;
+}
+
 // the five launches on a problem of z length nz (the caller's, or the pruned length when g != null)
 static int corr3d_core(const double *A, const double *B, double alphaA, double alphaB, double dV,
                        int nx, int ny, int nz, int z_lo, int z_hi, double *E_win,
@@ -416,40 +511,8 @@ static int corr3d_core(const double *A, const double *B, double alphaA, double a
 
     // fused z: forward, untangle, product, window phase, pruned inverse
     if (!(flags & DBSPM_CORR_SKIP_Z)) {
-        DevPlan *pl = nullptr, *plN = nullptr;
-        rc = get_plan(n, st, &pl, ZF2_MAX_RADIX);
+        rc = launch_zfused(WA, WB, W, nx, ny, nz, z_lo, nwh, dV / ((double)nx * (double)ny * (double)nz) * 0.25, 0, 0, flags, st);
         if (rc) return rc;
-        rc = get_plan(nz, st, &plN);
-        if (rc) return rc;
-        ZFusedParams P;
-        P.ZA = WA; P.ZB = WB; P.W = W;
-        P.nx = nx; P.ny = ny; P.n = n; P.nwh = nwh; P.z_lo = z_lo;
-        P.scale = dV / ((double)nx * (double)ny * (double)nz) * 0.25;
-        P.plan = pl->host.dev; P.tw = pl->tw; P.pos_of = pl->pos_of; P.freq_of = pl->freq_of; P.twN = plN->tw;
-        P.npairs = (long long)(nx / 2 + 1) * ny;
-        const bool v2 = axis_v2_ok(P.plan) && zfused2_smem_bytes<ZF2_PAIRS>(n) <= 113 * 1024 &&
-                        !(flags & DBSPM_CORR_AXIS_V1);
-        if (v2) {
-            const long long ngroups = (P.npairs + ZF2_PAIRS - 1) / ZF2_PAIRS;
-            const size_t smem = zfused2_smem_bytes<ZF2_PAIRS>(n);
-            // persistent blocks: a few per SM (148 SMs), each walking over its share of the pair groups
-            int per_sm = (int)((220 * 1024) / (smem + 1024));
-            per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-            long long nblocks = 148LL * per_sm * 2;
-            if (nblocks > ngroups) nblocks = ngroups;
-            DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            zfused2_kernel<<<(unsigned)nblocks, ZF2_THREADS, smem, st>>>(P);
-        } else {
-            const long long nblocks = (P.npairs + ZL - 1) / ZL;
-            const size_t smem = zfused_smem_bytes(n);
-            DBSPM_REQUIRE(smem <= 227 * 1024, DBSPM_EUNSUPPORTED, "nz=%d too long for the fused z kernel", nz);
-            DBSPM_REQUIRE(nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large");
-            DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            zfused_kernel<<<(unsigned)nblocks, DBSPM_THREADS, smem, st>>>(P);
-        }
-        DBSPM_CUDA_TRY(cudaGetLastError());
     }
 
     // inverse y, then x on the packed window (in place)
@@ -533,6 +596,98 @@ extern "C" int dbspm_corr3d_pruned_f64(const double *A, const double *B, double 
     g.src_nz = nz; g.dst_nz = G.Mp;
     g.z0[0] = G.zA0; g.z0[1] = G.zB0; g.valid[0] = G.validA; g.valid[1] = G.validB;
     return corr3d_core(A, B, alphaA, alphaB, dV, nx, ny, G.Mp, G.w_lo, G.w_lo + (z_hi - z_lo), E_win, workspace, flags, st, &g);
+}
+
+// ---- distributed correlation: x-slab decomposition over the G ranks of a group -----------------------------
+// Rank g of G holds the x-slab [g*nx/G, (g+1)*nx/G) of A and B.  (1) fwd: y transform of the slab (power fused),
+// written destination-major: block h of the send buffer = the ny/G frequencies (slot order) rank h owns.
+// (2) the caller exchanges the blocks (all-to-all: the one data-path collective of the sr/es step).  (3) mid: x
+// transform of the received (nx, ny/G, nz/2) spectra in place, fused z kernel, inverse x transform of this rank's
+// packed window rows.  (4) the caller gathers the G packed windows.  (5) fin: inverse y transform reading its rows
+// through the slot table, into the real window.  Every output plane needs every input plane, so nothing else of
+// the transform can be split without an exchange; this order needs one all-to-all of 16N/G bytes per rank.
+extern "C" int dbspm_corr3d_dist_supported(int nx, int ny, int nz, int G)
+{
+    if (!dist_shape_ok(nx, ny, nz, G)) return 0;
+    HostPlan hx, hy, hz;
+    if (!dbspm_make_plan(nx, hx) || !dbspm_make_plan(ny, hy) || !dbspm_make_plan(nz / 2, hz, ZF2_MAX_RADIX)) return 0;
+    if (!axis_v2_ok(hx.dev) || !axis_v2_ok(hy.dev)) return 0;
+    int ts, tws;
+    axis2_config(ny, nz / 2, hy.dev.nstages, &ts, &tws);
+    if (axis2_smem_bytes(ny, ts, hy.dev.nstages, tws) > 227 * 1024) return 0;
+    if (zfused_smem_bytes(nz / 2) > 227 * 1024) return 0;
+    return 1;
+}
+
+extern "C" int dbspm_corr3d_dist_fwd_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
+                                         int nxl, int ny, int nz, int G, void *sendA, void *sendB, int flags, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    DBSPM_REQUIRE(A_slab && B_slab && sendA && sendB, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(dist_shape_ok(nxl * G, ny, nz, G), DBSPM_EUNSUPPORTED,
+                  "distributed correlation needs even nz, ny %% (2G) == 0 (got slab %d x %d x %d, G=%d)", nxl, ny, nz, G);
+    DBSPM_REQUIRE(((uintptr_t)A_slab & 15) == 0 && ((uintptr_t)B_slab & 15) == 0 && ((uintptr_t)sendA & 15) == 0 &&
+                  ((uintptr_t)sendB & 15) == 0, DBSPM_EINVAL, "buffers must be 16-byte aligned");
+    const int n = nz / 2, nyl = ny / G;
+    const int *omap = nullptr;
+    int rc = get_rowmap(ny, G, (long long)nxl * nyl, st, &omap);
+    if (rc) return rc;
+    AxisMap mp;
+    mp.in_map = nullptr; mp.out_map = omap; mp.in_ostride = 0; mp.out_ostride = (long long)nyl * n;
+    return launch_axis<-1>((const cplx *)A_slab, (cplx *)sendA, (const cplx *)B_slab, (cplx *)sendB, 2, alphaA, alphaB, 1,
+                           ny, n, nxl, st, flags, nullptr, &mp);
+}
+
+extern "C" int dbspm_corr3d_dist_mid_f64(void *recvA, void *recvB, double dV, int nx, int ny, int nz, int G, int h,
+                                         int z_lo, int z_hi, void *W_local, int flags, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    DBSPM_REQUIRE(recvA && recvB && W_local, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(dist_shape_ok(nx, ny, nz, G) && h >= 0 && h < G, DBSPM_EUNSUPPORTED,
+                  "distributed correlation: bad shape (%d,%d,%d) / rank %d of %d", nx, ny, nz, h, G);
+    DBSPM_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= nz, DBSPM_EINVAL, "bad window [%d,%d) for nz=%d", z_lo, z_hi, nz);
+    const int n = nz / 2, nyl = ny / G, nwh = (z_hi - z_lo + 1) / 2;
+    cplx *WA = (cplx *)recvA, *WB = (cplx *)recvB, *W = (cplx *)W_local;
+    int rc = launch_axis<-1>(WA, WA, WB, WB, 2, 1.0, 1.0, 0, nx, (long long)nyl * n, 1, st, flags);
+    if (rc) return rc;
+    rc = launch_zfused(WA, WB, W, nx, nyl, nz, z_lo, nwh, dV / ((double)nx * (double)ny * (double)nz) * 0.25, 1, h * nyl, flags, st);
+    if (rc) return rc;
+    return launch_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)nyl * nwh, 1, st, flags);
+}
+
+extern "C" size_t dbspm_corr3d_dist_fin_workspace_bytes(int nx, int ny, int z_lo, int z_hi)
+{
+    const int nzw = z_hi - z_lo;
+    if (nx < 1 || ny < 1 || nzw < 1) return 0;
+    return (nzw & 1) ? align_up((size_t)nx * ny * ((nzw + 1) / 2) * 16, 256) : 0;
+}
+
+extern "C" int dbspm_corr3d_dist_fin_f64(const void *W_all, int nx, int ny, int G, int z_lo, int z_hi, double *E_win,
+                                         void *workspace, size_t workspace_bytes, int flags, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    DBSPM_REQUIRE(W_all && E_win, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(G >= 1 && ny % (2 * G) == 0 && z_hi > z_lo, DBSPM_EUNSUPPORTED, "distributed correlation: ny %% (2G) != 0");
+    const int nzw = z_hi - z_lo, nwh = (nzw + 1) / 2, nyl = ny / G;
+    const size_t need = dbspm_corr3d_dist_fin_workspace_bytes(nx, ny, z_lo, z_hi);
+    DBSPM_REQUIRE(need == 0 || (workspace && workspace_bytes >= need && ((uintptr_t)workspace & 255) == 0), DBSPM_EWORKSPACE,
+                  "workspace needs %zu bytes, 256-byte aligned (got %zu)", need, workspace_bytes);
+    cplx *W = (nzw & 1) ? (cplx *)workspace : (cplx *)E_win;
+    const int *imap = nullptr;
+    int rc = get_rowmap(ny, G, (long long)nx * nyl, st, &imap);
+    if (rc) return rc;
+    AxisMap mp;
+    mp.in_map = imap; mp.out_map = nullptr; mp.in_ostride = (long long)nyl * nwh; mp.out_ostride = 0;
+    rc = launch_axis<1>((const cplx *)W_all, W, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, st, flags, nullptr, &mp);
+    if (rc) return rc;
+    if (nzw & 1) {
+        const long long ncol = (long long)nx * ny;
+        long long blocks = (ncol * nzw + DBSPM_THREADS - 1) / DBSPM_THREADS;
+        if (blocks > 148LL * 32) blocks = 148LL * 32;
+        compact_kernel<<<(unsigned)blocks, DBSPM_THREADS, 0, st>>>((const double *)W, E_win, ncol, nzw, 2 * nwh);
+        DBSPM_CUDA_TRY(cudaGetLastError());
+    }
+    return DBSPM_OK;
 }
 
 extern "C" int dbspm_zsupport_f64(const double *B, int nx, int ny, int nz, int *plane_nonzero, void *stream)

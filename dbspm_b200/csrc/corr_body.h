@@ -50,7 +50,38 @@ struct AxisParams {
     long long g_src_inner;
     int g_dst_nzh, g_src_nzh;
     int g_zp0[2], g_valid[2];
+    // distributed correlation (v2 body, MAP variant): row K of the transform axis lives at row in_map[K] /
+    // goes to row out_map[K] (units of `inner` elements) and slab o starts at o * in_ostride / o * out_ostride
+    // elements; null maps = natural rows.  Without maps the strides are n * inner.
+    const int *in_map, *out_map;
+    long long in_ostride, out_ostride;
 };
+
+// ---- distributed correlation: slot order of a transform axis --------------------------------------
+// The x-slab decomposition hands each of G ranks n/G frequencies of the y axis.  The fused
+// z kernel needs the frequencies ky and -ky on the same rank, so frequencies are dealt in "slot" order
+// 0, n/2, 1, n-1, 2, n-2, ...: slot(0) = 0, slot(n/2) = 1, slot(k) = 2k, slot(n-k) = 2k+1 (0 < k < n/2); the
+// mirror of slot S is S itself for S < 2 and S^1 otherwise.  Rank h owns slots [h*n/G, (h+1)*n/G), n/G even.
+HD int dist_slot_of(int K, int n)
+{
+    if (K == 0) return 0;
+    if (2 * K == n) return 1;
+    return 2 * K < n ? 2 * K : 2 * (n - K) + 1;
+}
+
+HD int dist_mirror_slot(int S) { return S < 2 ? S : (S ^ 1); }
+
+// row (units of `inner`) of frequency K inside a buffer laid out (G, rows_per_rank_block / (n/G), n/G, inner)
+HD int dist_row_of(int K, int n, int G, long long blockrows)
+{
+    const int nl = n / G, S = dist_slot_of(K, n);
+    return (int)((long long)(S / nl) * blockrows + (S % nl));
+}
+
+HD bool dist_shape_ok(int nx, int ny, int nz, int G)
+{
+    return G >= 1 && nx >= 1 && ny >= 2 && nz >= 2 && (nz % 2) == 0 && (ny % (2 * G)) == 0 && (nx % G) == 0;
+}
 
 // ---- z-pruned correlation: geometry ---------------------------------------------------------
 // When the tip array B is exactly zero outside the planes (s_lo + m) mod nz, m in [0, s_len), the window
@@ -200,7 +231,7 @@ HD void axis2_config(int n, long long inner, int nstages, int *tshift, int *tw_s
     *tw_smem = axis2_smem_bytes(n, ts, nstages, 1) <= budget ? 1 : 0;
 }
 
-template <int D, int R>
+template <int D, int R, int MAP>
 HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gin, cplx *gout, int tcount,
                     bool do_pow, double alpha, int which, long long i0, int tid, int nthr)
 {
@@ -223,8 +254,13 @@ HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gi
             src = P.in[which] + ((size_t)y * P.g_src_nzh + zs) + (size_t)j * rstride;
         }
         if (have) {
+            if (MAP && P.in_map) {
 #pragma unroll
-            for (int k = 0; k < R; ++k) v[k] = ld_stream(src + (size_t)k * q * rstride);
+                for (int k = 0; k < R; ++k) v[k] = ld_stream(gin + (size_t)LDG(P.in_map + j + k * q) * rstride + t);
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; ++k) v[k] = ld_stream(src + (size_t)k * q * rstride);
+            }
             if (do_pow) {
 #pragma unroll
                 for (int k = 0; k < R; ++k) { v[k].x = pow_nonneg(v[k].x, alpha); v[k].y = pow_nonneg(v[k].y, alpha); }
@@ -237,7 +273,8 @@ HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gi
         if (single) {
             if (t < tcount) {
 #pragma unroll
-                for (int k = 0; k < R; ++k) st_stream(gout + (size_t)k * P.inner + t, v[k]);
+                for (int k = 0; k < R; ++k)
+                    st_stream(gout + (size_t)((MAP && P.out_map) ? LDG(P.out_map + k) : k) * P.inner + t, v[k]);
             }
         } else {
 #pragma unroll
@@ -252,7 +289,7 @@ HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gi
     }
 }
 
-template <int D, int R>
+template <int D, int R, int MAP>
 HD void axis2_last(const AxisParams &P, const cplx *s, cplx *gout, int tcount, int tid, int nthr)
 {
     const int n = P.n, nb = n / R, tmask = (1 << P.tshift) - 1;
@@ -266,14 +303,19 @@ HD void axis2_last(const AxisParams &P, const cplx *s, cplx *gout, int tcount, i
         bfly<R, D>(v);
         if (t < tcount) {
             const int K0 = LDG(P.freq_of + blk * R);           // frequency held by position blk*R
-            cplx *dst = gout + (size_t)K0 * P.inner + t;
+            if (MAP && P.out_map) {
 #pragma unroll
-            for (int k = 0; k < R; ++k) st_stream(dst + (size_t)k * nb * P.inner, v[k]);
+                for (int k = 0; k < R; ++k) st_stream(gout + (size_t)LDG(P.out_map + K0 + k * nb) * P.inner + t, v[k]);
+            } else {
+                cplx *dst = gout + (size_t)K0 * P.inner + t;
+#pragma unroll
+                for (int k = 0; k < R; ++k) st_stream(dst + (size_t)k * nb * P.inner, v[k]);
+            }
         }
     }
 }
 
-template <int D>
+template <int D, int MAP = 0>
 HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long long bid, int which, int tid, int nthr)
 {
     const int n = P.n, T = 1 << P.tshift;
@@ -286,8 +328,8 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
     const long long tile = bid - o * P.tiles;
     const long long i0 = tile << P.tshift;
     const int tcount = (int)((P.inner - i0) < T ? (P.inner - i0) : T);
-    const cplx *gin = P.in[which] + (size_t)o * n * P.inner + i0;
-    cplx *gout = P.out[which] + (size_t)o * n * P.inner + i0;
+    const cplx *gin = P.in[which] + (MAP ? (size_t)o * P.in_ostride : (size_t)o * n * P.inner) + i0;
+    cplx *gout = P.out[which] + (MAP ? (size_t)o * P.out_ostride : (size_t)o * n * P.inner) + i0;
     const double alpha = P.alpha[which];
     const bool do_pow = P.use_pow && alpha != 1.0;
 
@@ -295,7 +337,7 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
         for (int e = tid; e < n; e += nthr) twbuf[e] = ldg_c(P.tw + e);
         BLOCK_SYNC();
     }
-#define CALL_(R) axis2_first<D, R>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr)
+#define CALL_(R) axis2_first<D, R, MAP>(P, s, tw, gin, gout, tcount, do_pow, alpha, which, i0, tid, nthr)
     DBSPM_FAST_RADIX_SWITCH(pl.radix[0], CALL_)
 #undef CALL_
     if (pl.nstages == 1) return;
@@ -309,7 +351,7 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
         m /= r;
         BLOCK_SYNC();
     }
-#define CALL_(R) axis2_last<D, R>(P, s, gout, tcount, tid, nthr)
+#define CALL_(R) axis2_last<D, R, MAP>(P, s, gout, tcount, tid, nthr)
     DBSPM_FAST_RADIX_SWITCH(pl.radix[pl.nstages - 1], CALL_)
 #undef CALL_
 }
@@ -560,6 +602,9 @@ struct ZFusedParams {
     const int *freq_of;       // length n: tile row -> frequency
     const cplx *twN;          // length-2n table: twN[e] = exp(-2 pi i e / nz)
     long long npairs;         // (nx/2+1) * ny candidate pairs
+    // distributed correlation: this rank holds the ny rows of the y axis that are slots [slot_base, slot_base + ny)
+    // of the global axis (dist_slot_of); row r pairs with the row of its mirror slot.  slot_mode = 0: natural rows
+    int slot_mode, slot_base;
 };
 
 HD size_t zfused_smem_bytes(int n)
@@ -577,7 +622,7 @@ HD ZPair zpair_of(const ZFusedParams &P, long long pid)
     z.kx = (int)(pid / P.ny);
     z.ky = (int)(pid - (long long)z.kx * P.ny);
     z.mx = z.kx == 0 ? 0 : P.nx - z.kx;
-    z.my = z.ky == 0 ? 0 : P.ny - z.ky;
+    z.my = P.slot_mode ? dist_mirror_slot(P.slot_base + z.ky) - P.slot_base : (z.ky == 0 ? 0 : P.ny - z.ky);
     if (z.mx == z.kx) {                       // kx is its own mirror: keep one of (ky, -ky)
         if (z.ky > z.my) return z;
         z.self = (z.ky == z.my);

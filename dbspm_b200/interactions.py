@@ -154,6 +154,62 @@ def get_density_overlap(rho0, rho1, dr):
     return density_overlap_window(rho0, rho1, dr)
 
 
+# ------------------------------------------------------------- sr / es over the ranks of a group
+# x-slab decomposition (include/dbspm_b200.h, "distributed"): the three compute stages; the two exchanges
+# between them (all-to-all, gather) belong to parallel.sr_es_distributed.  Buffers are float64 CUDA tensors
+# whose last axis holds (re, im) pairs.
+def dist_supported(shape, G: int) -> bool:
+    nx, ny, nz = (int(v) for v in shape)
+    return bool(_lib.lib().dbspm_corr3d_dist_supported(nx, ny, nz, int(G)))
+
+
+def dist_forward(a_slab, b_slab, G, alpha0=1.0, alpha1=1.0, out=None, flags=0):
+    """y transform of this rank's x-slab (nxl,ny,nz) of both arrays, power fused, written destination-major:
+    returns (sendA, sendB), each (G, nxl, ny/G, nz) float64 = complex (.., nz/2); block h goes to rank h."""
+    dev = a_slab.device
+    a, b = _to_dev(a_slab, dev), _to_dev(b_slab, dev)
+    nxl, ny, nz = (int(v) for v in a.shape)
+    G = int(G)
+    if out is None:
+        out = (torch.empty((G, nxl, ny // G, nz), dtype=torch.float64, device=dev),
+               torch.empty((G, nxl, ny // G, nz), dtype=torch.float64, device=dev))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dbspm_corr3d_dist_fwd_f64(a.data_ptr(), b.data_ptr(), float(alpha0), float(alpha1), nxl, ny, nz,
+                                                        G, out[0].data_ptr(), out[1].data_ptr(), int(flags), _stream_ptr(dev)))
+    return out
+
+
+def dist_middle(recvA, recvB, dr, shape, G, h, z_lo, z_hi, out=None, flags=0):
+    """x transform (in place) of the received spectra (nx, ny/G, nz), fused z kernel, inverse x transform:
+    returns this rank's rows of the packed window, (nx, ny/G, 2*ceil(nzw/2)) float64."""
+    dev = recvA.device
+    nx, ny, nz = (int(v) for v in shape)
+    nwh = (int(z_hi) - int(z_lo) + 1) // 2
+    if out is None:
+        out = torch.empty((nx, ny // int(G), 2 * nwh), dtype=torch.float64, device=dev)
+    dV = float(np.prod(np.asarray(dr, dtype=np.float64)))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dbspm_corr3d_dist_mid_f64(recvA.data_ptr(), recvB.data_ptr(), dV, nx, ny, nz, int(G), int(h),
+                                                        int(z_lo), int(z_hi), out.data_ptr(), int(flags), _stream_ptr(dev)))
+    return out
+
+
+def dist_finish(W_all, shape, G, z_lo, z_hi, out=None, flags=0):
+    """inverse y transform of the gathered packed windows (G, nx, ny/G, 2*ceil(nzw/2)) -> (nx, ny, nzw)."""
+    dev = W_all.device
+    nx, ny, _ = (int(v) for v in shape)
+    z_lo, z_hi = int(z_lo), int(z_hi)
+    if out is None:
+        out = torch.empty((nx, ny, z_hi - z_lo), dtype=torch.float64, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        need = L.dbspm_corr3d_dist_fin_workspace_bytes(nx, ny, z_lo, z_hi)
+        ws = _workspace(need, dev) if need else None
+        _lib.check(L.dbspm_corr3d_dist_fin_f64(W_all.data_ptr(), nx, ny, int(G), z_lo, z_hi, out.data_ptr(),
+                                               ws.data_ptr() if ws is not None else None, need, int(flags), _stream_ptr(dev)))
+    return out
+
+
 # ------------------------------------------------------------------------------------ static
 def build_static(components, device=None):
     """static = sum_l scale_l * comp_l in the given order (dbspm:479-486: sr is scaled by V,

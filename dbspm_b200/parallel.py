@@ -135,6 +135,77 @@ def gather_windows(plan, mine, nx, ny, z_lo, z_hi, device, n_inter: int = 2, dst
     return out
 
 
+# ---- sr / es with the transform itself distributed (x-slab decomposition) ----------------------------------
+_GROUPS: dict = {}
+
+
+def dist_groups(world: int, n_inter: int = 2):
+    """Rank groups for the distributed transform: n_inter equal groups of G = world / n_inter >= 2 consecutive
+    ranks (group i computes interaction i), or None when the world does not divide that way (the callers then
+    use interaction_plan: replicated inputs, z-slab split of the output)."""
+    if world % n_inter or world // n_inter < 2:
+        return None
+    G = world // n_inter
+    return [list(range(i * G, (i + 1) * G)) for i in range(n_inter)]
+
+
+def _process_groups(groups):
+    """torch.distributed groups for `groups` (created once; every rank creates every group, in order)."""
+    key = tuple(tuple(g) for g in groups)
+    if key not in _GROUPS:
+        _GROUPS[key] = [dist.new_group(ranks=g) for g in groups]
+    return _GROUPS[key]
+
+
+def slot_order(n: int):
+    """Frequencies of an axis of even length n in slot order 0, n/2, 1, n-1, 2, n-2, ... (dist_slot_of in
+    csrc/corr_body.h): k and -k are neighbours, so equal even-sized blocks of slots are closed under k -> -k,
+    which is what the fused z kernel needs of the rows a rank owns."""
+    order = [0, n // 2]
+    for k in range(1, n // 2):
+        order += [k, n - k]
+    return order[:n]
+
+
+def x_slab(nx: int, G: int, h: int):
+    return h * (nx // G), (h + 1) * (nx // G)
+
+
+def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, groups, dst: int = 0, marks=None):
+    """The distributed sr / es step (replaces the rank-0-only dbspm:320-352).
+
+    groups[i] = the G ranks that compute interaction i; this rank, member h of its group, passes the x-slab
+    x_slab(nx, G, h) of its interaction's two arrays.  `stages` provides the three compute stages
+    (dbspm_b200.interactions: dist_forward / dist_middle / dist_finish; the CPU tests inject numpy ones).
+    Data-path collectives: one all-to-all per array inside the group (the transpose every distributed FFT needs:
+    16N/G bytes per rank) and one gather of the packed window rows to rank `dst`, which runs the final inverse
+    y pass of every interaction.  Returns the list of (nx,ny,nzw) windows on `dst`, None elsewhere."""
+    rank, world = _world()
+    G = len(groups[0])
+    which = next(i for i, g in enumerate(groups) if rank in g)
+    h = groups[which].index(rank)
+    pg = _process_groups(groups)[which]
+    sendA, sendB = stages.dist_forward(a_slab, b_slab, G, alpha, alpha)
+    recvA, recvB = torch.empty_like(sendA), torch.empty_like(sendB)
+    if marks is not None:
+        marks.append("fwd")
+    dist.all_to_all_single(recvA, sendA, group=pg)
+    dist.all_to_all_single(recvB, sendB, group=pg)
+    if marks is not None:
+        marks.append("a2a")
+    # (G, nxl, ny/G, nz) received = (nx, ny/G, nz): source ranks are consecutive x-slabs
+    W = stages.dist_middle(recvA, recvB, dr, shape, G, h, z_lo, z_hi)
+    if marks is not None:
+        marks.append("mid")
+    big = None
+    if rank == dst:
+        big = torch.empty((world,) + tuple(W.shape), dtype=W.dtype, device=W.device)
+    dist.gather(W.contiguous(), list(big.unbind(0)) if rank == dst else None, dst=dst)
+    if rank != dst:
+        return None
+    return [stages.dist_finish(big[g[0]:g[0] + G], shape, G, z_lo, z_hi) for g in groups]
+
+
 def relax_sharded(compute_tile, nx, device):
     """compute_tile(i_lo, i_hi) -> dict of tensors whose first axis is the tile's x extent
     (E, theta, phi, tip_x, tip_y, tip_z: (ni,ny,nz)).  Rank 0 returns the concatenated dict."""

@@ -89,6 +89,30 @@ int dbspm_corr3d_pruned_f64(const double *A, const double *B, double alphaA, dou
                             void *workspace, size_t workspace_bytes, int flags, void *stream);
 int dbspm_zsupport_f64(const double *B, int nx, int ny, int nz, int *plane_nonzero, void *stream);
 
+/* ---- sr / es distributed over the G ranks of a group (x-slab decomposition) ------------------
+ * Replaces the same reference lines as dbspm_corr3d_f64 (the reference computes sr / es on rank 0 only,
+ * dbspm:320,339).  Rank g holds the x-slab [g*nx/G, (g+1)*nx/G) of A and B -- contiguous in the .npz member, so a
+ * rank reads and uploads 1/G of each input.  The caller owns the two exchanges (NCCL through torch.distributed):
+ *   1. dbspm_corr3d_dist_fwd_f64: y transform of the slab (power fused on load) written destination-major:
+ *      sendA/sendB = (G, nxl, ny/G, nz/2) complex128; block h holds the ny/G y-frequencies rank h owns.
+ *      Frequencies are dealt in slot order 0, ny/2, 1, ny-1, 2, ny-2, ... so that ky and -ky sit on one rank.
+ *   2. all-to-all of the G blocks  ->  recvA/recvB = (nx, ny/G, nz/2) on every rank.
+ *   3. dbspm_corr3d_dist_mid_f64 (rank h of G): x transform in place, fused z kernel (forward z, spectral product,
+ *      inverse z of the window planes only), inverse x transform -> W_local = (nx, ny/G, ceil(nzw/2)) complex128.
+ *   4. gather of the G W_local blocks -> W_all = (G, nx, ny/G, ceil(nzw/2)).
+ *   5. dbspm_corr3d_dist_fin_f64: inverse y transform reading its rows through the slot table -> E_win (nx,ny,nzw).
+ * Requires even nz, nx % G == 0, ny % (2G) == 0 and lengths nx, ny whose prime factors are <= 7
+ * (dbspm_corr3d_dist_supported returns 0 otherwise; callers then use dbspm_corr3d_f64 on replicated inputs).
+ * G = 1 needs no exchange and equals dbspm_corr3d_f64.  fin needs a workspace only for an odd window.          */
+int dbspm_corr3d_dist_supported(int nx, int ny, int nz, int G);
+int dbspm_corr3d_dist_fwd_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
+                              int nxl, int ny, int nz, int G, void *sendA, void *sendB, int flags, void *stream);
+int dbspm_corr3d_dist_mid_f64(void *recvA, void *recvB, double dV, int nx, int ny, int nz, int G, int h,
+                              int z_lo, int z_hi, void *W_local, int flags, void *stream);
+size_t dbspm_corr3d_dist_fin_workspace_bytes(int nx, int ny, int z_lo, int z_hi);
+int dbspm_corr3d_dist_fin_f64(const void *W_all, int nx, int ny, int G, int z_lo, int z_hi, double *E_win,
+                              void *workspace, size_t workspace_bytes, int flags, void *stream);
+
 /* ---- static potential assembly: acc = (init ? 0 : acc) + comp*scale  (separate mul, add) -- */
 int dbspm_static_accumulate_f64(double *acc, const double *comp, double scale, size_t n,
                                 int init, void *stream);

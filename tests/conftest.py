@@ -48,6 +48,8 @@ class Emu:
                                      C.c_int, C.c_int, _dp, C.c_int]
         L.emu_corr3d_pruned_f64.argtypes = [_dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]
+        L.emu_corr3d_dist_f64.argtypes = [_dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, _dp, C.c_int, C.c_int]
         L.emu_fft_lines.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int]
         L.emu_fft_lines_t.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int]
         L.emu_relax_powell_f64.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -71,6 +73,18 @@ class Emu:
                                    z_lo, z_hi, self._p(out), tshift)
         if rc:
             raise RuntimeError(f"emu_corr3d_f64 -> {rc}")
+        return out
+
+    def corr3d_dist(self, a, b, dr, z_lo, z_hi, G, alpha0=1.0, alpha1=1.0, tshift=-1):
+        """the x-slab distributed correlation with G ranks run one after the other"""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        nx, ny, nz = a.shape
+        out = np.empty((nx, ny, z_hi - z_lo))
+        rc = self.L.emu_corr3d_dist_f64(self._p(a), self._p(b), alpha0, alpha1, float(np.prod(dr)), nx, ny, nz,
+                                        z_lo, z_hi, self._p(out), G, tshift)
+        if rc:
+            raise RuntimeError(f"emu_corr3d_dist_f64 -> {rc}")
         return out
 
     def corr3d_pruned(self, a, b, dr, z_lo, z_hi, s_lo, s_len, alpha0=1.0, alpha1=1.0, tshift=-1):

@@ -28,10 +28,12 @@ static int pick_tshift(int n, long long inner)
 }
 
 struct EmuGather { int src_nz, dst_nz, z0[2], valid[2]; };
+struct EmuMap { const int *in_map, *out_map; long long in_ostride, out_ostride; };
 
 template <int D>
 static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, int narrays, double a0, double a1,
-                    int use_pow, int n, long long inner, long long outer, int force_tshift, const EmuGather *g = nullptr)
+                    int use_pow, int n, long long inner, long long outer, int force_tshift, const EmuGather *g = nullptr,
+                    const EmuMap *mp = nullptr)
 {
     HostPlan hp;
     if (!dbspm_make_plan(n, hp)) return -2;
@@ -39,6 +41,15 @@ static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, in
     P.in[0] = in0; P.in[1] = in1; P.out[0] = out0; P.out[1] = out1;
     P.alpha[0] = a0; P.alpha[1] = a1; P.use_pow = use_pow; P.narrays = narrays;
     P.gather = 0;
+    P.in_map = P.out_map = nullptr;
+    P.in_ostride = P.out_ostride = (long long)n * inner;
+    if (mp) {   // as launch_axis(): row-mapped passes exist in the register-staged body only
+        if (!axis_v2_ok(hp.dev)) return -2;
+        if (force_tshift >= 100) force_tshift = -1;
+        P.in_map = mp->in_map; P.out_map = mp->out_map;
+        if (mp->in_ostride) P.in_ostride = mp->in_ostride;
+        if (mp->out_ostride) P.out_ostride = mp->out_ostride;
+    }
     if (g) {   // as launch_axis(): the remapped first pass exists in the register-staged body only
         if (!axis_v2_ok(hp.dev)) return -2;
         if (force_tshift >= 100) force_tshift = -1;
@@ -84,7 +95,8 @@ static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, in
     unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
     for (int w = 0; w < narrays; ++w)
         for (long long b = 0; b < outer * P.tiles; ++b) {
-            if (P.v2) axis_pass_body_v2<D>(P, sm, b, w, 0, 1);
+            if (P.v2 && mp) axis_pass_body_v2<D, 1>(P, sm, b, w, 0, 1);
+            else if (P.v2) axis_pass_body_v2<D>(P, sm, b, w, 0, 1);
             else axis_pass_body<D>(P, sm, b, w, 0, 1);
         }
     return 0;
@@ -137,6 +149,7 @@ static int emu_corr3d_core(const double *A, const double *B, double alphaA, doub
         P.scale = dV / ((double)nx * (double)ny * (double)nz) * 0.25;
         P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data(); P.freq_of = hp.freq_of.data(); P.twN = hpN.tw.data();
         P.npairs = (long long)(nx / 2 + 1) * ny;
+        P.slot_mode = 0; P.slot_base = 0;
         // same selection as dbspm_corr3d_f64: v2 (4 pairs / block) when the plan is all fast radices
         const bool v2 = axis_v2_ok(P.plan) && (force_tshift < 100 || force_tshift >= 200);
         std::vector<unsigned char> smem((v2 ? zfused2_smem_bytes<4>(n) : zfused_smem_bytes(n)) + 64);
@@ -172,6 +185,60 @@ extern "C" int emu_corr3d_pruned_f64(const double *A, const double *B, double al
     g.src_nz = nz; g.dst_nz = G.Mp; g.z0[0] = G.zA0; g.z0[1] = G.zB0; g.valid[0] = G.validA; g.valid[1] = G.validB;
     const int rc = emu_corr3d_core(A, B, alphaA, alphaB, dV, nx, ny, G.Mp, G.w_lo, G.w_lo + (z_hi - z_lo), E_win, force_tshift, &g);
     return rc ? rc : G.Mp;
+}
+
+// what parallel.corr3d_distributed does with G ranks, run serially: dbspm_corr3d_dist_fwd_f64 per rank, the
+// all-to-all as plain block copies, dbspm_corr3d_dist_mid_f64 per rank, the gather, dbspm_corr3d_dist_fin_f64
+extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                                   int nx, int ny, int nz, int z_lo, int z_hi, double *E_win, int G, int force_tshift)
+{
+    if (!dist_shape_ok(nx, ny, nz, G)) return -3;
+    const int n = nz / 2, nxl = nx / G, nyl = ny / G, nzw = z_hi - z_lo, nwh = (nzw + 1) / 2;
+    const size_t blk = (size_t)nxl * nyl * n;                     // one (source, destination) block of the exchange
+    std::vector<std::vector<cplx>> sendA(G), sendB(G), recvA(G), recvB(G);
+    std::vector<int> omap(ny), imap(ny);
+    for (int K = 0; K < ny; ++K) { omap[K] = dist_row_of(K, ny, G, (long long)nxl * nyl); imap[K] = dist_row_of(K, ny, G, (long long)nx * nyl); }
+    int rc;
+    for (int g = 0; g < G; ++g) {
+        sendA[g].assign(blk * G, cmake(0, 0)); sendB[g].assign(blk * G, cmake(0, 0));
+        const cplx *As = (const cplx *)A + (size_t)g * nxl * ny * n, *Bs = (const cplx *)B + (size_t)g * nxl * ny * n;
+        EmuMap mp = {nullptr, omap.data(), 0, (long long)nyl * n};
+        if ((rc = run_axis<-1>(As, sendA[g].data(), Bs, sendB[g].data(), 2, alphaA, alphaB, 1, ny, n, nxl, force_tshift, nullptr, &mp))) return rc;
+    }
+    for (int h = 0; h < G; ++h) {                                  // all-to-all: block h of rank g -> block g of rank h
+        recvA[h].resize(blk * G); recvB[h].resize(blk * G);
+        for (int g = 0; g < G; ++g) {
+            memcpy(recvA[h].data() + blk * g, sendA[g].data() + blk * h, blk * sizeof(cplx));
+            memcpy(recvB[h].data() + blk * g, sendB[g].data() + blk * h, blk * sizeof(cplx));
+        }
+    }
+    std::vector<cplx> Wall((size_t)G * nx * nyl * nwh);
+    HostPlan hp, hpN;
+    if (!dbspm_make_plan(n, hp) || !dbspm_make_plan(nz, hpN)) return -2;
+    for (int h = 0; h < G; ++h) {
+        cplx *WA = recvA[h].data(), *WB = recvB[h].data(), *W = Wall.data() + (size_t)h * nx * nyl * nwh;
+        if ((rc = run_axis<-1>(WA, WA, WB, WB, 2, 1.0, 1.0, 0, nx, (long long)nyl * n, 1, force_tshift))) return rc;
+        ZFusedParams P;
+        P.ZA = WA; P.ZB = WB; P.W = W;
+        P.nx = nx; P.ny = nyl; P.n = n; P.nwh = nwh; P.z_lo = z_lo;
+        P.scale = dV / ((double)nx * (double)ny * (double)nz) * 0.25;
+        P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data(); P.freq_of = hp.freq_of.data(); P.twN = hpN.tw.data();
+        P.npairs = (long long)(nx / 2 + 1) * nyl;
+        P.slot_mode = 1; P.slot_base = h * nyl;
+        const bool v2 = axis_v2_ok(P.plan) && (force_tshift < 100 || force_tshift >= 200);
+        std::vector<unsigned char> smem((v2 ? zfused2_smem_bytes<4>(n) : zfused_smem_bytes(n)) + 64);
+        unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
+        if (v2) for (long long b = 0; b < 3; ++b) zfused_body_v2<4>(P, sm, b, 3, 0, 1);
+        else for (long long b = 0; b < (P.npairs + ZL - 1) / ZL; ++b) zfused_body(P, sm, b, 0, 1);
+        if ((rc = run_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)nyl * nwh, 1, force_tshift))) return rc;
+    }
+    std::vector<cplx> Wodd;
+    cplx *Wf = (cplx *)E_win;
+    if (nzw & 1) { Wodd.resize((size_t)nx * ny * nwh); Wf = Wodd.data(); }
+    EmuMap mp = {imap.data(), nullptr, (long long)nyl * nwh, 0};
+    if ((rc = run_axis<1>(Wall.data(), Wf, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, force_tshift, nullptr, &mp))) return rc;
+    if (nzw & 1) compact_body((const double *)Wf, E_win, (long long)nx * ny, nzw, 2 * nwh, 0, 1);
+    return 0;
 }
 
 // plain 1-D FFT of T interleaved lines through the tile routine (plan / butterfly unit test)

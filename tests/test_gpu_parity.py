@@ -59,6 +59,60 @@ def test_overlap_edge_shapes(ops, shape, window):
     assert _rel(got, ref) <= 1e-9
 
 
+def _dist_on_one_gpu(ops, a, b, dr, z_lo, z_hi, G, alpha=1.0):
+    """The distributed sr/es step with its G ranks run one after the other on this GPU: the three kernels stages
+    per rank, the all-to-all and the gather as block copies (what parallel.sr_es_distributed does over NCCL)."""
+    dev = torch.device("cuda", 0)
+    A, B = torch.as_tensor(a, device=dev), torch.as_tensor(b, device=dev)
+    nx, ny, nz = A.shape
+    nxl = nx // G
+    sends = [ops.dist_forward(A[g * nxl:(g + 1) * nxl], B[g * nxl:(g + 1) * nxl], G, alpha, alpha) for g in range(G)]
+    Ws = []
+    for h in range(G):
+        recvA = torch.stack([sends[g][0][h] for g in range(G)]).contiguous()
+        recvB = torch.stack([sends[g][1][h] for g in range(G)]).contiguous()
+        Ws.append(ops.dist_middle(recvA, recvB, dr, (nx, ny, nz), G, h, z_lo, z_hi))
+    return ops.dist_finish(torch.stack(Ws).contiguous(), (nx, ny, nz), G, z_lo, z_hi).cpu().numpy()
+
+
+@pytest.mark.parametrize("shape,window,G", [
+    ((4, 4, 4), (0, 4), 1), ((6, 8, 8), (3, 7), 2), ((8, 16, 12), (2, 9), 4), ((12, 24, 10), (0, 5), 3),
+    ((16, 16, 6), (5, 6), 8), ((10, 20, 28), (7, 21), 5), ((64, 96, 40), (11, 30), 4), ((128, 128, 64), (20, 47), 8),
+    ((256, 384, 32), (4, 20), 2),
+])
+def test_overlap_distributed_x_slabs(ops, shape, window, G):
+    assert ops.dist_supported(shape, G)
+    rng = np.random.default_rng(sum(shape) + G)
+    a, b = rng.random(shape), rng.random(shape) + 0.05
+    dr = np.array([0.1, 0.2, 0.3])
+    ref = O.density_overlap_fft(a ** 1.08, b ** 1.08, dr)[:, :, window[0]:window[1]]
+    got = _dist_on_one_gpu(ops, a, b, dr, window[0], window[1], G, alpha=1.08)
+    assert _rel(got, ref) <= 1e-9, (shape, window, G, _rel(got, ref))
+    one = ops.density_overlap_window(a, b, dr, window[0], window[1], 1.08, 1.08)
+    assert _rel(got, one) <= 1e-12
+
+
+def test_overlap_distributed_goldens_and_unsupported(ops, overlap_golden, manifest):
+    g = overlap_golden
+    for case in manifest["overlap"]:
+        i, alpha = case["idx"], case["alpha"]
+        a, b, dr, ref = g[f"a{i}"], g[f"b{i}"], g[f"dr{i}"], g[f"E{i}"]
+        nx, ny, nz = a.shape
+        for G in (1, 2):
+            if not ops.dist_supported(a.shape, G):
+                continue
+            got = _dist_on_one_gpu(ops, a, b, dr, 1, nz, G, alpha=alpha)
+            assert np.abs(got - ref[:, :, 1:nz]).max() <= 1e-9 * np.abs(ref).max(), (case, G)
+    assert not ops.dist_supported((8, 8, 9), 2)        # odd nz
+    assert not ops.dist_supported((8, 6, 8), 2)        # ny % (2G) != 0
+    assert not ops.dist_supported((9, 8, 8), 2)        # nx % G != 0
+    assert not ops.dist_supported((8, 44, 8), 2)       # prime factor 11: the row-mapped pass has fast radices only
+    from dbspm_b200 import _lib
+    x = torch.zeros((4, 6, 8), dtype=torch.float64, device="cuda")
+    with pytest.raises(_lib.DbspmError):
+        ops.dist_forward(x, x, 2)
+
+
 @pytest.mark.parametrize("flags", [0, 1 << 1, 1 << 2, 1 << 3])
 def test_overlap_kernel_variants_agree(ops, overlap_golden, manifest, flags):
     """default (register-first/last) axis pass, all-in-shared-memory variant (1<<1) and the TMA-fed

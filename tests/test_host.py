@@ -207,6 +207,47 @@ if rank == 0:
     assert [float(g["tip_x"][1, 2]) for g in got] == [10.0, 11.0, 12.0, 13.0, 14.0]
 else:
     assert got is None
+# distributed transform: one interaction over both ranks (x-slabs, all-to-all in slot order, gather, final y pass)
+class NumpyStages:
+    # the three compute stages of dbspm_b200.interactions.dist_* restated with numpy on unpacked complex arrays
+    @staticmethod
+    def dist_forward(a, b, G, alpha0, alpha1):
+        out = []
+        for arr, al in ((a, alpha0), (b, alpha1)):
+            f = np.fft.fft(arr.numpy() ** al, axis=1)[:, parallel.slot_order(arr.shape[1]), :]
+            nxl, ny, nz = f.shape
+            blk = np.ascontiguousarray(f.reshape(nxl, G, ny // G, nz).transpose(1, 0, 2, 3))
+            out.append(torch.from_numpy(blk.view(np.float64)))
+        return tuple(out)
+    @staticmethod
+    def dist_middle(ra, rb, dr, shape, G, h, z_lo, z_hi):
+        nx, ny, nz = shape
+        A = ra.numpy().view(np.complex128).reshape(nx, ny // G, nz)
+        B = rb.numpy().view(np.complex128).reshape(nx, ny // G, nz)
+        S = np.fft.fft(np.fft.fft(A, axis=0), axis=2) * np.conj(np.fft.fft(np.fft.fft(B, axis=0), axis=2)) * np.prod(dr)
+        w = np.fft.ifft(np.fft.ifft(S, axis=2)[:, :, z_lo:z_hi], axis=0)
+        return torch.from_numpy(np.ascontiguousarray(w).view(np.float64))
+    @staticmethod
+    def dist_finish(W_all, shape, G, z_lo, z_hi):
+        nx, ny, nz = shape
+        w = W_all.numpy().view(np.complex128)                              # (G, nx, ny/G, nzw)
+        slots = w.transpose(1, 0, 2, 3).reshape(nx, ny, z_hi - z_lo)
+        nat = np.empty_like(slots)
+        nat[:, parallel.slot_order(ny), :] = slots
+        return torch.from_numpy(np.fft.ifft(nat, axis=1).real.copy())
+shape = (6, 8, 10)
+A = rng.random(shape); B = rng.random(shape) + 0.1
+drr = np.array([0.1, 0.2, 0.3])
+x0, x1 = parallel.x_slab(shape[0], 2, rank)
+wins = parallel.sr_es_distributed(NumpyStages, torch.from_numpy(A[x0:x1].copy()), torch.from_numpy(B[x0:x1].copy()), 1.08,
+                                  shape, drr, 2, 9, [[0, 1]])
+if rank == 0:
+    ref = (np.fft.ifftn(np.fft.fftn(A ** 1.08) * np.conj(np.fft.fftn(B ** 1.08))).real * np.prod(drr))[:, :, 2:9]
+    assert np.abs(wins[0].numpy() - ref).max() <= 1e-12 * np.abs(ref).max(), "distributed transform"
+else:
+    assert wins is None
+assert parallel.dist_groups(8) == [[0, 1, 2, 3], [4, 5, 6, 7]] and parallel.dist_groups(2) is None
+assert parallel.dist_groups(6) == [[0, 1, 2], [3, 4, 5]] and parallel.dist_groups(5) is None
 t = torch.arange(3.0) if rank == 0 else torch.zeros(3)
 parallel.broadcast_(t)
 assert torch.equal(t, torch.arange(3.0))
