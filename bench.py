@@ -243,6 +243,16 @@ def run_gpu_arm(args):
     # (each half splits the window's planes); with N = 1 the single rank runs both
     plan = parallel.interaction_plan(world, z_lo, z_hi)
     jobs = plan[rank]
+    # N >= 4: the transform itself is distributed inside each group (x-slabs, one all-to-all, gather of the packed
+    # window rows); N = 2 has one rank per interaction and N = 1 runs both, so they keep the single-GPU five-pass path
+    groups = None if args.no_dist else parallel.dist_groups(world)
+    if groups is not None and not ops.dist_supported(cfg.shape, len(groups[0])):
+        groups = None
+    if groups is not None:
+        G = len(groups[0])
+        my_which, my_h = rank // G, rank % G
+        sx0, sx1 = parallel.x_slab(nx, G, my_h)
+    dist_marks = []
     tiles = parallel.split_range(0, nx, world)
     my_il, my_ih = tiles[rank]
     inputs = {0: (rhoS, rhoT, cfg.alpha), 1: (potS, nrhoT, 1.0)}
@@ -255,6 +265,16 @@ def run_gpu_arm(args):
         return e
 
     def corr_phase(src, marks=None, supports=None):
+        if groups is not None and supports is None:
+            a, b, al = src[my_which]
+            rec = [("start", ev())] if marks is not None else None
+            wins = parallel.sr_es_distributed(ops, a[sx0:sx1], b[sx0:sx1], al, cfg.shape, dr, z_lo, z_hi, groups,
+                                              on_stage=(lambda name: rec.append((name, ev()))) if rec is not None else None)
+            launches["n"] += 4 + (2 if rank == 0 else 0)          # y fwd | x fwd, z, x inv | y inv of both windows
+            if marks is not None:
+                marks.append(ev())
+                dist_marks.append(rec)
+            return wins
         for (which, zl, zh), buf in zip(jobs, bufs):
             a, b, al = src[which]
             if zh > zl:
@@ -302,6 +322,7 @@ def run_gpu_arm(args):
         step(None)
     barrier()
     launches["n"] = 0
+    dist_marks.clear()
     marks = []
     with ClockSampler(dev.index) as clk:
         barrier()
@@ -383,26 +404,42 @@ def run_gpu_arm(args):
     # ---- end to end: pinned host inputs in, results out, inside the timed region -----------
     e2e = None
     if not args.no_e2e:
-        need = {"vdw"} | {n for (w, _, _) in jobs for n in (("rhoS", "rhoT") if w == 0 else ("potS", "nrhoT"))}
+        names = {0: ("rhoS", "rhoT", cfg.alpha), 1: ("potS", "nrhoT", 1.0)}
         dev_src = {"rhoS": rhoS, "potS": potS, "rhoT": rhoT, "nrhoT": nrhoT, "vdw": vdw}
-        hosts = {k: torch.empty(dev_src[k].shape, dtype=torch.float64).pin_memory().copy_(dev_src[k]) for k in sorted(need)}
-        outs_h = [torch.empty(tuple(b.shape), dtype=torch.float64).pin_memory() for b in bufs]
+        if groups is not None:
+            # distributed transform: a rank uploads only its x-slab of its interaction's two arrays
+            need = set(names[my_which][:2])
+            hosts = {k: torch.empty(dev_src[k][sx0:sx1].shape, dtype=torch.float64).pin_memory().copy_(dev_src[k][sx0:sx1])
+                     for k in sorted(need)}
+            hosts["vdw"] = torch.empty(vdw.shape, dtype=torch.float64).pin_memory().copy_(vdw)
+            outs_h = [torch.empty((nx, ny, nzw), dtype=torch.float64).pin_memory() for _ in range(2)] if rank == 0 else []
+        else:
+            need = {"vdw"} | {n for (w, _, _) in jobs for n in names[w][:2]}
+            hosts = {k: torch.empty(dev_src[k].shape, dtype=torch.float64).pin_memory().copy_(dev_src[k]) for k in sorted(need)}
+            outs_h = [torch.empty(tuple(b.shape), dtype=torch.float64).pin_memory() for b in bufs]
         ni = my_ih - my_il
         out_rel = torch.empty((4, ni, ny, nz_relax), dtype=torch.float64).pin_memory()
         d_in = {k: torch.empty_like(v, device=dev) for k, v in hosts.items()}
         del rhoS, potS, rhoT, nrhoT, dev_src, inputs
         torch.cuda.empty_cache()
-        names = {0: ("rhoS", "rhoT", cfg.alpha), 1: ("potS", "nrhoT", 1.0)}
 
         def e2e_step(rec):
             e0 = ev()
-            for (which, zl, zh), buf, oh in zip(jobs, bufs, outs_h):
-                na, nb, al = names[which]
+            if groups is not None:
+                na, nb, al = names[my_which]
                 d_in[na].copy_(hosts[na], non_blocking=True)
                 d_in[nb].copy_(hosts[nb], non_blocking=True)
-                if zh > zl:
-                    ops.density_overlap_window(d_in[na], d_in[nb], dr, zl, zh, al, al, out=buf)
-                oh.copy_(buf, non_blocking=True)
+                wins = parallel.sr_es_distributed(ops, d_in[na], d_in[nb], al, cfg.shape, dr, z_lo, z_hi, groups)
+                for w, oh in zip(wins or [], outs_h):
+                    oh.copy_(w, non_blocking=True)
+            else:
+                for (which, zl, zh), buf, oh in zip(jobs, bufs, outs_h):
+                    na, nb, al = names[which]
+                    d_in[na].copy_(hosts[na], non_blocking=True)
+                    d_in[nb].copy_(hosts[nb], non_blocking=True)
+                    if zh > zl:
+                        ops.density_overlap_window(d_in[na], d_in[nb], dr, zl, zh, al, al, out=buf)
+                    oh.copy_(buf, non_blocking=True)
             e1 = ev()
             d_in["vdw"].copy_(hosts["vdw"], non_blocking=True)
             if world == 1:
@@ -424,19 +461,34 @@ def run_gpu_arm(args):
             e2e_step(rec)
         barrier()
         tc, tr = max_over_ranks([float(np.mean([x[0] for x in rec])), float(np.mean([x[1] for x in rec]))])
-        h2d = 8 * (2 * len(jobs) * N + Nw)
-        d2h = 8 * (sum(int(b.numel()) for b in bufs) + 4 * ni * ny * nz_relax)
+        if groups is not None:
+            h2d = 8 * (2 * N // G + Nw)
+            d2h = 8 * (sum(int(o.numel()) for o in outs_h) + 4 * ni * ny * nz_relax)
+        else:
+            h2d = 8 * (2 * len(jobs) * N + Nw)
+            d2h = 8 * (sum(int(b.numel()) for b in bufs) + 4 * ni * ny * nz_relax)
         e2e = {"value": 2 * N / (tc * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_sr_es": tc, "relax_value": nx * ny * nz_relax / (tr * 1e-3), "relax_unit": "tip positions/s",
-               "ms_relax": tr, "note": "per rank: pinned host -> HBM copies of the input grids of its interaction(s) "
-                                       "+ vdw, its window slab(s) and relax tile copied back, all inside the timed "
-                                       "region; byte counts are per rank"}
+               "ms_relax": tr, "note": ("per rank: pinned host -> HBM copies of its x-slab of its interaction's two input "
+                                        "grids + vdw; rank 0 copies both windows back, every rank its relax tile; all "
+                                        "inside the timed region; byte counts are rank 0's" if groups is not None else
+                                        "per rank: pinned host -> HBM copies of the input grids of its interaction(s) "
+                                        "+ vdw, its window slab(s) and relax tile copied back, all inside the timed "
+                                        "region; byte counts are per rank")}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
+    dist_stages = None
+    if dist_marks:
+        acc = {}
+        for rec_ in dist_marks:
+            for (n0, e_a), (n1, e_b) in zip(rec_[:-1], rec_[1:]):
+                acc.setdefault(n1, []).append(e_a.elapsed_time(e_b))
+        dist_stages = {k: float(np.median(v)) for k, v in acc.items()}
+        print("dist stage times per step (ms):", {k: [round(x, 3) for x in v] for k, v in acc.items()}, file=sys.stderr)
     peak, peak_src = measured_peak()
     balg = 8 * (2 * N + Nw)                       # per interaction
     t_corr = t_sr + t_es
@@ -445,7 +497,9 @@ def run_gpu_arm(args):
             "traffic": (2 * profiled_traffic(args.workload) if world == 1 and profiled_traffic(args.workload) else None),
             "traffic_note": "dram bytes read+write of sr+es (2 x 5 launches), ncu --set full, profiles/traffic.json",
             "peak_source": peak_src,
-            "kernel": "dbspm_corr3d_f64 = 5 launches (axis_pass x_fwd, y_fwd, zfused, axis_pass y_inv, x_inv)",
+            "kernel": ("dbspm_corr3d_dist_{fwd,mid,fin}_f64 = 5 launches per rank (axis_pass y_fwd | x_fwd, zfused, x_inv | "
+                       "y_inv on rank 0) + all-to-all + gather" if groups is not None else
+                       "dbspm_corr3d_f64 = 5 launches (axis_pass x_fwd, y_fwd, zfused, axis_pass y_inv, x_inv)"),
             "algorithmic_bytes_per_interaction": balg, "ms_sr_plus_es": t_corr,
             "ms_sr": t_sr if world == 1 else None, "ms_es": t_es if world == 1 else None,
             "note": "frac = algorithmic bytes of sr+es / (time * n_gpus * peak)"
@@ -464,8 +518,12 @@ def run_gpu_arm(args):
                    "window_z": [z_lo, z_hi], "relax_shape": [nx, ny, nz_relax], "alpha": cfg.alpha, "V": cfg.V,
                    "kappa": cfg.kappa, "rpivot": cfg.rpivot, "tip": "noisy (non-compact, full-z path)",
                    "l2": "inputs are %.2f GB each, far larger than the 126 MB L2 (no flush needed)" % (8 * N / 1e9),
-                   "parallelism": (f"sr | es on disjoint rank groups, z-slab within a group ({world} ranks), "
-                                   f"x-tile x{world} (relax), gather to rank 0") if world > 1 else "single GPU"},
+                   "parallelism": ((f"sr | es on disjoint groups of {G} ranks; inside a group the transform is distributed "
+                                    f"over x-slabs (y pass, all-to-all of 16N/{G} B per rank, x pass + z kernel + inverse x, "
+                                    f"gather of the packed window rows to rank 0, inverse y there); x-tile x{world} (relax)")
+                                   if groups is not None else
+                                   (f"sr | es on disjoint rank groups, z-slab within a group ({world} ranks), "
+                                    f"x-tile x{world} (relax), gather to rank 0") if world > 1 else "single GPU")},
         "relax": {"value": nx * ny * nz_relax / (relax_ms_max * 1e-3), "unit": "tip positions/s",
                   "ms": relax_ms_max, "mean_nfev": nfev_mean, "in_step_ms_static_relax_gather": t_rest,
                   # the kernel is bound by L1 wavefronts, not HBM (compulsory HBM bytes are ~50 B/position):
@@ -474,7 +532,7 @@ def run_gpu_arm(args):
                   "stencil_gbs": nx * ny * nz_relax * nfev_mean * 512 / (relax_ms_max * 1e-3) / 1e9,
                   "l1_nominal_gbs": world * 148 * 128 * 1.965,
                   "hbm_bytes_per_position": 8.0 * nzw / nz_relax + 56.0},
-        "stages_ms": stages, "compact_tip": compact, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+        "stages_ms": stages, "dist_stages_ms": dist_stages, "compact_tip": compact, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": n_launch, "clocks": clk.summary(), "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line), flush=True)
@@ -492,6 +550,7 @@ def main():
     ap.add_argument("--workload", default="large_slab", choices=sorted(WORKLOAD_DESC))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dist", action="store_true", help="N >= 4: replicated inputs + z-slab split instead of the distributed transform")
     ap.add_argument("--no-compact", action="store_true", help="skip the compact-tip (z-pruned path) measurement")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -171,7 +171,7 @@ def x_slab(nx: int, G: int, h: int):
     return h * (nx // G), (h + 1) * (nx // G)
 
 
-def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, groups, dst: int = 0, marks=None):
+def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, groups, dst: int = 0, on_stage=None):
     """The distributed sr / es step (replaces the rank-0-only dbspm:320-352).
 
     groups[i] = the G ranks that compute interaction i; this rank, member h of its group, passes the x-slab
@@ -179,7 +179,9 @@ def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, grou
     (dbspm_b200.interactions: dist_forward / dist_middle / dist_finish; the CPU tests inject numpy ones).
     Data-path collectives: one all-to-all per array inside the group (the transpose every distributed FFT needs:
     16N/G bytes per rank) and one gather of the packed window rows to rank `dst`, which runs the final inverse
-    y pass of every interaction.  Returns the list of (nx,ny,nzw) windows on `dst`, None elsewhere."""
+    y pass of every interaction.  Returns the list of (nx,ny,nzw) windows on `dst`, None elsewhere.
+    on_stage(name) is called after each stage has been enqueued (bench.py records a CUDA event there)."""
+    mark = on_stage or (lambda name: None)
     rank, world = _world()
     G = len(groups[0])
     which = next(i for i, g in enumerate(groups) if rank in g)
@@ -187,23 +189,23 @@ def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, grou
     pg = _process_groups(groups)[which]
     sendA, sendB = stages.dist_forward(a_slab, b_slab, G, alpha, alpha)
     recvA, recvB = torch.empty_like(sendA), torch.empty_like(sendB)
-    if marks is not None:
-        marks.append("fwd")
+    mark("fwd")
     dist.all_to_all_single(recvA, sendA, group=pg)
     dist.all_to_all_single(recvB, sendB, group=pg)
-    if marks is not None:
-        marks.append("a2a")
+    mark("a2a")
     # (G, nxl, ny/G, nz) received = (nx, ny/G, nz): source ranks are consecutive x-slabs
     W = stages.dist_middle(recvA, recvB, dr, shape, G, h, z_lo, z_hi)
-    if marks is not None:
-        marks.append("mid")
+    mark("mid")
     big = None
     if rank == dst:
         big = torch.empty((world,) + tuple(W.shape), dtype=W.dtype, device=W.device)
     dist.gather(W.contiguous(), list(big.unbind(0)) if rank == dst else None, dst=dst)
+    mark("gather")
     if rank != dst:
         return None
-    return [stages.dist_finish(big[g[0]:g[0] + G], shape, G, z_lo, z_hi) for g in groups]
+    wins = [stages.dist_finish(big[g[0]:g[0] + G], shape, G, z_lo, z_hi) for g in groups]
+    mark("fin")
+    return wins
 
 
 def relax_sharded(compute_tile, nx, device):
