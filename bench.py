@@ -269,7 +269,8 @@ def run_gpu_arm(args):
             a, b, al = src[my_which]
             rec = [("start", ev())] if marks is not None else None
             wins = parallel.sr_es_distributed(ops, a[sx0:sx1], b[sx0:sx1], al, cfg.shape, dr, z_lo, z_hi, groups,
-                                              on_stage=(lambda name: rec.append((name, ev()))) if rec is not None else None)
+                                              on_stage=(lambda name: rec.append((name, ev()))) if rec is not None else None,
+                                              peer=not args.no_peer)
             launches["n"] += 4 + (2 if rank == 0 else 0)          # y fwd | x fwd, z, x inv | y inv of both windows
             if marks is not None:
                 marks.append(ev())
@@ -321,6 +322,16 @@ def run_gpu_arm(args):
     for _ in range(args.warmup):
         step(None)
     barrier()
+    # distributed transform: rank 0 checks the assembled es window against the single-GPU five-pass path once
+    dist_check = None
+    if groups is not None:
+        wins = corr_phase(inputs, None)
+        if rank == 0:
+            one = ops.density_overlap_window(potS, nrhoT, dr, z_lo, z_hi)
+            dist_check = float((wins[1] - one).abs().max() / one.abs().max())
+            del one
+        del wins
+        barrier()
     launches["n"] = 0
     dist_marks.clear()
     marks = []
@@ -429,7 +440,8 @@ def run_gpu_arm(args):
                 na, nb, al = names[my_which]
                 d_in[na].copy_(hosts[na], non_blocking=True)
                 d_in[nb].copy_(hosts[nb], non_blocking=True)
-                wins = parallel.sr_es_distributed(ops, d_in[na], d_in[nb], al, cfg.shape, dr, z_lo, z_hi, groups)
+                wins = parallel.sr_es_distributed(ops, d_in[na], d_in[nb], al, cfg.shape, dr, z_lo, z_hi, groups,
+                                                  peer=not args.no_peer)
                 for w, oh in zip(wins or [], outs_h):
                     oh.copy_(w, non_blocking=True)
             else:
@@ -519,8 +531,10 @@ def run_gpu_arm(args):
                    "kappa": cfg.kappa, "rpivot": cfg.rpivot, "tip": "noisy (non-compact, full-z path)",
                    "l2": "inputs are %.2f GB each, far larger than the 126 MB L2 (no flush needed)" % (8 * N / 1e9),
                    "parallelism": ((f"sr | es on disjoint groups of {G} ranks; inside a group the transform is distributed "
-                                    f"over x-slabs (y pass, all-to-all of 16N/{G} B per rank, x pass + z kernel + inverse x, "
-                                    f"gather of the packed window rows to rank 0, inverse y there); x-tile x{world} (relax)")
+                                    f"over x-slabs (y pass " + ("+ all-to-all through NCCL" if args.no_peer else
+                                    "whose stores go straight into the owners' buffers over NVLink (symmetric memory)")
+                                    + f", x pass + z kernel + inverse x, gather of the packed window rows to rank 0, "
+                                    f"inverse y there); x-tile x{world} (relax)")
                                    if groups is not None else
                                    (f"sr | es on disjoint rank groups, z-slab within a group ({world} ranks), "
                                     f"x-tile x{world} (relax), gather to rank 0") if world > 1 else "single GPU")},
@@ -532,7 +546,7 @@ def run_gpu_arm(args):
                   "stencil_gbs": nx * ny * nz_relax * nfev_mean * 512 / (relax_ms_max * 1e-3) / 1e9,
                   "l1_nominal_gbs": world * 148 * 128 * 1.965,
                   "hbm_bytes_per_position": 8.0 * nzw / nz_relax + 56.0},
-        "stages_ms": stages, "dist_stages_ms": dist_stages, "compact_tip": compact, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+        "stages_ms": stages, "dist_stages_ms": dist_stages, "dist_check_rel_err_es": dist_check, "compact_tip": compact, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": n_launch, "clocks": clk.summary(), "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line), flush=True)
@@ -550,6 +564,7 @@ def main():
     ap.add_argument("--workload", default="large_slab", choices=sorted(WORKLOAD_DESC))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="distributed transform: NCCL all-to-all instead of the fused peer-store exchange")
     ap.add_argument("--no-dist", action="store_true", help="N >= 4: replicated inputs + z-slab split instead of the distributed transform")
     ap.add_argument("--no-compact", action="store_true", help="skip the compact-tip (z-pruned path) measurement")
     args = ap.parse_args()

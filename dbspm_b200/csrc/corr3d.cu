@@ -49,6 +49,22 @@ __global__ void __launch_bounds__(AXIS2_THREADS, AXIS2_MIN_BLOCKS) axis_pass2m_k
     axis_pass_body_v2<D, 1>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
 }
 
+// fused-exchange variant: every output row is stored straight into its owner's receive buffer (peer memory, NVLink)
+template <int D>
+__global__ void __launch_bounds__(AXIS2_THREADS, AXIS2_MIN_BLOCKS) axis_pass2p_kernel(const __grid_constant__ AxisParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    axis_pass_body_v2<D, 2>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
+}
+
+// same with 8-line tiles (one CTA of 512 threads per SM): every remote store is a full 128-byte segment
+template <int D>
+__global__ void __launch_bounds__(512, 1) axis_pass2pw_kernel(const __grid_constant__ AxisParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    axis_pass_body_v2<D, 2>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
+}
+
 __global__ void __launch_bounds__(DBSPM_THREADS) zfused_kernel(const __grid_constant__ ZFusedParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -182,7 +198,7 @@ static int get_rowmap(int n, int G, long long blockrows, cudaStream_t st, const 
     if (it != g_rowmaps.end()) { *out = it->second; return DBSPM_OK; }
     DBSPM_REQUIRE((long long)G * blockrows < 2147483647LL, DBSPM_EUNSUPPORTED, "row table overflows 32 bits");
     std::vector<int> h((size_t)n);
-    for (int K = 0; K < n; ++K) h[K] = dist_row_of(K, n, G, blockrows);
+    for (int K = 0; K < n; ++K) h[K] = blockrows < 0 ? dist_peer_entry(K, n, G) : dist_row_of(K, n, G, blockrows);
     int *d = nullptr;
     DBSPM_CUDA_TRY(cudaMalloc((void **)&d, sizeof(int) * (size_t)n));
     DBSPM_CUDA_TRY(cudaMemcpyAsync(d, h.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -311,6 +327,9 @@ struct GatherSpec {
 struct AxisMap {
     const int *in_map, *out_map;
     long long in_ostride, out_ostride;      // elements between consecutive slabs (0 = n * inner)
+    int npeers;                             // > 0: fused exchange, out_map holds dist_peer_entry values
+    cplx *peer[2][DBSPM_MAX_PEERS];
+    long long out_base_off;
 };
 
 template <int D>
@@ -338,6 +357,12 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
         P.in_map = mp->in_map; P.out_map = mp->out_map;
         if (mp->in_ostride) P.in_ostride = mp->in_ostride;
         if (mp->out_ostride) P.out_ostride = mp->out_ostride;
+        P.out_base_off = 0;
+        if (mp->npeers > 0) {
+            for (int w = 0; w < 2; ++w)
+                for (int q = 0; q < DBSPM_MAX_PEERS; ++q) P.out_peer[w][q] = q < mp->npeers ? mp->peer[w][q] : nullptr;
+            P.out_base_off = mp->out_base_off;
+        }
     }
     if (g) {
         // only the register-staged body can remap its loads
@@ -375,6 +400,14 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
             smem = axis2_smem_bytes(n, 3, P.plan.nstages, 0);
         }
 #endif
+        // fused exchange: NVLink moves 128-byte segments much better than 64-byte ones, so the peer-store pass takes
+        // 8-line tiles whenever they fit (measured in profiles/README.md)
+        if (P.v2 && mp && mp->npeers > 0 && !(flags & DBSPM_CORR_PEER_NARROW) && P.tshift < 3 && inner >= 8 && P.plan.nstages > 1 &&
+            axis2_smem_bytes(n, 3, P.plan.nstages, 0) <= 200 * 1024) {
+            wide = true;
+            P.tshift = 3; P.tw_smem = 0;
+            smem = axis2_smem_bytes(n, 3, P.plan.nstages, 0);
+        }
     }
     DBSPM_REQUIRE(P.v2 || !mp, DBSPM_EUNSUPPORTED, "row-mapped pass: axis length %d does not fit in shared memory", n);
     if (!P.v2) {
@@ -385,7 +418,13 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     P.tiles = (inner + (1LL << P.tshift) - 1) >> P.tshift;
     const long long nblocks = outer * P.tiles;
     DBSPM_REQUIRE(nblocks > 0 && nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large (%lld blocks)", nblocks);
-    if (P.v2 && mp) {
+    if (P.v2 && mp && mp->npeers > 0 && wide) {
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2pw_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        axis_pass2pw_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), 512, smem, st>>>(P);
+    } else if (P.v2 && mp && mp->npeers > 0) {
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2p_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        axis_pass2p_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), AXIS2_THREADS, smem, st>>>(P);
+    } else if (P.v2 && mp) {
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2m_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         axis_pass2m_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), AXIS2_THREADS, smem, st>>>(P);
     } else if (P.v2 && wide) {
@@ -634,7 +673,35 @@ extern "C" int dbspm_corr3d_dist_fwd_f64(const double *A_slab, const double *B_s
     if (rc) return rc;
     AxisMap mp;
     mp.in_map = nullptr; mp.out_map = omap; mp.in_ostride = 0; mp.out_ostride = (long long)nyl * n;
+    mp.npeers = 0; mp.out_base_off = 0;
     return launch_axis<-1>((const cplx *)A_slab, (cplx *)sendA, (const cplx *)B_slab, (cplx *)sendB, 2, alphaA, alphaB, 1,
+                           ny, n, nxl, st, flags, nullptr, &mp);
+}
+
+// fused exchange: the y pass of rank `me` stores every row straight into its owner's receive buffer
+// peer_recv[h] = rank h's (2, nx, ny/G, nz/2) complex buffer (A then B), mapped into this process (symmetric memory)
+extern "C" int dbspm_corr3d_dist_fwd_peer_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
+                                              int nxl, int ny, int nz, int G, int me, void *const *peer_recv, int flags, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    DBSPM_REQUIRE(A_slab && B_slab && peer_recv, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(dist_shape_ok(nxl * G, ny, nz, G) && G <= DBSPM_MAX_PEERS && me >= 0 && me < G, DBSPM_EUNSUPPORTED,
+                  "fused exchange needs even nz, ny %% (2G) == 0, G <= %d (got slab %d x %d x %d, rank %d of %d)",
+                  DBSPM_MAX_PEERS, nxl, ny, nz, me, G);
+    const int n = nz / 2, nyl = ny / G, nx = nxl * G;
+    DBSPM_REQUIRE(nyl < (1 << DIST_PEER_SHIFT), DBSPM_EUNSUPPORTED, "ny/G too large for the peer table");
+    const int *omap = nullptr;
+    int rc = get_rowmap(ny, G, -1, st, &omap);
+    if (rc) return rc;
+    AxisMap mp;
+    mp.in_map = nullptr; mp.out_map = omap; mp.in_ostride = 0; mp.out_ostride = (long long)nyl * n;
+    mp.npeers = G; mp.out_base_off = (long long)me * nxl * nyl * n;
+    for (int h = 0; h < G; ++h) {
+        DBSPM_REQUIRE(peer_recv[h] && ((uintptr_t)peer_recv[h] & 15) == 0, DBSPM_EINVAL, "peer buffer %d null or misaligned", h);
+        mp.peer[0][h] = (cplx *)peer_recv[h];
+        mp.peer[1][h] = (cplx *)peer_recv[h] + (size_t)nx * nyl * n;
+    }
+    return launch_axis<-1>((const cplx *)A_slab, mp.peer[0][me], (const cplx *)B_slab, mp.peer[1][me], 2, alphaA, alphaB, 1,
                            ny, n, nxl, st, flags, nullptr, &mp);
 }
 
@@ -678,6 +745,7 @@ extern "C" int dbspm_corr3d_dist_fin_f64(const void *W_all, int nx, int ny, int 
     if (rc) return rc;
     AxisMap mp;
     mp.in_map = imap; mp.out_map = nullptr; mp.in_ostride = (long long)nyl * nwh; mp.out_ostride = 0;
+    mp.npeers = 0; mp.out_base_off = 0;
     rc = launch_axis<1>((const cplx *)W_all, W, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, st, flags, nullptr, &mp);
     if (rc) return rc;
     if (nzw & 1) {

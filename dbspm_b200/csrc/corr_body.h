@@ -26,6 +26,8 @@
 // memory as s[n][T]; global rows are T*16-byte contiguous segments (128 B for T = 8).
 // blockIdx.y selects one of two arrays (A and B travel in one launch).
 // ------------------------------------------------------------------------------------------
+#define DBSPM_MAX_PEERS 8
+#define DIST_PEER_SHIFT 20
 struct AxisParams {
     const cplx *in[2];
     cplx *out[2];
@@ -55,6 +57,10 @@ struct AxisParams {
     // elements; null maps = natural rows.  Without maps the strides are n * inner.
     const int *in_map, *out_map;
     long long in_ostride, out_ostride;
+    // MAP == 2 (fused exchange): out_map[K] = (h << DIST_PEER_SHIFT) | row, and the row is stored straight into rank h's
+    // receive buffer out_peer[which][h] (peer memory over NVLink) at element out_base_off + o * out_ostride + row * inner
+    cplx *out_peer[2][DBSPM_MAX_PEERS];
+    long long out_base_off;
 };
 
 // ---- distributed correlation: slot order of a transform axis --------------------------------------
@@ -76,6 +82,13 @@ HD int dist_row_of(int K, int n, int G, long long blockrows)
 {
     const int nl = n / G, S = dist_slot_of(K, n);
     return (int)((long long)(S / nl) * blockrows + (S % nl));
+}
+
+// fused-exchange table entry of frequency K: (owner rank << DIST_PEER_SHIFT) | row inside the owner's block
+HD int dist_peer_entry(int K, int n, int G)
+{
+    const int nl = n / G, S = dist_slot_of(K, n);
+    return ((S / nl) << DIST_PEER_SHIFT) | (S % nl);
 }
 
 HD bool dist_shape_ok(int nx, int ny, int nz, int G)
@@ -273,8 +286,15 @@ HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gi
         if (single) {
             if (t < tcount) {
 #pragma unroll
-                for (int k = 0; k < R; ++k)
-                    st_stream(gout + (size_t)((MAP && P.out_map) ? LDG(P.out_map + k) : k) * P.inner + t, v[k]);
+                for (int k = 0; k < R; ++k) {
+                    if (MAP == 2) {
+                        const int m = LDG(P.out_map + k);
+                        st_stream(P.out_peer[which][m >> DIST_PEER_SHIFT] + (gout - P.out[which]) +
+                                  (size_t)(m & ((1 << DIST_PEER_SHIFT) - 1)) * P.inner + t, v[k]);
+                    } else {
+                        st_stream(gout + (size_t)((MAP && P.out_map) ? LDG(P.out_map + k) : k) * P.inner + t, v[k]);
+                    }
+                }
             }
         } else {
 #pragma unroll
@@ -290,7 +310,7 @@ HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gi
 }
 
 template <int D, int R, int MAP>
-HD void axis2_last(const AxisParams &P, const cplx *s, cplx *gout, int tcount, int tid, int nthr)
+HD void axis2_last(const AxisParams &P, const cplx *s, cplx *gout, int tcount, int which, int tid, int nthr)
 {
     const int n = P.n, nb = n / R, tmask = (1 << P.tshift) - 1;
     const int total = nb << P.tshift;
@@ -303,7 +323,14 @@ HD void axis2_last(const AxisParams &P, const cplx *s, cplx *gout, int tcount, i
         bfly<R, D>(v);
         if (t < tcount) {
             const int K0 = LDG(P.freq_of + blk * R);           // frequency held by position blk*R
-            if (MAP && P.out_map) {
+            if (MAP == 2) {
+                const size_t goff = (size_t)(gout - P.out[which]) + t;
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int m = LDG(P.out_map + K0 + k * nb);
+                    st_stream(P.out_peer[which][m >> DIST_PEER_SHIFT] + goff + (size_t)(m & ((1 << DIST_PEER_SHIFT) - 1)) * P.inner, v[k]);
+                }
+            } else if (MAP && P.out_map) {
 #pragma unroll
                 for (int k = 0; k < R; ++k) st_stream(gout + (size_t)LDG(P.out_map + K0 + k * nb) * P.inner + t, v[k]);
             } else {
@@ -329,7 +356,7 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
     const long long i0 = tile << P.tshift;
     const int tcount = (int)((P.inner - i0) < T ? (P.inner - i0) : T);
     const cplx *gin = P.in[which] + (MAP ? (size_t)o * P.in_ostride : (size_t)o * n * P.inner) + i0;
-    cplx *gout = P.out[which] + (MAP ? (size_t)o * P.out_ostride : (size_t)o * n * P.inner) + i0;
+    cplx *gout = P.out[which] + (MAP == 2 ? (size_t)P.out_base_off : 0) + (MAP ? (size_t)o * P.out_ostride : (size_t)o * n * P.inner) + i0;
     const double alpha = P.alpha[which];
     const bool do_pow = P.use_pow && alpha != 1.0;
 
@@ -351,7 +378,7 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
         m /= r;
         BLOCK_SYNC();
     }
-#define CALL_(R) axis2_last<D, R, MAP>(P, s, gout, tcount, tid, nthr)
+#define CALL_(R) axis2_last<D, R, MAP>(P, s, gout, tcount, which, tid, nthr)
     DBSPM_FAST_RADIX_SWITCH(pl.radix[pl.nstages - 1], CALL_)
 #undef CALL_
 }

@@ -179,6 +179,19 @@ def dist_forward(a_slab, b_slab, G, alpha0=1.0, alpha1=1.0, out=None, flags=0):
     return out
 
 
+def dist_forward_peer(a_slab, b_slab, G, me, peer_ptrs, alpha0=1.0, alpha1=1.0, flags=0):
+    """dist_forward fused with the exchange: every output row is stored straight into its owner's receive buffer.
+    peer_ptrs[h] = device address (int) of rank h's (2, nx, ny/G, nz) float64 receive buffer mapped into this process
+    (torch symmetric memory).  The caller brackets the call with two group barriers."""
+    dev = a_slab.device
+    a, b = _to_dev(a_slab, dev), _to_dev(b_slab, dev)
+    nxl, ny, nz = (int(v) for v in a.shape)
+    ptrs = (C.c_void_p * int(G))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dbspm_corr3d_dist_fwd_peer_f64(a.data_ptr(), b.data_ptr(), float(alpha0), float(alpha1), nxl, ny, nz,
+                                                             int(G), int(me), ptrs, int(flags), _stream_ptr(dev)))
+
+
 def dist_middle(recvA, recvB, dr, shape, G, h, z_lo, z_hi, out=None, flags=0):
     """x transform (in place) of the received spectra (nx, ny/G, nz), fused z kernel, inverse x transform:
     returns this rank's rows of the packed window, (nx, ny/G, 2*ceil(nzw/2)) float64."""

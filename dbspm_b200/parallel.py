@@ -171,7 +171,31 @@ def x_slab(nx: int, G: int, h: int):
     return h * (nx // G), (h + 1) * (nx // G)
 
 
-def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, groups, dst: int = 0, on_stage=None):
+_SYMM: dict = {}
+
+
+def peer_receive_buffer(shape, G: int, pg, device):
+    """This rank's (2, nx, ny/G, nz) float64 receive buffer of the fused exchange, allocated in symmetric memory and
+    mapped into every process of the group (torch.distributed._symmetric_memory): returns (buffer, handle) or None
+    when symmetric memory is unavailable (CPU tests, no peer access) -- the callers then exchange through NCCL."""
+    if device.type != "cuda" or os.environ.get("DBSPM_NO_PEER"):
+        return None
+    key = (tuple(int(v) for v in shape), int(G), id(pg), device.index)
+    if key not in _SYMM:
+        try:
+            import torch.distributed._symmetric_memory as symm
+            nx, ny, nz = key[0]
+            buf = symm.empty((2, nx, ny // G, nz), dtype=torch.float64, device=device)
+            hdl = symm.rendezvous(buf, pg)
+            _SYMM[key] = (buf, hdl)
+        except Exception as exc:                                   # noqa: BLE001 -- any failure = no peer path
+            print(f"dbspm_b200: symmetric memory unavailable ({exc!r}); exchanging through NCCL", flush=True)
+            _SYMM[key] = None
+    return _SYMM[key]
+
+
+def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, groups, dst: int = 0, on_stage=None,
+                      peer: bool = True):
     """The distributed sr / es step (replaces the rank-0-only dbspm:320-352).
 
     groups[i] = the G ranks that compute interaction i; this rank, member h of its group, passes the x-slab
@@ -187,12 +211,25 @@ def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, grou
     which = next(i for i, g in enumerate(groups) if rank in g)
     h = groups[which].index(rank)
     pg = _process_groups(groups)[which]
-    sendA, sendB = stages.dist_forward(a_slab, b_slab, G, alpha, alpha)
-    recvA, recvB = torch.empty_like(sendA), torch.empty_like(sendB)
-    mark("fwd")
-    dist.all_to_all_single(recvA, sendA, group=pg)
-    dist.all_to_all_single(recvB, sendB, group=pg)
-    mark("a2a")
+    symm = peer_receive_buffer(shape, G, pg, a_slab.device) if (peer and hasattr(stages, "dist_forward_peer")) else None
+    if symm is not None:
+        # compute + exchange in one kernel: the y pass stores each row into its owner's buffer over NVLink.
+        # barrier 0: every rank is done reading its buffer (previous call); barrier 1: everyone's stores have landed
+        buf, hdl = symm
+        hdl.barrier(channel=0)
+        stages.dist_forward_peer(a_slab, b_slab, G, h, hdl.buffer_ptrs, alpha, alpha,
+                                 flags=int(os.environ.get("DBSPM_DIST_FLAGS", "0")))
+        mark("fwd")
+        hdl.barrier(channel=1)
+        recvA, recvB = buf[0], buf[1]
+        mark("a2a")
+    else:
+        sendA, sendB = stages.dist_forward(a_slab, b_slab, G, alpha, alpha)
+        recvA, recvB = torch.empty_like(sendA), torch.empty_like(sendB)
+        mark("fwd")
+        dist.all_to_all_single(recvA, sendA, group=pg)
+        dist.all_to_all_single(recvB, sendB, group=pg)
+        mark("a2a")
     # (G, nxl, ny/G, nz) received = (nx, ny/G, nz): source ranks are consecutive x-slabs
     W = stages.dist_middle(recvA, recvB, dr, shape, G, h, z_lo, z_hi)
     mark("mid")

@@ -52,6 +52,7 @@ extern "C" {
 #define DBSPM_CORR_NO_TMA     (1 << 3)   /* force the register-staged axis pass.  Default: picked per axis length --
                                             TMA for 256 <= n <= 576 (27 % faster at n = 384 on B200), register-staged
                                             otherwise (n = 1024 is FP64/shared-memory bound with 4-line tiles) */
+#define DBSPM_CORR_PEER_NARROW (1 << 4)  /* fused exchange: keep the 4-line tiles of the local pass (64-byte remote stores; A/B timing) */
 /* profiling aid: skip stages (results are then meaningless); bench.py times each launch alone */
 #define DBSPM_CORR_SKIP_XFWD  (1 << 8)
 #define DBSPM_CORR_SKIP_YFWD  (1 << 9)
@@ -107,6 +108,13 @@ int dbspm_zsupport_f64(const double *B, int nx, int ny, int nz, int *plane_nonze
 int dbspm_corr3d_dist_supported(int nx, int ny, int nz, int G);
 int dbspm_corr3d_dist_fwd_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
                               int nxl, int ny, int nz, int G, void *sendA, void *sendB, int flags, void *stream);
+/* Steps 1 + 2 fused (compute + exchange in one kernel): the y pass of rank `me` stores every output row straight into
+ * its owner's receive buffer through peer memory (NVLink / NVSwitch); no send buffer and no all-to-all.
+ * peer_recv: HOST array of G device pointers, peer_recv[h] = rank h's receive buffer (2, nx, ny/G, nz/2) complex128
+ * (A's spectra, then B's) mapped into this process (e.g. torch symmetric memory buffer_ptrs).  The caller brackets the
+ * call with two group barriers: every rank has finished reading its buffer / every rank's stores have landed.      */
+int dbspm_corr3d_dist_fwd_peer_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
+                                   int nxl, int ny, int nz, int G, int me, void *const *peer_recv, int flags, void *stream);
 int dbspm_corr3d_dist_mid_f64(void *recvA, void *recvB, double dV, int nx, int ny, int nz, int G, int h,
                               int z_lo, int z_hi, void *W_local, int flags, void *stream);
 size_t dbspm_corr3d_dist_fin_workspace_bytes(int nx, int ny, int z_lo, int z_hi);

@@ -28,7 +28,7 @@ static int pick_tshift(int n, long long inner)
 }
 
 struct EmuGather { int src_nz, dst_nz, z0[2], valid[2]; };
-struct EmuMap { const int *in_map, *out_map; long long in_ostride, out_ostride; };
+struct EmuMap { const int *in_map, *out_map; long long in_ostride, out_ostride; int npeers; cplx *peer[2][DBSPM_MAX_PEERS]; long long out_base_off; };
 
 template <int D>
 static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, int narrays, double a0, double a1,
@@ -49,6 +49,9 @@ static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, in
         P.in_map = mp->in_map; P.out_map = mp->out_map;
         if (mp->in_ostride) P.in_ostride = mp->in_ostride;
         if (mp->out_ostride) P.out_ostride = mp->out_ostride;
+        P.out_base_off = mp->out_base_off;
+        for (int w = 0; w < 2; ++w)
+            for (int q = 0; q < DBSPM_MAX_PEERS; ++q) P.out_peer[w][q] = q < mp->npeers ? mp->peer[w][q] : nullptr;
     }
     if (g) {   // as launch_axis(): the remapped first pass exists in the register-staged body only
         if (!axis_v2_ok(hp.dev)) return -2;
@@ -95,7 +98,8 @@ static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, in
     unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
     for (int w = 0; w < narrays; ++w)
         for (long long b = 0; b < outer * P.tiles; ++b) {
-            if (P.v2 && mp) axis_pass_body_v2<D, 1>(P, sm, b, w, 0, 1);
+            if (P.v2 && mp && mp->npeers > 0) axis_pass_body_v2<D, 2>(P, sm, b, w, 0, 1);
+            else if (P.v2 && mp) axis_pass_body_v2<D, 1>(P, sm, b, w, 0, 1);
             else if (P.v2) axis_pass_body_v2<D>(P, sm, b, w, 0, 1);
             else axis_pass_body<D>(P, sm, b, w, 0, 1);
         }
@@ -192,21 +196,38 @@ extern "C" int emu_corr3d_pruned_f64(const double *A, const double *B, double al
 extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
                                    int nx, int ny, int nz, int z_lo, int z_hi, double *E_win, int G, int force_tshift)
 {
-    if (!dist_shape_ok(nx, ny, nz, G)) return -3;
+    const bool peer = force_tshift >= 1000;          // fused exchange: the y pass stores into the owners' buffers
+    if (peer) force_tshift -= 1001;
+    if (!dist_shape_ok(nx, ny, nz, G) || (peer && G > DBSPM_MAX_PEERS)) return -3;
     const int n = nz / 2, nxl = nx / G, nyl = ny / G, nzw = z_hi - z_lo, nwh = (nzw + 1) / 2;
     const size_t blk = (size_t)nxl * nyl * n;                     // one (source, destination) block of the exchange
     std::vector<std::vector<cplx>> sendA(G), sendB(G), recvA(G), recvB(G);
     std::vector<int> omap(ny), imap(ny);
     for (int K = 0; K < ny; ++K) { omap[K] = dist_row_of(K, ny, G, (long long)nxl * nyl); imap[K] = dist_row_of(K, ny, G, (long long)nx * nyl); }
     int rc;
+    std::vector<int> pmap(ny);
+    for (int K = 0; K < ny; ++K) pmap[K] = dist_peer_entry(K, ny, G);
+    std::vector<std::vector<cplx>> recvAB(G);                      // peer mode: rank h's (2, nx, nyl, n) receive buffer
+    if (peer) for (int h = 0; h < G; ++h) recvAB[h].assign(2 * blk * G, cmake(0, 0));
     for (int g = 0; g < G; ++g) {
-        sendA[g].assign(blk * G, cmake(0, 0)); sendB[g].assign(blk * G, cmake(0, 0));
         const cplx *As = (const cplx *)A + (size_t)g * nxl * ny * n, *Bs = (const cplx *)B + (size_t)g * nxl * ny * n;
-        EmuMap mp = {nullptr, omap.data(), 0, (long long)nyl * n};
+        if (peer) {
+            EmuMap mp = {nullptr, pmap.data(), 0, (long long)nyl * n, G, {}, (long long)g * nxl * nyl * n};
+            for (int h = 0; h < G; ++h) { mp.peer[0][h] = recvAB[h].data(); mp.peer[1][h] = recvAB[h].data() + blk * G; }
+            if ((rc = run_axis<-1>(As, mp.peer[0][g], Bs, mp.peer[1][g], 2, alphaA, alphaB, 1, ny, n, nxl, force_tshift, nullptr, &mp))) return rc;
+            continue;
+        }
+        sendA[g].assign(blk * G, cmake(0, 0)); sendB[g].assign(blk * G, cmake(0, 0));
+        EmuMap mp = {nullptr, omap.data(), 0, (long long)nyl * n, 0, {}, 0};
         if ((rc = run_axis<-1>(As, sendA[g].data(), Bs, sendB[g].data(), 2, alphaA, alphaB, 1, ny, n, nxl, force_tshift, nullptr, &mp))) return rc;
     }
     for (int h = 0; h < G; ++h) {                                  // all-to-all: block h of rank g -> block g of rank h
         recvA[h].resize(blk * G); recvB[h].resize(blk * G);
+        if (peer) {
+            memcpy(recvA[h].data(), recvAB[h].data(), blk * G * sizeof(cplx));
+            memcpy(recvB[h].data(), recvAB[h].data() + blk * G, blk * G * sizeof(cplx));
+            continue;
+        }
         for (int g = 0; g < G; ++g) {
             memcpy(recvA[h].data() + blk * g, sendA[g].data() + blk * h, blk * sizeof(cplx));
             memcpy(recvB[h].data() + blk * g, sendB[g].data() + blk * h, blk * sizeof(cplx));
@@ -235,7 +256,7 @@ extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alph
     std::vector<cplx> Wodd;
     cplx *Wf = (cplx *)E_win;
     if (nzw & 1) { Wodd.resize((size_t)nx * ny * nwh); Wf = Wodd.data(); }
-    EmuMap mp = {imap.data(), nullptr, (long long)nyl * nwh, 0};
+    EmuMap mp = {imap.data(), nullptr, (long long)nyl * nwh, 0, 0, {}, 0};
     if ((rc = run_axis<1>(Wall.data(), Wf, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, force_tshift, nullptr, &mp))) return rc;
     if (nzw & 1) compact_body((const double *)Wf, E_win, (long long)nx * ny, nzw, 2 * nwh, 0, 1);
     return 0;

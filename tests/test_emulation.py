@@ -84,7 +84,8 @@ def test_corr3d_distributed_x_slabs(emu, shape, window, G):
     a, b = rng.random(shape), rng.random(shape) - 0.4
     dr = np.array([0.1, 0.2, 0.3])
     ref = O.density_overlap_fft(a ** 1.08, b, dr)[:, :, window[0]:window[1]]
-    for tshift in (-1, 0, 2):
+    # 1000+: fused exchange (the y pass stores every row straight into its owner's receive buffer)
+    for tshift in (-1, 0, 2, 1000, 1001, 1003):
         got = emu.corr3d_dist(a, b, dr, window[0], window[1], G, alpha0=1.08, tshift=tshift)
         assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, window, G, tshift)
 

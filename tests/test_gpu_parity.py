@@ -59,13 +59,20 @@ def test_overlap_edge_shapes(ops, shape, window):
     assert _rel(got, ref) <= 1e-9
 
 
-def _dist_on_one_gpu(ops, a, b, dr, z_lo, z_hi, G, alpha=1.0):
+def _dist_on_one_gpu(ops, a, b, dr, z_lo, z_hi, G, alpha=1.0, peer=False):
     """The distributed sr/es step with its G ranks run one after the other on this GPU: the three kernels stages
     per rank, the all-to-all and the gather as block copies (what parallel.sr_es_distributed does over NCCL)."""
     dev = torch.device("cuda", 0)
     A, B = torch.as_tensor(a, device=dev), torch.as_tensor(b, device=dev)
     nx, ny, nz = A.shape
     nxl = nx // G
+    if peer:
+        # fused exchange: the "peers" are G receive buffers on this GPU; every rank's y pass stores into all of them
+        recv = [torch.full((2, nx, ny // G, nz), float("nan"), dtype=torch.float64, device=dev) for _ in range(G)]
+        for g in range(G):
+            ops.dist_forward_peer(A[g * nxl:(g + 1) * nxl], B[g * nxl:(g + 1) * nxl], G, g, [r.data_ptr() for r in recv], alpha, alpha)
+        Ws = [ops.dist_middle(recv[h][0], recv[h][1], dr, (nx, ny, nz), G, h, z_lo, z_hi) for h in range(G)]
+        return ops.dist_finish(torch.stack(Ws).contiguous(), (nx, ny, nz), G, z_lo, z_hi).cpu().numpy()
     sends = [ops.dist_forward(A[g * nxl:(g + 1) * nxl], B[g * nxl:(g + 1) * nxl], G, alpha, alpha) for g in range(G)]
     Ws = []
     for h in range(G):
@@ -90,6 +97,9 @@ def test_overlap_distributed_x_slabs(ops, shape, window, G):
     assert _rel(got, ref) <= 1e-9, (shape, window, G, _rel(got, ref))
     one = ops.density_overlap_window(a, b, dr, window[0], window[1], 1.08, 1.08)
     assert _rel(got, one) <= 1e-12
+    # compute + exchange in one kernel (peer stores) gives the same bits as send buffer + all-to-all
+    fused = _dist_on_one_gpu(ops, a, b, dr, window[0], window[1], G, alpha=1.08, peer=True)
+    assert np.array_equal(fused, got)
 
 
 def test_overlap_distributed_goldens_and_unsupported(ops, overlap_golden, manifest):
