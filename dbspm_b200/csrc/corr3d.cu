@@ -99,6 +99,12 @@ axis_tma_kernel(const __grid_constant__ AxisTmaParams P, const __grid_constant__
 #ifndef ZF2_MIN_BLOCKS
 #define ZF2_MIN_BLOCKS 1
 #endif
+#ifndef ZF2_MAX_PER_SM
+#define ZF2_MAX_PER_SM 4      /* cap on resident persistent blocks per SM */
+#endif
+#ifndef ZF2_WAVES
+#define ZF2_WAVES 2
+#endif
 __global__ void __launch_bounds__(ZF2_THREADS, ZF2_MIN_BLOCKS) zfused2_kernel(const __grid_constant__ ZFusedParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -417,6 +423,13 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     }
     P.tiles = (inner + (1LL << P.tshift) - 1) >> P.tshift;
     const long long nblocks = outer * P.tiles;
+    // L2 prefetch distance = the blocks resident at once (148 SMs x CTAs per SM): block b + distance takes the slot of b
+    P.pf_ahead = 0;
+    // (not for the slowest axis: its rows are megabytes apart and the prefetch measured slower, 2.49 -> 2.75 ms at n = 1024)
+    if (P.v2 && outer > 1 && !(flags & DBSPM_CORR_NO_PREFETCH)) {
+        const int per_sm = wide ? 1 : (int)((227 * 1024) / (smem + 1024) < AXIS2_MIN_BLOCKS ? (227 * 1024) / (smem + 1024) : AXIS2_MIN_BLOCKS);
+        P.pf_ahead = 148 * (per_sm < 1 ? 1 : per_sm);
+    }
     DBSPM_REQUIRE(nblocks > 0 && nblocks < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large (%lld blocks)", nblocks);
     if (P.v2 && mp && mp->npeers > 0 && wide) {
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2pw_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -499,6 +512,7 @@ static int launch_zfused(const cplx *WA, const cplx *WB, cplx *W, int nx, int ny
     P.plan = pl->host.dev; P.tw = pl->tw; P.pos_of = pl->pos_of; P.freq_of = pl->freq_of; P.twN = plN->tw;
     P.npairs = (long long)(nx / 2 + 1) * ny_rows;
     P.slot_mode = slot_mode; P.slot_base = slot_base;
+    P.prefetch = (flags & DBSPM_CORR_NO_PREFETCH) ? 0 : 1;
     const bool v2 = axis_v2_ok(P.plan) && zfused2_smem_bytes<ZF2_PAIRS>(n) <= 113 * 1024 &&
                     !(flags & DBSPM_CORR_AXIS_V1);
     if (v2) {
@@ -506,8 +520,8 @@ static int launch_zfused(const cplx *WA, const cplx *WB, cplx *W, int nx, int ny
         const size_t smem = zfused2_smem_bytes<ZF2_PAIRS>(n);
         // persistent blocks: a few per SM (148 SMs), each walking over its share of the pair groups
         int per_sm = (int)((220 * 1024) / (smem + 1024));
-        per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-        long long nblocks = 148LL * per_sm * 2;
+        per_sm = per_sm < 1 ? 1 : (per_sm > ZF2_MAX_PER_SM ? ZF2_MAX_PER_SM : per_sm);
+        long long nblocks = 148LL * per_sm * ZF2_WAVES;
         if (nblocks > ngroups) nblocks = ngroups;
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

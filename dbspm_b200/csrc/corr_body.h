@@ -61,6 +61,9 @@ struct AxisParams {
     // receive buffer out_peer[which][h] (peer memory over NVLink) at element out_base_off + o * out_ostride + row * inner
     cplx *out_peer[2][DBSPM_MAX_PEERS];
     long long out_base_off;
+    // > 0: every block first asks the L2 for the rows of the tile that block `bid + pf_ahead` will read (the block that
+    // takes this SM slot next), so that its first-stage loads hit the L2 instead of waiting on DRAM
+    int pf_ahead;
 };
 
 // ---- distributed correlation: slot order of a transform axis --------------------------------------
@@ -360,6 +363,16 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
     const double alpha = P.alpha[which];
     const bool do_pow = P.use_pow && alpha != 1.0;
 
+#if defined(__CUDA_ARCH__)
+    if (P.pf_ahead > 0 && !P.gather && !(MAP && P.in_map)) {
+        const long long nb = bid + P.pf_ahead;
+        if (nb < P.outer * P.tiles) {
+            const long long o2 = nb / P.tiles, t2 = nb - o2 * P.tiles;
+            const cplx *g2 = P.in[which] + (MAP ? (size_t)o2 * P.in_ostride : (size_t)o2 * n * P.inner) + (t2 << P.tshift);
+            for (int r = tid; r < n; r += nthr) asm volatile("prefetch.global.L2 [%0];" ::"l"(g2 + (size_t)r * P.inner));
+        }
+    }
+#endif
     if (P.tw_smem && pl.nstages > 1) {
         for (int e = tid; e < n; e += nthr) twbuf[e] = ldg_c(P.tw + e);
         BLOCK_SYNC();
@@ -632,6 +645,7 @@ struct ZFusedParams {
     // distributed correlation: this rank holds the ny rows of the y axis that are slots [slot_base, slot_base + ny)
     // of the global axis (dist_slot_of); row r pairs with the row of its mirror slot.  slot_mode = 0: natural rows
     int slot_mode, slot_base;
+    int prefetch;             // 1: a persistent block asks the L2 for the 4*ZLV lines of its next pair group (bulk prefetch)
 };
 
 HD size_t zfused_smem_bytes(int n)
@@ -837,6 +851,18 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
         pi[0] = z.kx; pi[1] = z.ky; pi[2] = z.mx; pi[3] = z.my; pi[4] = z.valid; pi[5] = z.self;
     }
     BLOCK_SYNC();
+#if defined(__CUDA_ARCH__)
+    if (P.prefetch && bid + bstride < ngroups) {
+        for (int line = tid; line < 4 * ZLV; line += nthr) {
+            const ZPair z = zpair_of(P, (bid + bstride) * ZLV + (line >> 2));
+            if (z.valid) {
+                const int role = line & 3;
+                const cplx *src = ((role & 2) ? P.ZB : P.ZA) + ((size_t)((role & 1) ? z.mx : z.kx) * P.ny + ((role & 1) ? z.my : z.ky)) * n;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n * 16) : "memory");
+            }
+        }
+    }
+#endif
 #define CALL_(R) zfused2_first<-1, R, ZLV>(P, U, tw, pinfo, tid, nthr)
     DBSPM_FAST_RADIX_SWITCH(P.plan.radix[0], CALL_)
 #undef CALL_

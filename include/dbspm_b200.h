@@ -53,6 +53,7 @@ extern "C" {
                                             TMA for 256 <= n <= 576 (27 % faster at n = 384 on B200), register-staged
                                             otherwise (n = 1024 is FP64/shared-memory bound with 4-line tiles) */
 #define DBSPM_CORR_PEER_NARROW (1 << 4)  /* fused exchange: keep the 4-line tiles of the local pass (64-byte remote stores; A/B timing) */
+#define DBSPM_CORR_NO_PREFETCH (1 << 5)  /* no L2 prefetch of the next tile / pair group (A/B timing) */
 /* profiling aid: skip stages (results are then meaningless); bench.py times each launch alone */
 #define DBSPM_CORR_SKIP_XFWD  (1 << 8)
 #define DBSPM_CORR_SKIP_YFWD  (1 << 9)

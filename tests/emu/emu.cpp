@@ -42,6 +42,7 @@ static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, in
     P.alpha[0] = a0; P.alpha[1] = a1; P.use_pow = use_pow; P.narrays = narrays;
     P.gather = 0;
     P.in_map = P.out_map = nullptr;
+    P.pf_ahead = 0;
     P.in_ostride = P.out_ostride = (long long)n * inner;
     if (mp) {   // as launch_axis(): row-mapped passes exist in the register-staged body only
         if (!axis_v2_ok(hp.dev)) return -2;
@@ -153,7 +154,7 @@ static int emu_corr3d_core(const double *A, const double *B, double alphaA, doub
         P.scale = dV / ((double)nx * (double)ny * (double)nz) * 0.25;
         P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data(); P.freq_of = hp.freq_of.data(); P.twN = hpN.tw.data();
         P.npairs = (long long)(nx / 2 + 1) * ny;
-        P.slot_mode = 0; P.slot_base = 0;
+        P.slot_mode = 0; P.slot_base = 0; P.prefetch = 0;
         // same selection as dbspm_corr3d_f64: v2 (4 pairs / block) when the plan is all fast radices
         const bool v2 = axis_v2_ok(P.plan) && (force_tshift < 100 || force_tshift >= 200);
         std::vector<unsigned char> smem((v2 ? zfused2_smem_bytes<4>(n) : zfused_smem_bytes(n)) + 64);
@@ -245,7 +246,7 @@ extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alph
         P.scale = dV / ((double)nx * (double)ny * (double)nz) * 0.25;
         P.plan = hp.dev; P.tw = hp.tw.data(); P.pos_of = hp.pos_of.data(); P.freq_of = hp.freq_of.data(); P.twN = hpN.tw.data();
         P.npairs = (long long)(nx / 2 + 1) * nyl;
-        P.slot_mode = 1; P.slot_base = h * nyl;
+        P.slot_mode = 1; P.slot_base = h * nyl; P.prefetch = 0;
         const bool v2 = axis_v2_ok(P.plan) && (force_tshift < 100 || force_tshift >= 200);
         std::vector<unsigned char> smem((v2 ? zfused2_smem_bytes<4>(n) : zfused_smem_bytes(n)) + 64);
         unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
