@@ -123,6 +123,48 @@ def test_overlap_distributed_goldens_and_unsupported(ops, overlap_golden, manife
         ops.dist_forward(x, x, 2)
 
 
+_DIST_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch
+from dbspm_b200 import interactions as ops, parallel
+rank, world, dev = parallel.init_from_env()
+shape, z_lo, z_hi = (64, 96, 40), 11, 30
+rng = np.random.default_rng(7)
+A, B = rng.random(shape), rng.random(shape) + 0.05
+dr = np.array([0.1, 0.2, 0.3])
+a, b = torch.as_tensor(A, device=dev), torch.as_tensor(B, device=dev)
+x0, x1 = parallel.x_slab(shape[0], world, rank)
+one = ops.density_overlap_window(a, b, dr, z_lo, z_hi, 1.08, 1.08)
+for peer in (False, True):
+    for rep in range(2):            # twice: the second call reuses the symmetric buffer (barrier protocol)
+        wins = parallel.sr_es_distributed(ops, a[x0:x1], b[x0:x1], 1.08, shape, dr, z_lo, z_hi, [list(range(world))], peer=peer)
+        if rank == 0:
+            err = float((wins[0] - one).abs().max() / one.abs().max())
+            assert err <= 1e-12, (peer, rep, err)
+        else:
+            assert wins is None
+torch.cuda.synchronize()
+if rank == 0:
+    print("DIST_OK", "symm" if parallel.peer_receive_buffer(shape, world, parallel._process_groups([list(range(world))])[0], dev) else "nccl-only")
+torch.distributed.barrier()
+torch.distributed.destroy_process_group()
+'''
+
+
+def test_overlap_distributed_two_processes_nccl(tmp_path):
+    """parallel.sr_es_distributed over real NCCL + symmetric memory with one process per GPU (needs >= 2 GPUs; the
+    one-GPU box runs the same kernels with virtual ranks in test_overlap_distributed_x_slabs)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "dist_worker.py"
+    script.write_text(_DIST_WORKER.format(root=ROOT))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DIST_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
 @pytest.mark.parametrize("flags", [0, 1 << 1, 1 << 2, 1 << 3])
 def test_overlap_kernel_variants_agree(ops, overlap_golden, manifest, flags):
     """default (register-first/last) axis pass, all-in-shared-memory variant (1<<1) and the TMA-fed
