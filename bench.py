@@ -271,7 +271,7 @@ def run_gpu_arm(args):
             wins = parallel.sr_es_distributed(ops, a[sx0:sx1], b[sx0:sx1], al, cfg.shape, dr, z_lo, z_hi, groups,
                                               on_stage=(lambda name: rec.append((name, ev()))) if rec is not None else None,
                                               peer=not args.no_peer)
-            launches["n"] += 4 + (2 if rank == 0 else 0)          # y fwd | x fwd, z, x inv | y inv of both windows
+            launches["n"] += 5                                     # y fwd | x fwd, z, x inv | y inv of this rank's x-slab
             if marks is not None:
                 marks.append(ev())
                 dist_marks.append(rec)
@@ -509,8 +509,8 @@ def run_gpu_arm(args):
             "traffic": (2 * profiled_traffic(args.workload) if world == 1 and profiled_traffic(args.workload) else None),
             "traffic_note": "dram bytes read+write of sr+es (2 x 5 launches), ncu --set full, profiles/traffic.json",
             "peak_source": peak_src,
-            "kernel": ("dbspm_corr3d_dist_{fwd,mid,fin}_f64 = 5 launches per rank (axis_pass y_fwd | x_fwd, zfused, x_inv | "
-                       "y_inv on rank 0) + all-to-all + gather" if groups is not None else
+            "kernel": ("dbspm_corr3d_dist_{fwd_peer,mid,fin}_f64 = 5 launches per rank (axis_pass y_fwd with peer stores | "
+                       "x_fwd, zfused, x_inv | y_inv of the rank's x-slab) + small all-to-all + gather" if groups is not None else
                        "dbspm_corr3d_f64 = 5 launches (axis_pass x_fwd, y_fwd, zfused, axis_pass y_inv, x_inv)"),
             "algorithmic_bytes_per_interaction": balg, "ms_sr_plus_es": t_corr,
             "ms_sr": t_sr if world == 1 else None, "ms_es": t_es if world == 1 else None,
@@ -533,8 +533,8 @@ def run_gpu_arm(args):
                    "parallelism": ((f"sr | es on disjoint groups of {G} ranks; inside a group the transform is distributed "
                                     f"over x-slabs (y pass " + ("+ all-to-all through NCCL" if args.no_peer else
                                     "whose stores go straight into the owners' buffers over NVLink (symmetric memory)")
-                                    + f", x pass + z kernel + inverse x, gather of the packed window rows to rank 0, "
-                                    f"inverse y there); x-tile x{world} (relax)")
+                                    + f", x pass + z kernel + inverse x, small all-to-all of the packed window rows back to "
+                                    f"x-slabs, inverse y, gather of the real slabs into place on rank 0); x-tile x{world} (relax)")
                                    if groups is not None else
                                    (f"sr | es on disjoint rank groups, z-slab within a group ({world} ranks), "
                                     f"x-tile x{world} (relax), gather to rank 0") if world > 1 else "single GPU")},

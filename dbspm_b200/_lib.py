@@ -43,6 +43,8 @@ _SIGNATURES = {
                                                  C.c_int, C.POINTER(_vp), C.c_int, _vp]),
     "dbspm_corr3d_dist_mid_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_int, _vp, C.c_int, _vp]),
+    "dbspm_corr3d_dist_mid_peer_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 C.c_int, C.c_int, _vp, C.POINTER(_vp), C.c_int, _vp]),
     "dbspm_corr3d_dist_fin_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "dbspm_corr3d_dist_fin_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t,
                                             C.c_int, _vp]),

@@ -204,7 +204,8 @@ static int get_rowmap(int n, int G, long long blockrows, cudaStream_t st, const 
     if (it != g_rowmaps.end()) { *out = it->second; return DBSPM_OK; }
     DBSPM_REQUIRE((long long)G * blockrows < 2147483647LL, DBSPM_EUNSUPPORTED, "row table overflows 32 bits");
     std::vector<int> h((size_t)n);
-    for (int K = 0; K < n; ++K) h[K] = blockrows < 0 ? dist_peer_entry(K, n, G) : dist_row_of(K, n, G, blockrows);
+    for (int K = 0; K < n; ++K)
+        h[K] = blockrows == -2 ? dist_block_entry(K, n, G) : (blockrows < 0 ? dist_peer_entry(K, n, G) : dist_row_of(K, n, G, blockrows));
     int *d = nullptr;
     DBSPM_CUDA_TRY(cudaMalloc((void **)&d, sizeof(int) * (size_t)n));
     DBSPM_CUDA_TRY(cudaMemcpyAsync(d, h.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -734,6 +735,38 @@ extern "C" int dbspm_corr3d_dist_mid_f64(void *recvA, void *recvB, double dV, in
     rc = launch_zfused(WA, WB, W, nx, nyl, nz, z_lo, nwh, dV / ((double)nx * (double)ny * (double)nz) * 0.25, 1, h * nyl, flags, st);
     if (rc) return rc;
     return launch_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)nyl * nwh, 1, st, flags);
+}
+
+// mid with the second exchange fused into the inverse x pass: row x of this rank's packed window goes straight into
+// the buffer of the rank that owns x-slab x / (nx/G): peer_w2[q] = rank q's (G, nx/G, ny/G, ceil(nzw/2)) complex buffer
+extern "C" int dbspm_corr3d_dist_mid_peer_f64(void *recvA, void *recvB, double dV, int nx, int ny, int nz, int G, int h,
+                                              int z_lo, int z_hi, void *W_local, void *const *peer_w2, int flags, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    DBSPM_REQUIRE(recvA && recvB && W_local && peer_w2, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(dist_shape_ok(nx, ny, nz, G) && G <= DBSPM_MAX_PEERS && h >= 0 && h < G, DBSPM_EUNSUPPORTED,
+                  "distributed correlation: bad shape (%d,%d,%d) / rank %d of %d", nx, ny, nz, h, G);
+    DBSPM_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= nz, DBSPM_EINVAL, "bad window [%d,%d) for nz=%d", z_lo, z_hi, nz);
+    const int n = nz / 2, nyl = ny / G, nxl = nx / G, nwh = (z_hi - z_lo + 1) / 2;
+    DBSPM_REQUIRE(nxl < (1 << DIST_PEER_SHIFT), DBSPM_EUNSUPPORTED, "nx/G too large for the peer table");
+    cplx *WA = (cplx *)recvA, *WB = (cplx *)recvB, *W = (cplx *)W_local;
+    int rc = launch_axis<-1>(WA, WA, WB, WB, 2, 1.0, 1.0, 0, nx, (long long)nyl * n, 1, st, flags);
+    if (rc) return rc;
+    rc = launch_zfused(WA, WB, W, nx, nyl, nz, z_lo, nwh, dV / ((double)nx * (double)ny * (double)nz) * 0.25, 1, h * nyl, flags, st);
+    if (rc) return rc;
+    const int *omap = nullptr;
+    rc = get_rowmap(nx, G, -2, st, &omap);
+    if (rc) return rc;
+    const long long inner = (long long)nyl * nwh;
+    AxisMap mp;
+    mp.in_map = nullptr; mp.out_map = omap; mp.in_ostride = 0; mp.out_ostride = 0;
+    mp.npeers = G; mp.out_base_off = (long long)h * nxl * inner;
+    for (int q = 0; q < G; ++q) {
+        DBSPM_REQUIRE(peer_w2[q] && ((uintptr_t)peer_w2[q] & 15) == 0, DBSPM_EINVAL, "peer buffer %d null or misaligned", q);
+        mp.peer[0][q] = (cplx *)peer_w2[q];
+        mp.peer[1][q] = nullptr;
+    }
+    return launch_axis<1>(W, mp.peer[0][h], nullptr, nullptr, 1, 1.0, 1.0, 0, nx, inner, 1, st, flags, nullptr, &mp);
 }
 
 extern "C" size_t dbspm_corr3d_dist_fin_workspace_bytes(int nx, int ny, int z_lo, int z_hi)

@@ -94,6 +94,13 @@ HD int dist_peer_entry(int K, int n, int G)
     return ((S / nl) << DIST_PEER_SHIFT) | (S % nl);
 }
 
+// fused second exchange: position X of the x axis belongs to the rank that owns its x-slab
+HD int dist_block_entry(int X, int n, int G)
+{
+    const int nl = n / G;
+    return ((X / nl) << DIST_PEER_SHIFT) | (X % nl);
+}
+
 HD bool dist_shape_ok(int nx, int ny, int nz, int G)
 {
     return G >= 1 && nx >= 1 && ny >= 2 && nz >= 2 && (nz % 2) == 0 && (ny % (2 * G)) == 0 && (nx % G) == 0;

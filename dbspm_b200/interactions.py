@@ -207,6 +207,24 @@ def dist_middle(recvA, recvB, dr, shape, G, h, z_lo, z_hi, out=None, flags=0):
     return out
 
 
+def dist_middle_peer(recvA, recvB, dr, shape, G, h, z_lo, z_hi, peer_ptrs, scratch=None, flags=0):
+    """dist_middle with the second exchange fused into its inverse x pass: row x of this rank's packed window is
+    stored into the (G, nx/G, ny/G, 2*ceil(nzw/2)) float64 buffer of the rank that owns x-slab x // (nx/G)
+    (peer_ptrs[q] = that buffer of rank q, symmetric memory).  The caller follows with a group barrier."""
+    dev = recvA.device
+    nx, ny, nz = (int(v) for v in shape)
+    nwh = (int(z_hi) - int(z_lo) + 1) // 2
+    if scratch is None:
+        scratch = torch.empty((nx, ny // int(G), 2 * nwh), dtype=torch.float64, device=dev)
+    dV = float(np.prod(np.asarray(dr, dtype=np.float64)))
+    ptrs = (C.c_void_p * int(G))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dbspm_corr3d_dist_mid_peer_f64(recvA.data_ptr(), recvB.data_ptr(), dV, nx, ny, nz, int(G), int(h),
+                                                             int(z_lo), int(z_hi), scratch.data_ptr(), ptrs, int(flags),
+                                                             _stream_ptr(dev)))
+    return scratch
+
+
 def dist_finish(W_all, shape, G, z_lo, z_hi, out=None, flags=0):
     """inverse y transform of the gathered packed windows (G, nx, ny/G, 2*ceil(nzw/2)) -> (nx, ny, nzw)."""
     dev = W_all.device

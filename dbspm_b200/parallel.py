@@ -174,6 +174,24 @@ def x_slab(nx: int, G: int, h: int):
 _SYMM: dict = {}
 
 
+def peer_buffer(key, dims, pg, device):
+    """A float64 buffer of shape `dims` in symmetric memory, mapped into every process of group `pg` (cached under
+    `key`): (buffer, handle) or None when symmetric memory is unavailable."""
+    if device.type != "cuda" or os.environ.get("DBSPM_NO_PEER"):
+        return None
+    key = (key, tuple(int(v) for v in dims), id(pg), device.index)
+    if key not in _SYMM:
+        try:
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty(tuple(int(v) for v in dims), dtype=torch.float64, device=device)
+            hdl = symm.rendezvous(buf, pg)
+            _SYMM[key] = (buf, hdl)
+        except Exception as exc:                                   # noqa: BLE001 -- any failure = no peer path
+            print(f"dbspm_b200: symmetric memory unavailable ({exc!r}); exchanging through NCCL", flush=True)
+            _SYMM[key] = None
+    return _SYMM[key]
+
+
 def peer_receive_buffer(shape, G: int, pg, device):
     """This rank's (2, nx, ny/G, nz) float64 receive buffer of the fused exchange, allocated in symmetric memory and
     mapped into every process of the group (torch.distributed._symmetric_memory): returns (buffer, handle) or None
@@ -201,9 +219,10 @@ def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, grou
     groups[i] = the G ranks that compute interaction i; this rank, member h of its group, passes the x-slab
     x_slab(nx, G, h) of its interaction's two arrays.  `stages` provides the three compute stages
     (dbspm_b200.interactions: dist_forward / dist_middle / dist_finish; the CPU tests inject numpy ones).
-    Data-path collectives: one all-to-all per array inside the group (the transpose every distributed FFT needs:
-    16N/G bytes per rank) and one gather of the packed window rows to rank `dst`, which runs the final inverse
-    y pass of every interaction.  Returns the list of (nx,ny,nzw) windows on `dst`, None elsewhere.
+    Data-path exchanges: the transpose every distributed FFT needs (16N/G bytes per rank; fused into the y pass as
+    peer stores when symmetric memory is available, else one all-to-all per array), a second, small all-to-all of the
+    packed window rows back to x-slabs (so the final inverse y pass is distributed as well), and one gather of the
+    finished real slabs into place on rank `dst`.  Returns the list of (nx,ny,nzw) windows on `dst`, None elsewhere.
     on_stage(name) is called after each stage has been enqueued (bench.py records a CUDA event there)."""
     mark = on_stage or (lambda name: None)
     rank, world = _world()
@@ -231,17 +250,45 @@ def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, grou
         dist.all_to_all_single(recvB, sendB, group=pg)
         mark("a2a")
     # (G, nxl, ny/G, nz) received = (nx, ny/G, nz): source ranks are consecutive x-slabs
+    nx, ny = int(shape[0]), int(shape[1])
+    nxl, nwh = nx // G, (int(z_hi) - int(z_lo) + 1) // 2
+    symm2 = peer_buffer("w2", (G, nxl, ny // G, 2 * nwh), pg, a_slab.device) if (symm is not None and hasattr(stages, "dist_middle_peer")) else None
+    if symm2 is not None:
+        # second exchange fused into the inverse x pass of the middle stage (peer stores); the previous reader of
+        # this buffer (the final pass of the previous call) finished before barrier 0 above
+        W2, hdl2 = symm2
+        stages.dist_middle_peer(recvA, recvB, dr, shape, G, h, z_lo, z_hi, hdl2.buffer_ptrs)
+        mark("mid")
+        hdl2.barrier(channel=0)
+        slab = stages.dist_finish(W2, (nxl,) + tuple(int(v) for v in shape[1:]), G, z_lo, z_hi)
+        mark("fin")
+        return _gather_slabs(slab, groups, G, nx, nxl, dst, mark)
     W = stages.dist_middle(recvA, recvB, dr, shape, G, h, z_lo, z_hi)
     mark("mid")
-    big = None
-    if rank == dst:
-        big = torch.empty((world,) + tuple(W.shape), dtype=W.dtype, device=W.device)
-    dist.gather(W.contiguous(), list(big.unbind(0)) if rank == dst else None, dst=dst)
-    mark("gather")
-    if rank != dst:
-        return None
-    wins = [stages.dist_finish(big[g[0]:g[0] + G], shape, G, z_lo, z_hi) for g in groups]
+    # second exchange (small: the packed window rows, 16 N_w / G bytes per rank): rank g receives the rows of x-slab g
+    # for every y-frequency, laid out (source rank, nxl, ny/G, .) -- exactly what the row-mapped inverse y pass reads --
+    # so the final pass is distributed too and rank `dst` only receives finished real slabs, straight into place
+    W2 = torch.empty_like(W)
+    dist.all_to_all_single(W2, W, group=pg)
+    slab = stages.dist_finish(W2.view((G, nxl) + tuple(W.shape[1:])), (nxl,) + tuple(int(v) for v in shape[1:]), G, z_lo, z_hi)
     mark("fin")
+    return _gather_slabs(slab, groups, G, nx, nxl, dst, mark)
+
+
+def _gather_slabs(slab, groups, G, nx, nxl, dst, mark):
+    """Finished real x-slabs of every interaction -> the full windows on rank `dst` (received straight into place)."""
+    rank, world = _world()
+    wins = None
+    gl = None
+    if rank == dst:
+        assert sorted(r for g in groups for r in g) == list(range(world)), "groups must cover the world"
+        wins = [torch.empty((nx,) + tuple(slab.shape[1:]), dtype=slab.dtype, device=slab.device) for _ in groups]
+        gl = [None] * world
+        for i, g in enumerate(groups):
+            for hh, r in enumerate(g):
+                gl[r] = wins[i][hh * nxl:(hh + 1) * nxl]
+    dist.gather(slab, gl, dst=dst)
+    mark("gather")
     return wins
 
 

@@ -118,6 +118,12 @@ int dbspm_corr3d_dist_fwd_peer_f64(const double *A_slab, const double *B_slab, d
                                    int nxl, int ny, int nz, int G, int me, void *const *peer_recv, int flags, void *stream);
 int dbspm_corr3d_dist_mid_f64(void *recvA, void *recvB, double dV, int nx, int ny, int nz, int G, int h,
                               int z_lo, int z_hi, void *W_local, int flags, void *stream);
+/* Step 3 with a second, small exchange fused into its inverse x pass: row x of the packed window is stored straight into
+ * the buffer of the rank that owns x-slab x / (nx/G), so that step 5 runs distributed (every rank: its own x-slab) and
+ * rank 0 only gathers finished real slabs.  peer_w2[q] = rank q's (G, nx/G, ny/G, ceil(nzw/2)) complex128 buffer;
+ * afterwards (group barrier) rank q calls dbspm_corr3d_dist_fin_f64(its buffer, nx/G, ny, G, ...) -> (nx/G, ny, nzw).  */
+int dbspm_corr3d_dist_mid_peer_f64(void *recvA, void *recvB, double dV, int nx, int ny, int nz, int G, int h,
+                                   int z_lo, int z_hi, void *W_local, void *const *peer_w2, int flags, void *stream);
 size_t dbspm_corr3d_dist_fin_workspace_bytes(int nx, int ny, int z_lo, int z_hi);
 int dbspm_corr3d_dist_fin_f64(const void *W_all, int nx, int ny, int G, int z_lo, int z_hi, double *E_win,
                               void *workspace, size_t workspace_bytes, int flags, void *stream);

@@ -234,11 +234,18 @@ extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alph
             memcpy(recvB[h].data() + blk * g, sendB[g].data() + blk * h, blk * sizeof(cplx));
         }
     }
-    std::vector<cplx> Wall((size_t)G * nx * nyl * nwh);
+    // packed window rows: W2[q] = rank q's (G, nxl, nyl, nwh) buffer = the rows of x-slab q from every rank
+    std::vector<std::vector<cplx>> W2(G);
+    for (int q = 0; q < G; ++q) W2[q].assign((size_t)G * nxl * nyl * nwh, cmake(0, 0));
+    std::vector<int> bmap(nx);
+    for (int X = 0; X < nx; ++X) bmap[X] = dist_block_entry(X, nx, G);
     HostPlan hp, hpN;
     if (!dbspm_make_plan(n, hp) || !dbspm_make_plan(nz, hpN)) return -2;
+    const long long winner = (long long)nyl * nwh;
     for (int h = 0; h < G; ++h) {
-        cplx *WA = recvA[h].data(), *WB = recvB[h].data(), *W = Wall.data() + (size_t)h * nx * nyl * nwh;
+        cplx *WA = recvA[h].data(), *WB = recvB[h].data();
+        std::vector<cplx> Wl((size_t)nx * nyl * nwh);
+        cplx *W = Wl.data();
         if ((rc = run_axis<-1>(WA, WA, WB, WB, 2, 1.0, 1.0, 0, nx, (long long)nyl * n, 1, force_tshift))) return rc;
         ZFusedParams P;
         P.ZA = WA; P.ZB = WB; P.W = W;
@@ -252,14 +259,30 @@ extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alph
         unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
         if (v2) for (long long b = 0; b < 3; ++b) zfused_body_v2<4>(P, sm, b, 3, 0, 1);
         else for (long long b = 0; b < (P.npairs + ZL - 1) / ZL; ++b) zfused_body(P, sm, b, 0, 1);
-        if ((rc = run_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, (long long)nyl * nwh, 1, force_tshift))) return rc;
+        if (peer) {
+            // dbspm_corr3d_dist_mid_peer_f64: the inverse x pass stores row x into the owner of x-slab x / nxl
+            EmuMap mp = {nullptr, bmap.data(), 0, 0, G, {}, (long long)h * nxl * winner};
+            for (int q = 0; q < G; ++q) { mp.peer[0][q] = W2[q].data(); mp.peer[1][q] = nullptr; }
+            if ((rc = run_axis<1>(W, mp.peer[0][h], nullptr, nullptr, 1, 1.0, 1.0, 0, nx, winner, 1, force_tshift, nullptr, &mp))) return rc;
+        } else {
+            if ((rc = run_axis<1>(W, W, nullptr, nullptr, 1, 1.0, 1.0, 0, nx, winner, 1, force_tshift))) return rc;
+            for (int q = 0; q < G; ++q)                            // second all-to-all: x-slab q of rank h -> block h of rank q
+                memcpy(W2[q].data() + (size_t)h * nxl * winner, W + (size_t)q * nxl * winner, (size_t)nxl * winner * sizeof(cplx));
+        }
     }
-    std::vector<cplx> Wodd;
-    cplx *Wf = (cplx *)E_win;
-    if (nzw & 1) { Wodd.resize((size_t)nx * ny * nwh); Wf = Wodd.data(); }
-    EmuMap mp = {imap.data(), nullptr, (long long)nyl * nwh, 0, 0, {}, 0};
-    if ((rc = run_axis<1>(Wall.data(), Wf, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nx, force_tshift, nullptr, &mp))) return rc;
-    if (nzw & 1) compact_body((const double *)Wf, E_win, (long long)nx * ny, nzw, 2 * nwh, 0, 1);
+    // every rank: inverse y pass of its x-slab through the slot table -> real slab, placed at its x range
+    std::vector<int> imap2(ny);
+    for (int K = 0; K < ny; ++K) imap2[K] = dist_row_of(K, ny, G, (long long)nxl * nyl);
+    for (int q = 0; q < G; ++q) {
+        std::vector<cplx> Wodd;
+        double *Eq = E_win + (size_t)q * nxl * ny * nzw;
+        cplx *Wf = (cplx *)Eq;
+        if (nzw & 1) { Wodd.resize((size_t)nxl * ny * nwh); Wf = Wodd.data(); }
+        EmuMap mp = {imap2.data(), nullptr, (long long)nyl * nwh, 0, 0, {}, 0};
+        if ((rc = run_axis<1>(W2[q].data(), Wf, nullptr, nullptr, 1, 1.0, 1.0, 0, ny, nwh, nxl, force_tshift, nullptr, &mp))) return rc;
+        if (nzw & 1) compact_body((const double *)Wf, Eq, (long long)nxl * ny, nzw, 2 * nwh, 0, 1);
+    }
+    (void)imap;
     return 0;
 }
 

@@ -71,8 +71,13 @@ def _dist_on_one_gpu(ops, a, b, dr, z_lo, z_hi, G, alpha=1.0, peer=False):
         recv = [torch.full((2, nx, ny // G, nz), float("nan"), dtype=torch.float64, device=dev) for _ in range(G)]
         for g in range(G):
             ops.dist_forward_peer(A[g * nxl:(g + 1) * nxl], B[g * nxl:(g + 1) * nxl], G, g, [r.data_ptr() for r in recv], alpha, alpha)
-        Ws = [ops.dist_middle(recv[h][0], recv[h][1], dr, (nx, ny, nz), G, h, z_lo, z_hi) for h in range(G)]
-        return ops.dist_finish(torch.stack(Ws).contiguous(), (nx, ny, nz), G, z_lo, z_hi).cpu().numpy()
+        # second exchange fused into the inverse x pass: rows go straight into the buffer of the x-slab's owner
+        nwh = (z_hi - z_lo + 1) // 2
+        w2 = [torch.full((G, nxl, ny // G, 2 * nwh), float("nan"), dtype=torch.float64, device=dev) for _ in range(G)]
+        for h in range(G):
+            ops.dist_middle_peer(recv[h][0], recv[h][1], dr, (nx, ny, nz), G, h, z_lo, z_hi, [w.data_ptr() for w in w2])
+        slabs = [ops.dist_finish(w2[q], (nxl, ny, nz), G, z_lo, z_hi) for q in range(G)]
+        return torch.cat(slabs, dim=0).cpu().numpy()
     sends = [ops.dist_forward(A[g * nxl:(g + 1) * nxl], B[g * nxl:(g + 1) * nxl], G, alpha, alpha) for g in range(G)]
     Ws = []
     for h in range(G):
