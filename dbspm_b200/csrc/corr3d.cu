@@ -400,7 +400,7 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
         // With the power fused into the load the pass is FP64-issue bound and two CTAs hide it better:
         // 4.21 ms (2 x 256) against 4.87 ms (1 x 512).
         else if (!mp && outer == 1 && P.tshift == 2 && inner >= 65536 && P.plan.nstages > 1 &&
-                 !(use_pow && (alpha0 != 1.0 || alpha1 != 1.0)) &&
+                 (!(use_pow && (alpha0 != 1.0 || alpha1 != 1.0)) || (flags & DBSPM_CORR_POW_WIDE)) &&
                  axis2_smem_bytes(n, 3, P.plan.nstages, 0) <= 200 * 1024) {
             wide = true;
             P.tshift = 3; P.tw_smem = 0;
@@ -421,6 +421,14 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
         P.tshift = pick_tshift(n, inner);
         DBSPM_REQUIRE(P.tshift >= 0, DBSPM_EUNSUPPORTED, "axis length %d does not fit in shared memory", n);
         smem = axis_smem_bytes(n, P.tshift);
+    }
+    // powered first pass: the table of pow_fast is staged behind the tile (DBSPM_CORR_SLOW_POW: libdevice exp(alpha log v))
+    P.pow_tab_off = -1;
+    if (P.v2 && use_pow && (alpha0 != 1.0 || alpha1 != 1.0) && !(flags & DBSPM_CORR_SLOW_POW)) {
+        pow_fast_bounds(alpha0, &P.pow_lo[0], &P.pow_hi[0]);
+        pow_fast_bounds(alpha1, &P.pow_lo[1], &P.pow_hi[1]);
+        P.pow_tab_off = (int)align_up(smem, 16);
+        smem = (size_t)P.pow_tab_off + DBSPM_POW_TABLE_LEN * sizeof(double);
     }
     P.tiles = (inner + (1LL << P.tshift) - 1) >> P.tshift;
     const long long nblocks = outer * P.tiles;

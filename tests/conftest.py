@@ -50,6 +50,7 @@ class Emu:
                                             C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]
         L.emu_corr3d_dist_f64.argtypes = [_dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, _dp, C.c_int, C.c_int]
+        L.emu_pow_fast.argtypes = [_dp, _dp, C.c_longlong, C.c_double]
         L.emu_fft_lines.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int]
         L.emu_fft_lines_t.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int]
         L.emu_relax_powell_f64.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -85,6 +86,12 @@ class Emu:
                                         z_lo, z_hi, self._p(out), G, tshift)
         if rc:
             raise RuntimeError(f"emu_corr3d_dist_f64 -> {rc}")
+        return out
+
+    def pow_fast(self, x, alpha):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        self.L.emu_pow_fast(self._p(x), self._p(out), x.size, float(alpha))
         return out
 
     def corr3d_pruned(self, a, b, dr, z_lo, z_hi, s_lo, s_len, alpha0=1.0, alpha1=1.0, tshift=-1):

@@ -43,6 +43,9 @@ static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, in
     P.gather = 0;
     P.in_map = P.out_map = nullptr;
     P.pf_ahead = 0;
+    P.pow_tab_off = (force_tshift == 1 || force_tshift >= 1000) ? -1 : 0;     // both power implementations are exercised
+    pow_fast_bounds(a0, &P.pow_lo[0], &P.pow_hi[0]);
+    pow_fast_bounds(a1, &P.pow_lo[1], &P.pow_hi[1]);
     P.in_ostride = P.out_ostride = (long long)n * inner;
     if (mp) {   // as launch_axis(): row-mapped passes exist in the register-staged body only
         if (!axis_v2_ok(hp.dev)) return -2;
@@ -284,6 +287,11 @@ extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alph
     }
     (void)imap;
     return 0;
+}
+
+extern "C" void emu_pow_fast(const double *in, double *out, long long n, double alpha)
+{
+    for (long long i = 0; i < n; ++i) out[i] = pow_fast(in[i], alpha, dbspm_pow_table_h);
 }
 
 // plain 1-D FFT of T interleaved lines through the tile routine (plan / butterfly unit test)

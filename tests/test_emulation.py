@@ -90,6 +90,25 @@ def test_corr3d_distributed_x_slabs(emu, shape, window, G):
         assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, window, G, tshift)
 
 
+def test_pow_fast_accuracy(emu):
+    """The table-driven v**alpha of the powered first pass against numpy's pow in extended precision."""
+    rng = np.random.default_rng(11)
+    for alpha in (1.08, 1.12, 0.5, 2.0, 3.7):
+        for (lo, hi), tol in (((-12, 2), 3e-14), ((-300, 300), 3e-13)):
+            x = np.concatenate([10.0 ** rng.uniform(lo, hi, 50000), [1.0, 2.0, 0.5, np.nextafter(1, 2), np.nextafter(1, 0),
+                                                                     1 + 1 / 32, 1 + 1 / 64, 2.3e-308]])
+            ref = np.power(x.astype(np.longdouble), np.longdouble(alpha))
+            with np.errstate(over="ignore"):
+                ok = np.isfinite(ref.astype(np.float64)) & (ref > 1e-300)
+            got = emu.pow_fast(x, alpha)
+            assert float(np.abs((got[ok] - ref[ok]) / ref[ok]).max()) <= tol, (alpha, lo, hi)
+    # zero, negative, non-finite and subnormal inputs take the libm path: same values as numpy
+    x = np.array([0.0, -1.0, np.inf, np.nan, 5e-324, 1e-310])
+    with np.errstate(all="ignore"):
+        want = np.power(x, 1.08)
+    assert np.array_equal(emu.pow_fast(x, 1.08), want, equal_nan=True)
+
+
 def test_corr3d_tiny_config_window(emu, overlap_golden):
     from dbspm_b200 import synth
     cfg = synth.CONFIGS["tiny"]
