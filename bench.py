@@ -434,6 +434,8 @@ def run_gpu_arm(args):
         del rhoS, potS, rhoT, nrhoT, dev_src, inputs
         torch.cuda.empty_cache()
 
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
         def e2e_step(rec):
             e0 = ev()
             if groups is not None:
@@ -445,13 +447,27 @@ def run_gpu_arm(args):
                 for w, oh in zip(wins or [], outs_h):
                     oh.copy_(w, non_blocking=True)
             else:
-                for (which, zl, zh), buf, oh in zip(jobs, bufs, outs_h):
+                # uploads on a copy stream, results back on a third one: the sr compute and its download hide behind
+                # the upload of the es inputs (PCIe is full duplex); an interaction starts when its two arrays have landed
+                main = torch.cuda.current_stream()
+                s_in.wait_stream(main)
+                landed = []
+                with torch.cuda.stream(s_in):
+                    for (which, zl, zh) in jobs:
+                        na, nb, al = names[which]
+                        d_in[na].copy_(hosts[na], non_blocking=True)
+                        d_in[nb].copy_(hosts[nb], non_blocking=True)
+                        e_l = torch.cuda.Event(); e_l.record(s_in)
+                        landed.append(e_l)
+                for (which, zl, zh), buf, oh, e_l in zip(jobs, bufs, outs_h, landed):
                     na, nb, al = names[which]
-                    d_in[na].copy_(hosts[na], non_blocking=True)
-                    d_in[nb].copy_(hosts[nb], non_blocking=True)
+                    main.wait_event(e_l)
                     if zh > zl:
                         ops.density_overlap_window(d_in[na], d_in[nb], dr, zl, zh, al, al, out=buf)
-                    oh.copy_(buf, non_blocking=True)
+                    s_out.wait_stream(main)
+                    with torch.cuda.stream(s_out):
+                        oh.copy_(buf, non_blocking=True)
+                main.wait_stream(s_out)
             e1 = ev()
             d_in["vdw"].copy_(hosts["vdw"], non_blocking=True)
             if world == 1:
@@ -486,7 +502,8 @@ def run_gpu_arm(args):
                                         "inside the timed region; byte counts are rank 0's" if groups is not None else
                                         "per rank: pinned host -> HBM copies of the input grids of its interaction(s) "
                                         "+ vdw, its window slab(s) and relax tile copied back, all inside the timed "
-                                        "region; byte counts are per rank")}
+                                        "region (uploads, compute and downloads on three streams so that they overlap); "
+                                        "byte counts are per rank")}
 
     if rank != 0:
         if world > 1:

@@ -677,6 +677,8 @@ extern "C" int dbspm_corr3d_dist_supported(int nx, int ny, int nz, int G)
     int ts, tws;
     axis2_config(ny, nz / 2, hy.dev.nstages, &ts, &tws);
     if (axis2_smem_bytes(ny, ts, hy.dev.nstages, tws) > 227 * 1024) return 0;
+    axis2_config(nx, (long long)(ny / G) * (nz / 2), hx.dev.nstages, &ts, &tws);      // row-mapped inverse x pass of mid_peer
+    if (axis2_smem_bytes(nx, ts, hx.dev.nstages, tws) > 227 * 1024) return 0;
     if (zfused_smem_bytes(nz / 2) > 227 * 1024) return 0;
     return 1;
 }

@@ -226,7 +226,14 @@ HD double pow_fast_core(double v, double alpha, const double *tab)
     const double m = dbspm_ll2d((b & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL);
     // exponent as a double without a conversion instruction: (1.5 * 2^52 + e) - 1.5 * 2^52
     const double ed = dbspm_ll2d(0x4338000000000000LL + (long long)((hi >> 20) - 1023)) - 6755399441055744.0;
-    const double r = fma(m, tab[2 * i], -1.0);
+    // one 16-byte look-up for (invc_i, t_i): the table is 16-byte aligned in shared memory
+#if defined(__CUDA_ARCH__)
+    const double2 lt = *reinterpret_cast<const double2 *>(tab + 2 * i);
+    const double invc = lt.x, ti = lt.y;
+#else
+    const double invc = tab[2 * i], ti = tab[2 * i + 1];
+#endif
+    const double r = fma(m, invc, -1.0);
     double p = 0.2060992915555662;
     p = fma(p, r, -0.2404491734814939);
     p = fma(p, r, 0.28853900817779266);
@@ -234,7 +241,7 @@ HD double pow_fast_core(double v, double alpha, const double *tab)
     p = fma(p, r, 0.4808983469629878);
     p = fma(p, r, -0.7213475204444817);
     p = fma(p, r, 1.4426950408889634);
-    const double y = alpha * fma(p, r, tab[2 * i + 1] + ed);
+    const double y = alpha * fma(p, r, ti + ed);
     const double shifter = 211106232532992.0;                     // 1.5 * 2^47: one ulp = 2^-5
     const double z = y + shifter;
     const int ki = (int)(unsigned int)(dbspm_d2ll(z) & 0xFFFFFFFFLL);   // round(32 y), two's complement
