@@ -50,6 +50,7 @@ class Emu:
                                             C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]
         L.emu_corr3d_dist_f64.argtypes = [_dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, _dp, C.c_int, C.c_int]
+        L.emu_dist_row_of.argtypes = [C.c_int, C.c_int, C.c_int, C.c_longlong]
         L.emu_pow_fast.argtypes = [_dp, _dp, C.c_longlong, C.c_double]
         L.emu_fft_lines.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int]
         L.emu_fft_lines_t.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int]

@@ -289,6 +289,10 @@ extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alph
     return 0;
 }
 
+extern "C" int emu_dist_slot_of(int K, int n) { return dist_slot_of(K, n); }
+extern "C" int emu_dist_mirror_slot(int S) { return dist_mirror_slot(S); }
+extern "C" int emu_dist_row_of(int K, int n, int G, long long blockrows) { return dist_row_of(K, n, G, blockrows); }
+
 extern "C" void emu_pow_fast(const double *in, double *out, long long n, double alpha)
 {
     for (long long i = 0; i < n; ++i) out[i] = pow_fast(in[i], alpha, dbspm_pow_table_h);

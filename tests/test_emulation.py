@@ -90,6 +90,29 @@ def test_corr3d_distributed_x_slabs(emu, shape, window, G):
         assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, window, G, tshift)
 
 
+def test_slot_order_host_and_device_agree(emu):
+    """parallel.slot_order (host) and dist_slot_of / dist_mirror_slot / dist_row_of (kernels) describe the same deal of
+    y-frequencies: k and -k are slot neighbours, equal even blocks are closed under k -> -k."""
+    from dbspm_b200 import parallel
+    L = emu.L
+    for n in (2, 4, 6, 8, 20, 30, 196, 1024):
+        order = parallel.slot_order(n)
+        assert sorted(order) == list(range(n))
+        for S, K in enumerate(order):
+            assert L.emu_dist_slot_of(K, n) == S
+            assert order[L.emu_dist_mirror_slot(S)] == (n - K) % n
+        for G in (1, 2, 4, 5, 8):
+            if n % (2 * G):
+                continue
+            nl = n // G
+            for h in range(G):
+                block = {order[S] for S in range(h * nl, (h + 1) * nl)}
+                assert block == {(n - K) % n for K in block}            # closed under the mirror
+            for K in range(n):
+                S = L.emu_dist_slot_of(K, n)
+                assert L.emu_dist_row_of(K, n, G, 1000) == (S // nl) * 1000 + S % nl
+
+
 def test_pow_fast_accuracy(emu):
     """The table-driven v**alpha of the powered first pass against numpy's pow in extended precision."""
     rng = np.random.default_rng(11)
