@@ -121,6 +121,20 @@ def test_sass_is_sm100a_only():
     assert archs == {"sm_100a"}, archs
 
 
+def test_sass_has_the_async_machinery_the_design_claims():
+    """DESIGN.md names TMA tensor loads/stores (axis_tma_kernel), the bulk L2 prefetch of the z kernel and the L2
+    prefetch of the y passes; their SASS mnemonics must be in the shipped library, and so must the distributed kernels."""
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    sass = out.stdout
+    for mnemonic in ("UTMALDG", "UTMASTG", "UBLKPF.L2", "CCTL.E.PF2", "DFMA"):
+        assert mnemonic in sass, mnemonic
+    for kernel in ("axis_pass2_kernel", "axis_pass2w_kernel", "axis_pass2m_kernel", "axis_pass2p_kernel", "axis_pass2pw_kernel",
+                   "axis_tma_kernel", "zfused2_kernel", "relax_kernel"):
+        assert kernel in sass, kernel
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "dbspm_b200")
     for dirpath, _, files in os.walk(pkg):
