@@ -41,6 +41,11 @@ _SIGNATURES = {
                                             _vp, _vp, C.c_int, _vp]),
     "dbspm_corr3d_dist_fwd_peer_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.c_int, C.POINTER(_vp), C.c_int, _vp]),
+    "dbspm_corr3d_pruned_geometry": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int)]),
+    "dbspm_corr3d_dist_fwd_cut_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.POINTER(C.c_int), _vp, _vp, C.c_int, _vp]),
+    "dbspm_corr3d_dist_fwd_peer_cut_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                     C.c_int, C.POINTER(C.c_int), C.POINTER(_vp), C.c_int, _vp]),
     "dbspm_corr3d_dist_mid_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_int, _vp, C.c_int, _vp]),
     "dbspm_corr3d_dist_mid_peer_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

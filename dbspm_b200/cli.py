@@ -108,11 +108,14 @@ def main(argv=None) -> int:
         def slab(zl, zh):
             return ops.density_overlap_window(a, b, calc.gridS.dr, zl, zh, alpha, alpha, tip_support=support)
 
-        if world > 1 and support is None and ops.dist_supported(a.shape, world):
-            # the transform itself is distributed: this rank transforms its x-slab, one exchange, gather to rank 0
+        cut = ops.pruned_cut(a.shape[2], z_lo, z_hi, support)
+        nz_problem = cut[1] if cut is not None else a.shape[2]
+        if world > 1 and ops.dist_supported((a.shape[0], a.shape[1], nz_problem), world):
+            # the transform itself is distributed: this rank transforms its x-slab (only the z-ranges the window can see
+            # when the tip is compact), exchange, gather to rank 0
             x0, x1 = parallel.x_slab(nx, world, rank)
             wins = parallel.sr_es_distributed(ops, a[x0:x1], b[x0:x1], alpha, tuple(a.shape), calc.gridS.dr, z_lo, z_hi,
-                                              [list(range(world))])
+                                              [list(range(world))], tip_support=support)
             win = wins[0] if rank == 0 else None
         else:
             win = parallel.corr3d_sharded(slab, nx, ny, z_lo, z_hi, device)

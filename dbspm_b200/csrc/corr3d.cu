@@ -360,7 +360,7 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     P.in_map = P.out_map = nullptr;
     P.in_ostride = P.out_ostride = (long long)n * inner;
     if (mp) {
-        DBSPM_REQUIRE(!g && axis_v2_ok(pl->host.dev), DBSPM_EUNSUPPORTED, "row-mapped pass needs an all-fast-radix plan (n=%d)", n);
+        DBSPM_REQUIRE(axis_v2_ok(pl->host.dev), DBSPM_EUNSUPPORTED, "row-mapped pass needs an all-fast-radix plan (n=%d)", n);
         P.in_map = mp->in_map; P.out_map = mp->out_map;
         if (mp->in_ostride) P.in_ostride = mp->in_ostride;
         if (mp->out_ostride) P.out_ostride = mp->out_ostride;
@@ -683,11 +683,43 @@ extern "C" int dbspm_corr3d_dist_supported(int nx, int ny, int nz, int G)
     return 1;
 }
 
-extern "C" int dbspm_corr3d_dist_fwd_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
-                                         int nxl, int ny, int nz, int G, void *sendA, void *sendB, int flags, void *stream)
+// geometry of the z-pruned problem (compact tip), for the callers of the *_cut_f64 entries:
+// out = {use, Mp, zA0, zB0, validA, validB, w_lo} (corr_body.h, pruned_geometry)
+extern "C" int dbspm_corr3d_pruned_geometry(int nz, int z_lo, int z_hi, int s_lo, int s_len, int *out)
+{
+    DBSPM_REQUIRE(out, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(nz >= 1 && z_lo >= 0 && z_hi > z_lo && z_hi <= nz && s_len >= 1 && s_len <= nz, DBSPM_EINVAL,
+                  "bad window [%d,%d) / support length %d for nz=%d", z_lo, z_hi, s_len, nz);
+    const PrunedGeom G = pruned_geometry(nz, z_lo, z_hi, s_lo, s_len);
+    out[0] = G.use; out[1] = G.Mp; out[2] = G.zA0; out[3] = G.zB0; out[4] = G.validA; out[5] = G.validB; out[6] = G.w_lo;
+    return DBSPM_OK;
+}
+
+// cut (nullable): the forward y pass reads the z-ranges of the pruned problem in place (as the pruned x pass of
+// dbspm_corr3d_pruned_f64 does) and writes spectra of z length Mp = cut[1]; everything downstream runs with nz = Mp
+static int dist_cut_spec(const int *cut, int nz_src, GatherSpec *g, int *nz_problem)
+{
+    *nz_problem = nz_src;
+    if (!cut) return 0;
+    DBSPM_REQUIRE(cut[0] == 1 && cut[1] >= 2 && (cut[1] & 1) == 0 && cut[1] <= nz_src && (nz_src & 1) == 0 &&
+                  cut[2] >= 0 && cut[3] >= 0 && cut[4] >= 0 && cut[5] >= 0 && cut[4] <= cut[1] && cut[5] <= cut[1] &&
+                  !((cut[2] | cut[3] | cut[4] | cut[5]) & 1), DBSPM_EINVAL, "bad z-range cut");
+    g->src_nz = nz_src; g->dst_nz = cut[1];
+    g->z0[0] = cut[2]; g->z0[1] = cut[3]; g->valid[0] = cut[4]; g->valid[1] = cut[5];
+    *nz_problem = cut[1];
+    return 1;
+}
+
+extern "C" int dbspm_corr3d_dist_fwd_cut_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
+                                             int nxl, int ny, int nz_src, int G, const int *cut, void *sendA, void *sendB,
+                                             int flags, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     DBSPM_REQUIRE(A_slab && B_slab && sendA && sendB, DBSPM_EINVAL, "null pointer argument");
+    GatherSpec gs;
+    int nz = nz_src;
+    const int has_cut = dist_cut_spec(cut, nz_src, &gs, &nz);
+    if (has_cut < 0) return has_cut;
     DBSPM_REQUIRE(dist_shape_ok(nxl * G, ny, nz, G), DBSPM_EUNSUPPORTED,
                   "distributed correlation needs even nz, ny %% (2G) == 0 (got slab %d x %d x %d, G=%d)", nxl, ny, nz, G);
     DBSPM_REQUIRE(((uintptr_t)A_slab & 15) == 0 && ((uintptr_t)B_slab & 15) == 0 && ((uintptr_t)sendA & 15) == 0 &&
@@ -700,16 +732,27 @@ extern "C" int dbspm_corr3d_dist_fwd_f64(const double *A_slab, const double *B_s
     mp.in_map = nullptr; mp.out_map = omap; mp.in_ostride = 0; mp.out_ostride = (long long)nyl * n;
     mp.npeers = 0; mp.out_base_off = 0;
     return launch_axis<-1>((const cplx *)A_slab, (cplx *)sendA, (const cplx *)B_slab, (cplx *)sendB, 2, alphaA, alphaB, 1,
-                           ny, n, nxl, st, flags, nullptr, &mp);
+                           ny, n, nxl, st, flags, has_cut ? &gs : nullptr, &mp);
+}
+
+extern "C" int dbspm_corr3d_dist_fwd_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
+                                         int nxl, int ny, int nz, int G, void *sendA, void *sendB, int flags, void *stream)
+{
+    return dbspm_corr3d_dist_fwd_cut_f64(A_slab, B_slab, alphaA, alphaB, nxl, ny, nz, G, nullptr, sendA, sendB, flags, stream);
 }
 
 // fused exchange: the y pass of rank `me` stores every row straight into its owner's receive buffer
 // peer_recv[h] = rank h's (2, nx, ny/G, nz/2) complex buffer (A then B), mapped into this process (symmetric memory)
-extern "C" int dbspm_corr3d_dist_fwd_peer_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
-                                              int nxl, int ny, int nz, int G, int me, void *const *peer_recv, int flags, void *stream)
+extern "C" int dbspm_corr3d_dist_fwd_peer_cut_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
+                                                  int nxl, int ny, int nz_src, int G, int me, const int *cut,
+                                                  void *const *peer_recv, int flags, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     DBSPM_REQUIRE(A_slab && B_slab && peer_recv, DBSPM_EINVAL, "null pointer argument");
+    GatherSpec gs;
+    int nz = nz_src;
+    const int has_cut = dist_cut_spec(cut, nz_src, &gs, &nz);
+    if (has_cut < 0) return has_cut;
     DBSPM_REQUIRE(dist_shape_ok(nxl * G, ny, nz, G) && G <= DBSPM_MAX_PEERS && me >= 0 && me < G, DBSPM_EUNSUPPORTED,
                   "fused exchange needs even nz, ny %% (2G) == 0, G <= %d (got slab %d x %d x %d, rank %d of %d)",
                   DBSPM_MAX_PEERS, nxl, ny, nz, me, G);
@@ -727,7 +770,13 @@ extern "C" int dbspm_corr3d_dist_fwd_peer_f64(const double *A_slab, const double
         mp.peer[1][h] = (cplx *)peer_recv[h] + (size_t)nx * nyl * n;
     }
     return launch_axis<-1>((const cplx *)A_slab, mp.peer[0][me], (const cplx *)B_slab, mp.peer[1][me], 2, alphaA, alphaB, 1,
-                           ny, n, nxl, st, flags, nullptr, &mp);
+                           ny, n, nxl, st, flags, has_cut ? &gs : nullptr, &mp);
+}
+
+extern "C" int dbspm_corr3d_dist_fwd_peer_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
+                                              int nxl, int ny, int nz, int G, int me, void *const *peer_recv, int flags, void *stream)
+{
+    return dbspm_corr3d_dist_fwd_peer_cut_f64(A_slab, B_slab, alphaA, alphaB, nxl, ny, nz, G, me, nullptr, peer_recv, flags, stream);
 }
 
 extern "C" int dbspm_corr3d_dist_mid_f64(void *recvA, void *recvB, double dV, int nx, int ny, int nz, int G, int h,

@@ -49,6 +49,7 @@ struct AxisParams {
     // z-pruned correlation (v2 body, first pass only): the pass reads a z-range of the caller's arrays
     // instead of a packed copy.  Destination line (y, zp) with zp < g_valid[w] comes from source column
     // y*g_src_nzh + (g_zp0[w] + zp) mod g_src_nzh, row stride g_src_inner; zp >= g_valid[w] reads as zero.
+    // Slab o of the source starts at o * n * g_src_inner (the distributed y pass: n = ny, lines are zp only).
     int gather;
     long long g_src_inner;
     int g_dst_nzh, g_src_nzh;
@@ -354,7 +355,7 @@ HD void axis2_config(int n, long long inner, int nstages, int *tshift, int *tw_s
 
 template <int D, int R, int MAP>
 HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gin, cplx *gout, int tcount,
-                    bool do_pow, double alpha, const double *ptab, int which, long long i0, int tid, int nthr)
+                    bool do_pow, double alpha, const double *ptab, int which, long long i0, size_t gbase, int tid, int nthr)
 {
     const int n = P.n, q = n / R, tmask = (1 << P.tshift) - 1;
     const bool single = P.plan.nstages == 1;
@@ -372,7 +373,7 @@ HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gi
             zs = zs >= P.g_src_nzh ? zs - P.g_src_nzh : zs;
             have = zp < P.g_valid[which];
             rstride = (size_t)P.g_src_inner;
-            src = P.in[which] + ((size_t)y * P.g_src_nzh + zs) + (size_t)j * rstride;
+            src = P.in[which] + gbase + ((size_t)y * P.g_src_nzh + zs) + (size_t)j * rstride;
         }
         if (have) {
             if (MAP && P.in_map) {
@@ -502,7 +503,10 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
             for (int e = tid; e < n; e += nthr) twbuf[e] = ldg_c(P.tw + e);
         BLOCK_SYNC();
     }
-#define CALL_(R) axis2_first<D, R, MAP>(P, s, tw, gin, gout, tcount, do_pow, alpha, ptab, which, i0, tid, nthr)
+    // z-range cut (gather): slab o of the source starts o * n source rows further (x pass: one slab; distributed y pass:
+    // one slab per x of the rank's x-slab)
+    const size_t gbase = P.gather ? (size_t)o * n * (size_t)P.g_src_inner : 0;
+#define CALL_(R) axis2_first<D, R, MAP>(P, s, tw, gin, gout, tcount, do_pow, alpha, ptab, which, i0, gbase, tid, nthr)
     DBSPM_FAST_RADIX_SWITCH(pl.radix[0], CALL_)
 #undef CALL_
     if (pl.nstages == 1) return;

@@ -163,23 +163,42 @@ def dist_supported(shape, G: int) -> bool:
     return bool(_lib.lib().dbspm_corr3d_dist_supported(nx, ny, nz, int(G)))
 
 
-def dist_forward(a_slab, b_slab, G, alpha0=1.0, alpha1=1.0, out=None, flags=0):
+def pruned_cut(nz, z_lo, z_hi, tip_support):
+    """Geometry of the z-pruned problem for a tip that is zero outside tip_support = (s_lo, s_len): None when pruning
+    does not pay (or tip_support is None), else the 7-int `cut` of include/dbspm_b200.h:
+    (use, Mp, zA0, zB0, validA, validB, w_lo)."""
+    if tip_support is None or int(nz) % 2:
+        return None
+    s_lo, s_len = (int(v) for v in tip_support)
+    cut = (C.c_int * 7)()
+    _lib.check(_lib.lib().dbspm_corr3d_pruned_geometry(int(nz), int(z_lo), int(z_hi), s_lo, s_len, cut))
+    return tuple(int(v) for v in cut) if cut[0] else None
+
+
+def _cut_arg(cut):
+    return (C.c_int * 7)(*[int(v) for v in cut]) if cut is not None else None
+
+
+def dist_forward(a_slab, b_slab, G, alpha0=1.0, alpha1=1.0, out=None, flags=0, cut=None):
     """y transform of this rank's x-slab (nxl,ny,nz) of both arrays, power fused, written destination-major:
-    returns (sendA, sendB), each (G, nxl, ny/G, nz) float64 = complex (.., nz/2); block h goes to rank h."""
+    returns (sendA, sendB), each (G, nxl, ny/G, nz) float64 = complex (.., nz/2); block h goes to rank h.
+    cut (pruned_cut): the pass reads the z-ranges of the pruned problem in place; nz of the buffers = cut[1]."""
     dev = a_slab.device
     a, b = _to_dev(a_slab, dev), _to_dev(b_slab, dev)
     nxl, ny, nz = (int(v) for v in a.shape)
     G = int(G)
+    nzp = int(cut[1]) if cut is not None else nz
     if out is None:
-        out = (torch.empty((G, nxl, ny // G, nz), dtype=torch.float64, device=dev),
-               torch.empty((G, nxl, ny // G, nz), dtype=torch.float64, device=dev))
+        out = (torch.empty((G, nxl, ny // G, nzp), dtype=torch.float64, device=dev),
+               torch.empty((G, nxl, ny // G, nzp), dtype=torch.float64, device=dev))
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().dbspm_corr3d_dist_fwd_f64(a.data_ptr(), b.data_ptr(), float(alpha0), float(alpha1), nxl, ny, nz,
-                                                        G, out[0].data_ptr(), out[1].data_ptr(), int(flags), _stream_ptr(dev)))
+        _lib.check(_lib.lib().dbspm_corr3d_dist_fwd_cut_f64(a.data_ptr(), b.data_ptr(), float(alpha0), float(alpha1), nxl, ny, nz,
+                                                            G, _cut_arg(cut), out[0].data_ptr(), out[1].data_ptr(), int(flags),
+                                                            _stream_ptr(dev)))
     return out
 
 
-def dist_forward_peer(a_slab, b_slab, G, me, peer_ptrs, alpha0=1.0, alpha1=1.0, flags=0):
+def dist_forward_peer(a_slab, b_slab, G, me, peer_ptrs, alpha0=1.0, alpha1=1.0, flags=0, cut=None):
     """dist_forward fused with the exchange: every output row is stored straight into its owner's receive buffer.
     peer_ptrs[h] = device address (int) of rank h's (2, nx, ny/G, nz) float64 receive buffer mapped into this process
     (torch symmetric memory).  The caller brackets the call with two group barriers."""
@@ -188,8 +207,9 @@ def dist_forward_peer(a_slab, b_slab, G, me, peer_ptrs, alpha0=1.0, alpha1=1.0, 
     nxl, ny, nz = (int(v) for v in a.shape)
     ptrs = (C.c_void_p * int(G))(*[int(p) for p in peer_ptrs])
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().dbspm_corr3d_dist_fwd_peer_f64(a.data_ptr(), b.data_ptr(), float(alpha0), float(alpha1), nxl, ny, nz,
-                                                             int(G), int(me), ptrs, int(flags), _stream_ptr(dev)))
+        _lib.check(_lib.lib().dbspm_corr3d_dist_fwd_peer_cut_f64(a.data_ptr(), b.data_ptr(), float(alpha0), float(alpha1), nxl, ny,
+                                                                 nz, int(G), int(me), _cut_arg(cut), ptrs, int(flags),
+                                                                 _stream_ptr(dev)))
 
 
 def dist_middle(recvA, recvB, dr, shape, G, h, z_lo, z_hi, out=None, flags=0):

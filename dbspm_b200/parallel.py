@@ -213,7 +213,7 @@ def peer_receive_buffer(shape, G: int, pg, device):
 
 
 def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, groups, dst: int = 0, on_stage=None,
-                      peer: bool = True):
+                      peer: bool = True, tip_support=None):
     """The distributed sr / es step (replaces the rank-0-only dbspm:320-352).
 
     groups[i] = the G ranks that compute interaction i; this rank, member h of its group, passes the x-slab
@@ -223,10 +223,20 @@ def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, grou
     peer stores when symmetric memory is available, else one all-to-all per array), a second, small all-to-all of the
     packed window rows back to x-slabs (so the final inverse y pass is distributed as well), and one gather of the
     finished real slabs into place on rank `dst`.  Returns the list of (nx,ny,nzw) windows on `dst`, None elsewhere.
-    on_stage(name) is called after each stage has been enqueued (bench.py records a CUDA event there)."""
+    on_stage(name) is called after each stage has been enqueued (bench.py records a CUDA event there).
+    tip_support = (s_lo, s_len): the caller's claim that the second array is exactly zero outside those z-planes
+    (interactions.tip_zsupport); when pruning pays, the forward pass reads only the z-ranges the window can see and
+    every later stage runs on the shorter z length (same result, see dbspm_corr3d_pruned_f64)."""
     mark = on_stage or (lambda name: None)
     rank, world = _world()
     G = len(groups[0])
+    cut = stages.pruned_cut(shape[2], z_lo, z_hi, tip_support) if (tip_support is not None and hasattr(stages, "pruned_cut")) else None
+    kw = {}
+    if cut is not None:
+        # the pruned problem: z length Mp, window at [w_lo, w_lo + nzw)
+        kw = {"cut": cut}
+        shape = (int(shape[0]), int(shape[1]), int(cut[1]))
+        z_lo, z_hi = int(cut[6]), int(cut[6]) + (int(z_hi) - int(z_lo))
     which = next(i for i, g in enumerate(groups) if rank in g)
     h = groups[which].index(rank)
     pg = _process_groups(groups)[which]
@@ -237,13 +247,13 @@ def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, grou
         buf, hdl = symm
         hdl.barrier(channel=0)
         stages.dist_forward_peer(a_slab, b_slab, G, h, hdl.buffer_ptrs, alpha, alpha,
-                                 flags=int(os.environ.get("DBSPM_DIST_FLAGS", "0")))
+                                 flags=int(os.environ.get("DBSPM_DIST_FLAGS", "0")), **kw)
         mark("fwd")
         hdl.barrier(channel=1)
         recvA, recvB = buf[0], buf[1]
         mark("a2a")
     else:
-        sendA, sendB = stages.dist_forward(a_slab, b_slab, G, alpha, alpha)
+        sendA, sendB = stages.dist_forward(a_slab, b_slab, G, alpha, alpha, **kw)
         recvA, recvB = torch.empty_like(sendA), torch.empty_like(sendB)
         mark("fwd")
         dist.all_to_all_single(recvA, sendA, group=pg)

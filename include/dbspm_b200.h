@@ -118,6 +118,17 @@ int dbspm_corr3d_dist_fwd_f64(const double *A_slab, const double *B_slab, double
  * call with two group barriers: every rank has finished reading its buffer / every rank's stores have landed.      */
 int dbspm_corr3d_dist_fwd_peer_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
                                    int nxl, int ny, int nz, int G, int me, void *const *peer_recv, int flags, void *stream);
+/* Compact tip on the distributed path: the forward y pass reads the z-ranges of the pruned problem in place (as
+ * dbspm_corr3d_pruned_f64 does in its x pass) and writes spectra of z length Mp.  dbspm_corr3d_pruned_geometry fills
+ * cut = {use, Mp, zA0, zB0, validA, validB, w_lo}; with use == 1 pass `cut` to a *_cut_f64 entry (buffers sized with Mp
+ * instead of nz) and run mid / fin with nz = Mp and the window [w_lo, w_lo + z_hi - z_lo).  cut == NULL: full length. */
+int dbspm_corr3d_pruned_geometry(int nz, int z_lo, int z_hi, int s_lo, int s_len, int *cut /* 7 ints */);
+int dbspm_corr3d_dist_fwd_cut_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
+                                  int nxl, int ny, int nz_src, int G, const int *cut, void *sendA, void *sendB,
+                                  int flags, void *stream);
+int dbspm_corr3d_dist_fwd_peer_cut_f64(const double *A_slab, const double *B_slab, double alphaA, double alphaB,
+                                       int nxl, int ny, int nz_src, int G, int me, const int *cut,
+                                       void *const *peer_recv, int flags, void *stream);
 int dbspm_corr3d_dist_mid_f64(void *recvA, void *recvB, double dV, int nx, int ny, int nz, int G, int h,
                               int z_lo, int z_hi, void *W_local, int flags, void *stream);
 /* Step 3 with a second, small exchange fused into its inverse x pass: row x of the packed window is stored straight into

@@ -50,6 +50,8 @@ class Emu:
                                             C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]
         L.emu_corr3d_dist_f64.argtypes = [_dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, _dp, C.c_int, C.c_int]
+        L.emu_corr3d_dist_pruned_f64.argtypes = [_dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                                 C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_int]
         L.emu_dist_row_of.argtypes = [C.c_int, C.c_int, C.c_int, C.c_longlong]
         L.emu_pow_fast.argtypes = [_dp, _dp, C.c_longlong, C.c_double]
         L.emu_fft_lines.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int]
@@ -88,6 +90,18 @@ class Emu:
         if rc:
             raise RuntimeError(f"emu_corr3d_dist_f64 -> {rc}")
         return out
+
+    def corr3d_dist_pruned(self, a, b, dr, z_lo, z_hi, s_lo, s_len, G, alpha0=1.0, alpha1=1.0, tshift=-1):
+        """-> (window, z length actually transformed) of the distributed step with a compact tip"""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        nx, ny, nz = a.shape
+        out = np.empty((nx, ny, z_hi - z_lo))
+        rc = self.L.emu_corr3d_dist_pruned_f64(self._p(a), self._p(b), alpha0, alpha1, float(np.prod(dr)), nx, ny, nz,
+                                               z_lo, z_hi, s_lo, s_len, self._p(out), G, tshift)
+        if rc < 0:
+            raise RuntimeError(f"emu_corr3d_dist_pruned_f64 -> {rc}")
+        return out, rc
 
     def pow_fast(self, x, alpha):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -197,13 +197,15 @@ extern "C" int emu_corr3d_pruned_f64(const double *A, const double *B, double al
 
 // what parallel.corr3d_distributed does with G ranks, run serially: dbspm_corr3d_dist_fwd_f64 per rank, the
 // all-to-all as plain block copies, dbspm_corr3d_dist_mid_f64 per rank, the gather, dbspm_corr3d_dist_fin_f64
-extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
-                                   int nx, int ny, int nz, int z_lo, int z_hi, double *E_win, int G, int force_tshift)
+// cut (nullable): the z-range cut of the pruned problem (compact tip); nz_src = z length of the caller's arrays
+static int emu_dist_core(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                         int nx, int ny, int nz_src, int nz, int z_lo, int z_hi, double *E_win, int G, int force_tshift,
+                         const EmuGather *cut)
 {
     const bool peer = force_tshift >= 1000;          // fused exchange: the y pass stores into the owners' buffers
     if (peer) force_tshift -= 1001;
     if (!dist_shape_ok(nx, ny, nz, G) || (peer && G > DBSPM_MAX_PEERS)) return -3;
-    const int n = nz / 2, nxl = nx / G, nyl = ny / G, nzw = z_hi - z_lo, nwh = (nzw + 1) / 2;
+    const int n = nz / 2, nsrc = nz_src / 2, nxl = nx / G, nyl = ny / G, nzw = z_hi - z_lo, nwh = (nzw + 1) / 2;
     const size_t blk = (size_t)nxl * nyl * n;                     // one (source, destination) block of the exchange
     std::vector<std::vector<cplx>> sendA(G), sendB(G), recvA(G), recvB(G);
     std::vector<int> omap(ny), imap(ny);
@@ -214,16 +216,16 @@ extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alph
     std::vector<std::vector<cplx>> recvAB(G);                      // peer mode: rank h's (2, nx, nyl, n) receive buffer
     if (peer) for (int h = 0; h < G; ++h) recvAB[h].assign(2 * blk * G, cmake(0, 0));
     for (int g = 0; g < G; ++g) {
-        const cplx *As = (const cplx *)A + (size_t)g * nxl * ny * n, *Bs = (const cplx *)B + (size_t)g * nxl * ny * n;
+        const cplx *As = (const cplx *)A + (size_t)g * nxl * ny * nsrc, *Bs = (const cplx *)B + (size_t)g * nxl * ny * nsrc;
         if (peer) {
             EmuMap mp = {nullptr, pmap.data(), 0, (long long)nyl * n, G, {}, (long long)g * nxl * nyl * n};
             for (int h = 0; h < G; ++h) { mp.peer[0][h] = recvAB[h].data(); mp.peer[1][h] = recvAB[h].data() + blk * G; }
-            if ((rc = run_axis<-1>(As, mp.peer[0][g], Bs, mp.peer[1][g], 2, alphaA, alphaB, 1, ny, n, nxl, force_tshift, nullptr, &mp))) return rc;
+            if ((rc = run_axis<-1>(As, mp.peer[0][g], Bs, mp.peer[1][g], 2, alphaA, alphaB, 1, ny, n, nxl, force_tshift, cut, &mp))) return rc;
             continue;
         }
         sendA[g].assign(blk * G, cmake(0, 0)); sendB[g].assign(blk * G, cmake(0, 0));
         EmuMap mp = {nullptr, omap.data(), 0, (long long)nyl * n, 0, {}, 0};
-        if ((rc = run_axis<-1>(As, sendA[g].data(), Bs, sendB[g].data(), 2, alphaA, alphaB, 1, ny, n, nxl, force_tshift, nullptr, &mp))) return rc;
+        if ((rc = run_axis<-1>(As, sendA[g].data(), Bs, sendB[g].data(), 2, alphaA, alphaB, 1, ny, n, nxl, force_tshift, cut, &mp))) return rc;
     }
     for (int h = 0; h < G; ++h) {                                  // all-to-all: block h of rank g -> block g of rank h
         recvA[h].resize(blk * G); recvB[h].resize(blk * G);
@@ -287,6 +289,28 @@ extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alph
     }
     (void)imap;
     return 0;
+}
+
+extern "C" int emu_corr3d_dist_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                                   int nx, int ny, int nz, int z_lo, int z_hi, double *E_win, int G, int force_tshift)
+{
+    return emu_dist_core(A, B, alphaA, alphaB, dV, nx, ny, nz, nz, z_lo, z_hi, E_win, G, force_tshift, nullptr);
+}
+
+// the distributed step for a tip that is zero outside (s_lo, s_len): returns the z length transformed, < 0 on error
+extern "C" int emu_corr3d_dist_pruned_f64(const double *A, const double *B, double alphaA, double alphaB, double dV,
+                                          int nx, int ny, int nz, int z_lo, int z_hi, int s_lo, int s_len, double *E_win,
+                                          int G, int force_tshift)
+{
+    const PrunedGeom P = pruned_geometry(nz, z_lo, z_hi, s_lo, s_len);
+    if (!P.use) {
+        const int rc = emu_dist_core(A, B, alphaA, alphaB, dV, nx, ny, nz, nz, z_lo, z_hi, E_win, G, force_tshift, nullptr);
+        return rc ? rc : nz;
+    }
+    EmuGather g;
+    g.src_nz = nz; g.dst_nz = P.Mp; g.z0[0] = P.zA0; g.z0[1] = P.zB0; g.valid[0] = P.validA; g.valid[1] = P.validB;
+    const int rc = emu_dist_core(A, B, alphaA, alphaB, dV, nx, ny, nz, P.Mp, P.w_lo, P.w_lo + (z_hi - z_lo), E_win, G, force_tshift, &g);
+    return rc ? rc : P.Mp;
 }
 
 extern "C" int emu_dist_slot_of(int K, int n) { return dist_slot_of(K, n); }

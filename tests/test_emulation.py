@@ -90,6 +90,28 @@ def test_corr3d_distributed_x_slabs(emu, shape, window, G):
         assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, window, G, tshift)
 
 
+@pytest.mark.parametrize("shape,window,support,G", [
+    ((8, 8, 64), (20, 30), (60, 9), 2), ((6, 12, 48), (10, 22), (44, 8), 3), ((8, 16, 40), (3, 9), (0, 5), 4),
+    ((4, 8, 32), (0, 32), (30, 4), 2), ((12, 8, 96), (40, 61), (90, 13), 2), ((8, 8, 64), (20, 30), (60, 9), 1),
+])
+def test_corr3d_distributed_pruned_equals_full_correlation(emu, shape, window, support, G):
+    """Compact tip on the distributed path: the forward y pass reads the z-ranges of the pruned problem in place, all
+    later stages run on the shorter z length; same window as the full periodic correlation."""
+    rng = np.random.default_rng(sum(shape) + window[0] + G)
+    nz = shape[2]
+    a = rng.random(shape)
+    b = np.zeros(shape)
+    s_lo, s_len = support
+    planes = (s_lo + np.arange(s_len)) % nz
+    b[:, :, planes] = rng.random(shape[:2] + (s_len,)) + 0.1
+    dr = np.array([0.1, 0.2, 0.3])
+    ref = O.density_overlap_fft(a ** 1.08, b ** 1.08, dr)[:, :, window[0]:window[1]]
+    for tshift in (-1, 0, 1000):
+        got, used = emu.corr3d_dist_pruned(a, b, dr, window[0], window[1], s_lo, s_len, G, alpha0=1.08, alpha1=1.08, tshift=tshift)
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, G, tshift)
+        assert (used == nz) == (shape == (4, 8, 32)), used          # the full window of (4,8,32) cannot be pruned
+
+
 def test_slot_order_host_and_device_agree(emu):
     """parallel.slot_order (host) and dist_slot_of / dist_mirror_slot / dist_row_of (kernels) describe the same deal of
     y-frequencies: k and -k are slot neighbours, equal even blocks are closed under k -> -k."""
