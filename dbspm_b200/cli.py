@@ -108,8 +108,10 @@ def main(argv=None) -> int:
         def slab(zl, zh):
             return ops.density_overlap_window(a, b, calc.gridS.dr, zl, zh, alpha, alpha, tip_support=support)
 
-        cut = ops.pruned_cut(a.shape[2], z_lo, z_hi, support)
-        nz_problem = cut[1] if cut is not None else a.shape[2]
+        nz_problem = a.shape[2]
+        if world > 1:
+            cut = ops.pruned_cut(a.shape[2], z_lo, z_hi, support)
+            nz_problem = cut[1] if cut is not None else a.shape[2]
         if world > 1 and ops.dist_supported((a.shape[0], a.shape[1], nz_problem), world):
             # the transform itself is distributed: this rank transforms its x-slab (only the z-ranges the window can see
             # when the tip is compact), exchange, gather to rank 0
