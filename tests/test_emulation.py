@@ -112,6 +112,38 @@ def test_corr3d_distributed_pruned_equals_full_correlation(emu, shape, window, s
         assert (used == nz) == (shape == (4, 8, 32)), used          # the full window of (4,8,32) cannot be pruned
 
 
+def test_corr3d_distributed_random_shapes(emu):
+    """Property test (hypothesis): for random 2-3-5-7-smooth shapes, rank counts, windows and tile widths the distributed
+    step -- with all-to-alls or with both exchanges fused as peer stores -- equals the reference's periodic correlation."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    smooth = [v for v in range(1, 33) if all(v % p for p in (11, 13, 17, 19, 23, 29, 31))]
+
+    @st.composite
+    def cases(draw):
+        G = draw(st.sampled_from([1, 2, 3, 4, 5, 8]))
+        nx = G * draw(st.sampled_from([v for v in smooth if v * G <= 40]))
+        ny = 2 * G * draw(st.sampled_from([v for v in smooth if 2 * v * G <= 48]))
+        nz = 2 * draw(st.sampled_from([v for v in smooth if v <= 16]))
+        z_lo = draw(st.integers(0, nz - 1))
+        z_hi = draw(st.integers(z_lo + 1, nz))
+        ts = draw(st.sampled_from([-1, 0, 1, 2, 1000, 1001, 1003]))
+        return G, (nx, ny, nz), (z_lo, z_hi), ts
+
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
+    @given(cases())
+    def run(case):
+        G, shape, (z_lo, z_hi), ts = case
+        rng = np.random.default_rng(sum(shape) * 7 + G)
+        a, b = rng.random(shape), rng.random(shape) - 0.4
+        dr = np.array([0.1, 0.2, 0.3])
+        ref = O.density_overlap_fft(a ** 1.08, b, dr)[:, :, z_lo:z_hi]
+        got = emu.corr3d_dist(a, b, dr, z_lo, z_hi, G, alpha0=1.08, tshift=ts)
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), case
+
+    run()
+
+
 def test_slot_order_host_and_device_agree(emu):
     """parallel.slot_order (host) and dist_slot_of / dist_mirror_slot / dist_row_of (kernels) describe the same deal of
     y-frequencies: k and -k are slot neighbours, equal even blocks are closed under k -> -k."""
