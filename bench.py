@@ -6,7 +6,11 @@
 One step = one pass of the hot path over the workload: sr (alpha-powered overlap), es,
 static = V*sr + es + vdw, relax of every tip position.  Default workload = BASELINE.json
 configs[4], the 1024x1024x256 slab (it fits one GPU, so N = 1, 2, 4, 8 all run it: strong
-scaling; sr/es shard by window z-slab, relax by lateral x-tile, NCCL only gathers).
+scaling).  N = 2: one rank per interaction.  N >= 4: an sr group and an es group; inside a group
+the transform itself is distributed over x-slabs (parallel.sr_es_distributed: both exchanges
+fused into the passes as peer stores over NVLink, gather of the finished slabs to rank 0; the
+assembled es window is checked against the single-GPU path once per run).  relax shards by
+lateral x-tile; NCCL gathers.
 Timed with CUDA events on the launching stream (torch's current stream), max over ranks.
 The arrays (2.1 GB each) are far larger than the 126 MB L2, so no explicit flush is needed.
 
