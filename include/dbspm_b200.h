@@ -154,7 +154,7 @@ int dbspm_static_accumulate_f64(double *acc, const double *comp, double scale, s
  * inv(dR^T).(x,y,z); NULL selects the orthogonal path.
  * out_E_theta_phi: (ni,nj,nz_relax,3) rows [E_min, theta, phi]
  * out_cart:        (3,ni,nj,nz_relax) tip_x, tip_y, tip_z = sph2cart(theta, phi, rpivot); nullable
- * out_nfev:        (ni,nj,nz_relax) objective evaluations per position; nullable
+ * out_nfev:        (ni,nj,nz_relax) objective evaluations per position; nullable           */
 int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
                            int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
                            double kappa, double rpivot, const double dr[3], const double *dR,

@@ -98,10 +98,65 @@ def test_npz_layout_roundtrip(tmp_path):
         Grid((4, 4, 4), cell=np.array([[1.0, 0, 0.2], [0, 1, 0], [0, 0, 1]]))   # z not orthogonal
 
 
-def test_library_loads_and_exports_every_declared_symbol():
-    header = open(os.path.join(ROOT, "include", "dbspm_b200.h")).read()
-    declared = set(re.findall(r"\b(dbspm_[a-z0-9_]+)\s*\(", header))
+def _declared_prototypes():
+    """Function names the C compiler sees after preprocessing include/dbspm_b200.h (comments stripped by gcc -E: a
+    prototype swallowed by an unterminated comment would be missing here, unlike in a regex over the raw text)."""
+    hdr = os.path.join(ROOT, "include", "dbspm_b200.h")
+    out = subprocess.run(["gcc", "-E", "-P", "-x", "c", hdr], capture_output=True, text=True, check=True).stdout
+    return set(re.findall(r"\b(dbspm_[a-z0-9_]+)\s*\(", out))
+
+
+def test_header_compiles_as_c_and_cpp_and_declares_every_export():
+    hdr = os.path.join(ROOT, "include", "dbspm_b200.h")
+    for lang, cc in (("c", "gcc"), ("c++", "g++")):
+        r = subprocess.run([cc, "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-x", lang, hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    declared = _declared_prototypes()
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+
+
+_C_CONSUMER = r"""
+#include <stdio.h>
+#include <string.h>
+#include "dbspm_b200.h"
+int main(void)
+{
+    const char *v = dbspm_version();
+    if (!v || !strstr(v, "sm_100a")) return 10;
+    /* argument validation happens before any CUDA call: usable on a box without a GPU */
+    const double dr[3] = {0.1, 0.1, 0.1};
+    int rc = dbspm_relax_powell_f64(NULL, 4, 4, 4, 0, 4, 0, 4, 2, 0.2, 3.0, dr, NULL, 1e-4, 1e-4, 2000,
+                                    NULL, NULL, NULL, NULL, 0, NULL);
+    if (rc != DBSPM_EINVAL) return 11;
+    if (!strstr(dbspm_last_error(), "null")) return 12;
+    double x = 0.0;
+    rc = dbspm_relax_powell_f64(&x, 4, 4, 4, 0, 4, 0, 4, 2, 0.2, 3.0, dr, NULL, 1e-4, 1e-4, 0, &x, NULL, NULL, NULL, 0, NULL);
+    if (rc != DBSPM_EINVAL || !strstr(dbspm_last_error(), "maxfev")) return 13;
+    if (dbspm_corr3d_workspace_bytes(196, 196, 240, 76, 130, 0) != (size_t)2 * 196 * 196 * 240 * 8) return 14;
+    if (dbspm_corr3d_f64(NULL, NULL, 1.0, 1.0, 1.0, 4, 4, 4, 0, 4, NULL, NULL, 0, 0, NULL) != DBSPM_EINVAL) return 15;
+    printf("%s\n", v);
+    return 0;
+}
+"""
+
+
+def test_c_program_links_against_the_library(tmp_path):
+    """A 20-line C consumer compiled against include/dbspm_b200.h with -Wall -Werror (an implicit declaration -- a
+    prototype missing from the header -- is an error) and linked against libdbspm_b200.so."""
+    src = tmp_path / "consumer.c"
+    src.write_text(_C_CONSUMER)
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-Werror=implicit-function-declaration",
+                        "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-ldbspm_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "sm_100a" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    declared = _declared_prototypes()
     L = _lib.lib()                                 # dlopen; no compute call without a GPU
     for name in declared:
         assert getattr(L, name) is not None
