@@ -36,6 +36,14 @@ __global__ void __launch_bounds__(256) transpose_yz_kernel(const double *in, dou
                       (int)threadIdx.x, (int)threadIdx.y, (int)blockDim.y);
 }
 
+// (nx,ny,nz) -> (nx,nz,ny,4): the four y neighbours of every stencil row as one aligned 32-byte sector (LAYOUT 2)
+__global__ void __launch_bounds__(256) quad_yz_kernel(const double *in, double *out, int ny, int nz)
+{
+    __shared__ double tile[35 * 33];
+    quad_yz_tile(in, out, ny, nz, tile, (int)blockIdx.x, (int)blockIdx.y, (long long)blockIdx.z,
+                 (int)threadIdx.x, (int)threadIdx.y, (int)blockDim.y);
+}
+
 __global__ void __launch_bounds__(256) accumulate_kernel(double *acc, const double *comp, double scale, size_t n, int init)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -119,10 +127,20 @@ extern "C" int dbspm_static_accumulate_f64(double *acc, const double *comp, doub
     return DBSPM_OK;
 }
 
-extern "C" size_t dbspm_relax_workspace_bytes(int nx, int ny, int nzc)
+// layout 1: y-fastest copy with a 3-plane periodic halo; layout 2: y-quads (four times the window)
+extern "C" size_t dbspm_relax_workspace_bytes_layout(int nx, int ny, int nzc, int layout)
 {
     if (nx < 1 || ny < 1 || nzc < 1) return 0;
-    return (size_t)nx * (ny + 3) * nzc * sizeof(double);       // y-fastest copy with a 3-plane periodic halo
+    if (layout == 1) return (size_t)nx * (ny + 3) * nzc * sizeof(double);
+    if (layout == 2) return (long long)nx * ny * nzc * 4 < 2147483647LL ? (size_t)nx * ny * nzc * 4 * sizeof(double) : 0;
+    return 0;
+}
+
+// the preferred workspace: the quad layout where its 32-bit element offsets allow, else the y-fastest copy
+extern "C" size_t dbspm_relax_workspace_bytes(int nx, int ny, int nzc)
+{
+    const size_t q = dbspm_relax_workspace_bytes_layout(nx, ny, nzc, 2);
+    return q ? q : dbspm_relax_workspace_bytes_layout(nx, ny, nzc, 1);
 }
 
 extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
@@ -161,16 +179,24 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
     const long long blocks = (ncol + RELAX_THREADS - 1) / RELAX_THREADS;
     DBSPM_REQUIRE(blocks < 2147483647LL, DBSPM_EUNSUPPORTED, "tile too large");
     if (workspace) {
-        // re-lay the potential with y fastest (once per call, ~2 passes over the window)
-        DBSPM_REQUIRE(workspace_bytes >= dbspm_relax_workspace_bytes(nx, ny, nzc) && ((uintptr_t)workspace & 15) == 0,
-                      DBSPM_EWORKSPACE, "relax workspace needs %zu bytes (got %zu)",
-                      dbspm_relax_workspace_bytes(nx, ny, nzc), workspace_bytes);
+        // re-lay the potential once per call (~2-5 passes over the window): the largest layout the workspace holds
+        const size_t need1 = dbspm_relax_workspace_bytes_layout(nx, ny, nzc, 1), need2 = dbspm_relax_workspace_bytes_layout(nx, ny, nzc, 2);
+        DBSPM_REQUIRE(workspace_bytes >= need1 && ((uintptr_t)workspace & 31) == 0,
+                      DBSPM_EWORKSPACE, "relax workspace needs %zu bytes (y-fastest copy) or %zu (y-quads), 32-byte aligned (got %zu)",
+                      need1, need2, workspace_bytes);
         DBSPM_REQUIRE(nx <= 65535, DBSPM_EUNSUPPORTED, "nx too large for the transpose grid");
-        dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 3 + 31) / 32), (unsigned)nx);
-        transpose_yz_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_win, (double *)workspace, ny, nzc);
-        DBSPM_CUDA_TRY(cudaGetLastError());
         P.grid = (const double *)workspace;
-        relax_kernel<1><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
+        if (need2 && workspace_bytes >= need2) {
+            dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 31) / 32), (unsigned)nx);
+            quad_yz_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_win, (double *)workspace, ny, nzc);
+            DBSPM_CUDA_TRY(cudaGetLastError());
+            relax_kernel<2><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
+        } else {
+            dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 3 + 31) / 32), (unsigned)nx);
+            transpose_yz_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_win, (double *)workspace, ny, nzc);
+            DBSPM_CUDA_TRY(cudaGetLastError());
+            relax_kernel<1><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
+        }
     } else {
         relax_kernel<0><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
     }

@@ -17,6 +17,7 @@
 // flow, constants and comparison directions follow scipy line by line; Powell bookkeeping is
 // compiled without FMA contraction (plain * and +, like numpy).
 #pragma once
+#include <string.h>
 #include "hd.h"
 
 #ifndef M_PI
@@ -44,6 +45,57 @@ struct RelaxParams {
     double *out_cart;         // (3,ni,nj,nz) or null
     int *out_nfev;            // (ni,nj,nz) or null
 };
+
+// ---- sin and cos of one argument, same bits on the device and on the host ---------------
+// A fixed sequence of IEEE operations (explicit fma, no library call): Cody-Waite reduction by pi/2 in three
+// pieces, then the classical degree-13 / degree-14 minimax kernels on [-pi/4, pi/4] (coefficients of fdlibm's
+// __kernel_sin / __kernel_cos).  <= 1.5 ulp for |x| <= 1e5 (tests/test_emulation.py), which is what CUDA's
+// own sincos() delivers; unlike a library call the result does not depend on who compiled the caller, so
+// the CPU twin of this kernel (oracle/dbspm_oracle.c, "kernel twin" mode) reproduces it bit for bit, and
+// it costs a third of the instructions of two libdevice sincos calls.  Larger or non-finite arguments
+// (never produced by a relaxation) go to the library.
+HD void dbspm_sincos(double x, double *sn, double *cs)
+{
+    if (!(fabs(x) <= 1.0e5)) {
+#if defined(__CUDA_ARCH__)
+        sincos(x, sn, cs);
+#else
+        *sn = sin(x); *cs = cos(x);
+#endif
+        return;
+    }
+    const double magic = 6755399441055744.0;                       // 1.5 * 2^52: (v + magic) - magic = rint(v)
+    const double t = fma(x, 0.63661977236758138, magic);
+    const double k = t - magic;
+#if defined(__CUDA_ARCH__)
+    const int q = __double2loint(t);
+#else
+    long long tb; memcpy(&tb, &t, sizeof tb);
+    const int q = (int)(tb & 0xffffffffLL);
+#endif
+    double r = fma(-k, 1.5707963267948966e+00, x);
+    r = fma(-k, 6.1232339957367574e-17, r);
+    r = fma(-k, 8.4784276603688985e-32, r);
+    const double z = r * r;
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, z, -2.50507602534068634195e-08);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double s0 = fma(r * z, ps, r);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double hz = 0.5 * z, w = 1.0 - hz;                       // fdlibm's compensated 1 - z/2
+    const double c0 = w + fma(z * z, pc, (1.0 - w) - hz);
+    const double sa = (q & 1) ? c0 : s0, ca = (q & 1) ? s0 : c0;
+    *sn = (q & 2) ? -sa : sa;
+    *cs = ((q + 1) & 2) ? -ca : ca;
+}
 
 // ---- periodic Catmull-Rom (a = -1/2) tricubic stencil in index units ---------------------
 // d = fmod(p, n), then "+= n if negative": the reference's periodic wrap, bit for bit.  fmod is
@@ -98,6 +150,21 @@ HD void cr_axis(double p, int n, double inv_n, int *i0, double *w)
 //           warp, which own adjacent y columns, read adjacent addresses -> 2-3 L1 wavefronts per load
 //           instead of ~8, and the four y neighbours of a stencil row are four consecutive doubles at
 //           immediate offsets from one base address, wrap or no wrap)
+// LAYOUT 2: g[((x*nz + z)*ny + y)*4 + c] = value at (x, (y - 1 + c) mod ny, z): every stencil row's four y
+//           neighbours are ONE aligned 32-byte sector, fetched by one 256-bit load (16 loads per evaluation instead
+//           of 64).  Lanes of a warp mostly sit in different (x, z) cells (their tips are deflected differently), so a
+//           load instruction of layout 1 touches about one 128-byte line per lane for 8 useful bytes; here the same
+//           line delivers 32 (traced on the CPU emulation: 3.6x fewer L1 wavefronts per evaluation).  Costs four
+//           times the memory of the window (1.8 GB for 1024 x 1024 x 54) -- HBM has it.
+HD void ld_quad(const double *p, double *q)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(q[0]), "=d"(q[1]), "=d"(q[2]), "=d"(q[3]) : "l"(p));
+#else
+    q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; q[3] = p[3];
+#endif
+}
+
 template <int LAYOUT>
 HD double tricubic_eval(const double *g, int nx, int ny, int nz, int nyp, const double *inv_n, double x, double y, double z)
 {
@@ -114,6 +181,10 @@ HD double tricubic_eval(const double *g, int nx, int ny, int nz, int nyp, const 
         stencil_idx(iy, ny, yo);
 #pragma unroll
         for (int c = 0; c < 4; ++c) { xo[c] *= ny * nz; yo[c] *= nz; }
+    } else if (LAYOUT == 2) {
+        const int y1 = (iy >= ny) ? iy - ny : iy;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { xo[c] *= 4 * ny * nz; zo[c] *= 4 * ny; yo[c] = 4 * y1; }
     } else {
         const int y1 = (iy >= ny) ? iy - ny : iy;          // stored index of plane y1 - 1
 #pragma unroll
@@ -134,6 +205,13 @@ HD double tricubic_eval(const double *g, int nx, int ny, int nz, int nyp, const 
                 ry = fma(wy[1], LDG(g + (o + yo[1])), ry);
                 ry = fma(wy[2], LDG(g + (o + yo[2])), ry);
                 ry = fma(wy[3], LDG(g + (o + yo[3])), ry);
+            } else if (LAYOUT == 2) {
+                double q[4];
+                ld_quad(g + (xo[a] + zo[c] + yo[0]), q);
+                ry = wy[0] * q[0];
+                ry = fma(wy[1], q[1], ry);
+                ry = fma(wy[2], q[2], ry);
+                ry = fma(wy[3], q[3], ry);
             } else {
                 const double *row = g + (xo[a] + zo[c] + yo[0]);
                 ry = wy[0] * LDG(row);
@@ -150,6 +228,8 @@ HD double tricubic_eval(const double *g, int nx, int ny, int nz, int nyp, const 
 
 #if defined(DBSPM_EMU_INTERP_HOOK) && !defined(__CUDA_ARCH__)
 extern double (*dbspm_emu_interp_hook)(double, double, double);
+// test/analysis only: called before every objective evaluation with (column, height, entry state, theta, phi)
+extern void (*dbspm_emu_trace_hook)(long long, int, int, double, double);
 #endif
 
 // ---- objective: Emin / Emin_norm ----------------------------------------------------------
@@ -159,12 +239,8 @@ HD double relax_objective(const RelaxParams &P, int oi, int oj, int ok, double t
     const double d = M_PI - th;
     const double spr = 0.5 * P.kappa * (d * d);
     double sth, cth, saz, caz;
-#if defined(__CUDA_ARCH__)
-    sincos(th, &sth, &cth);
-    sincos(az, &saz, &caz);
-#else
-    sth = sin(th); cth = cos(th); saz = sin(az); caz = cos(az);
-#endif
+    dbspm_sincos(th, &sth, &cth);
+    dbspm_sincos(az, &saz, &caz);
     double ox, oy, oz;
     if (!P.noortho) {
         ox = div_by(P.rpivot_rt * sth * caz, P.dr[0], P.inv_dr[0]);
@@ -291,6 +367,9 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
         const bool hold = !done && R.pc == PC_INIT && k < kmax - RELAX_DRIFT;
 #else
         const bool hold = false;
+#endif
+#if defined(DBSPM_EMU_INTERP_HOOK) && !defined(__CUDA_ARCH__)
+        if (!done && !hold && dbspm_emu_trace_hook) dbspm_emu_trace_hook(col, k, R.pc, R.p[0] + alpha * R.xi[0], R.p[1] + alpha * R.xi[1]);
 #endif
         if (!done && !hold) fe = relax_objective<LAYOUT>(P, oi, oj, ok, R.p[0] + alpha * R.xi[0], R.p[1] + alpha * R.xi[1]);
         WARP_SYNC();
@@ -564,9 +643,38 @@ HD void relax_cart_body(const double *etp, double *cart, long long npos, double 
 {
     for (long long o = gid; o < npos; o += gstride) {
         const double th = etp[3 * o + 1], az = etp[3 * o + 2];
-        cart[o] = rpivot * sin(th) * cos(az);
-        cart[npos + o] = rpivot * sin(th) * sin(az);
-        cart[2 * npos + o] = rpivot * cos(th);
+        double sth, cth, saz, caz;
+        dbspm_sincos(th, &sth, &cth);
+        dbspm_sincos(az, &saz, &caz);
+        cart[o] = rpivot * sth * caz;
+        cart[npos + o] = rpivot * sth * saz;
+        cart[2 * npos + o] = rpivot * cth;
+    }
+}
+
+// (nx, ny, nz) -> (nx, nz, ny, 4) with quad y holding the values at y - 1, y, y + 1, y + 2 (periodic): a tile of
+// 32 y-quads x 32 z through shared memory (tile[35][33]: 32 + 3 halo rows), one x-slab per blockIdx.z
+HD void quad_yz_tile(const double *in, double *out, int ny, int nz, double *tile /* 35*33 */,
+                     int bx /* z tile */, int by /* y tile */, long long slab, int tx, int ty, int nty)
+{
+    const double *src = in + (size_t)slab * ny * nz;
+    double *dst = out + (size_t)slab * ny * nz * 4;
+    for (int r = ty; r < 35; r += nty) {
+        const int y = by * 32 + r - 1, z = bx * 32 + tx;               // rows y0 - 1 ... y0 + 33
+        if (z < nz) tile[r * 33 + tx] = src[(size_t)(((y % ny) + ny) % ny) * nz + z];
+    }
+    BLOCK_SYNC();
+    for (int r = ty; r < 32; r += nty) {
+        const int z = bx * 32 + r, y = by * 32 + tx;
+        if (y < ny && z < nz) {
+            double *d = dst + ((size_t)z * ny + y) * 4;
+#if defined(__CUDA_ARCH__)
+            reinterpret_cast<double2 *>(d)[0] = make_double2(tile[tx * 33 + r], tile[(tx + 1) * 33 + r]);
+            reinterpret_cast<double2 *>(d)[1] = make_double2(tile[(tx + 2) * 33 + r], tile[(tx + 3) * 33 + r]);
+#else
+            for (int c = 0; c < 4; ++c) d[c] = tile[(tx + c) * 33 + r];
+#endif
+        }
     }
 }
 

@@ -323,7 +323,7 @@ class TricubicField:
 
 
 def relax_grid(static, kappa, rpivot, dr, nz_relax, dR=None, tile=None, xtol=1e-4, ftol=1e-4,
-               maxfev=2000, method="Powell", want_nfev=False, device=None, coalesce=True):
+               maxfev=2000, method="Powell", want_nfev=False, device=None, coalesce=True, layout=None):
     """Relax the probe at every (i, j, k) of a lateral tile (default: the whole window).
 
     static: (Nx,Ny,Nzc) window potential (numpy, CUDA tensor or TricubicField).
@@ -351,10 +351,17 @@ def relax_grid(static, kappa, rpivot, dr, nz_relax, dR=None, tile=None, xtol=1e-
         raise ValueError(f"tile {(i_lo, i_hi, j_lo, j_hi)} outside the {nx}x{ny} lateral grid")
     if etp.numel() > 0:                     # an empty tile (a rank with no columns) launches nothing
         with torch.cuda.device(dev):
-            # y-fastest copy of the potential (coalesced stencil loads); single columns read in place
+            # re-laid copy of the potential (include/dbspm_b200.h: y-quads, else y fastest); small tiles read in
+            # place.  layout = 0 / 1 / 2 forces in-place / y fastest / y-quads (tests, A/B timing); same bits
             ws = None
-            if coalesce and ni * nj >= 1024:
-                ws = torch.empty(_lib.lib().dbspm_relax_workspace_bytes(nx, ny, nzc), dtype=torch.uint8, device=dev)
+            if layout is None:
+                layout = -1 if (coalesce and ni * nj >= 1024) else 0
+            if layout:
+                L = _lib.lib()
+                need = L.dbspm_relax_workspace_bytes(nx, ny, nzc) if layout < 0 else \
+                    L.dbspm_relax_workspace_bytes_layout(nx, ny, nzc, int(layout))
+                if need:
+                    ws = torch.empty(need, dtype=torch.uint8, device=dev)
             _lib.check(_lib.lib().dbspm_relax_powell_f64(
                 field.data.data_ptr(), nx, ny, nzc, i_lo, i_hi, j_lo, j_hi, nz, float(kappa), float(rpivot),
                 dr3, dR9, float(xtol), float(ftol), int(maxfev), etp.data_ptr(), cart.data_ptr(),

@@ -161,10 +161,14 @@ int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
                            double xtol, double ftol, int maxfev,
                            double *out_E_theta_phi, double *out_cart, int *out_nfev,
                            void *workspace, size_t workspace_bytes, void *stream);
-/* workspace (nullable): dbspm_relax_workspace_bytes(nx,ny,nzc) bytes, 16-byte aligned.  With it the
- * potential is re-laid with y fastest so a warp's loads coalesce (about 2x faster); without it the
- * kernel reads static_win in place.  Results are identical either way.                              */
+/* workspace (nullable), 32-byte aligned: the potential is re-laid once per call so that the stencil loads of a warp
+ * waste less of every cache line.  Layout 1 (dbspm_relax_workspace_bytes_layout(.., 1) bytes): y fastest with a periodic
+ * halo.  Layout 2 (4x the window; returns 0 when 32-bit element offsets would overflow): the four y neighbours of every
+ * stencil row as one 32-byte sector, one 256-bit load per row.  The kernel takes the largest layout the workspace
+ * holds; dbspm_relax_workspace_bytes returns the preferred size (layout 2, else 1).  Without a workspace the kernel
+ * reads static_win in place.  Results are bit-identical in all three cases.                                       */
 size_t dbspm_relax_workspace_bytes(int nx, int ny, int nzc);
+size_t dbspm_relax_workspace_bytes_layout(int nx, int ny, int nzc, int layout);
 
 /* ---- tricubic gather: out[p] = interp(data)(pts[p,0], pts[p,1], pts[p,2]), index units ---- */
 int dbspm_tricubic_gather_f64(const double *data, int nx, int ny, int nz,

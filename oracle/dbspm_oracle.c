@@ -24,6 +24,16 @@
  *                        spring_energy :49-52, sph2grid grid.py:364-369; and the
  *                        non-orthogonal variant :88-105 with Emin_norm :62-67
  *
+ *   "kernel twin" mode   (oracle_relax_tile_twin) the same relax loop and the same scipy restatement, with
+ *                        the two ingredients in which the CUDA kernel differs from the reference at the
+ *                        1e-14 level swapped for CPU statements of the kernel's own arithmetic: the
+ *                        separable Catmull-Rom stencil in the kernel's summation order with fused
+ *                        multiply-adds (tc_ip_twin) and the library-independent sin/cos (det_sincos).
+ *                        A GPU run must equal this mode BIT FOR BIT (tests/test_gpu_parity.py); the
+ *                        difference between the two modes is then exactly "Lekien-Marsden vs
+ *                        Catmull-Rom form + libm vs fixed-sequence sin/cos", measured on the CPU
+ *                        (tests/test_oracle.py), with no GPU effect mixed in.
+ *
  * Parity status: the sr/es part is pinned against the reference's own
  * get_density_overlap run in the build container (oracle/make_golden.py ->
  * tests/golden/).  The Powell part is pinned against the installed scipy
@@ -226,6 +236,71 @@ double tc_ip_catmull(const tc_t *t, double x, double y, double z)
         r += w[0][a] * ry;
     }
     return r;
+}
+
+/* "kernel twin" of the interpolant: the CUDA kernel's arithmetic (dbspm_b200/csrc/relax_body.h tricubic_eval) stated
+   independently -- same weights, y innermost / z middle / x outermost, the first product of every row a plain multiply
+   and every accumulation a fused multiply-add */
+double tc_ip_twin(const tc_t *t, double x, double y, double z)
+{
+    double p[3] = {x, y, z}, w[3][4];
+    int n[3] = {t->n1, t->n2, t->n3}, i0[3];
+    for (int a = 0; a < 3; ++a) {
+        double d = fmod(p[a], (double)n[a]);
+        if (d < 0) d += n[a];
+        double fl = floor(d);
+        double u = d - fl, u2 = u * u, u3 = u2 * u;
+        i0[a] = (int)fl;
+        w[a][0] = -0.5 * u3 + u2 - 0.5 * u;
+        w[a][1] = 1.5 * u3 - 2.5 * u2 + 1.0;
+        w[a][2] = -1.5 * u3 + 2.0 * u2 + 0.5 * u;
+        w[a][3] = 0.5 * u3 - 0.5 * u2;
+    }
+    double r = 0.0;
+    for (int a = 0; a < 4; ++a) {
+        double rx = 0.0;
+        for (int c = 0; c < 4; ++c) {
+            double ry = w[1][0] * tc_at(t, i0[0] - 1 + a, i0[1] - 1, i0[2] - 1 + c);
+            for (int b = 1; b < 4; ++b) ry = fma(w[1][b], tc_at(t, i0[0] - 1 + a, i0[1] - 1 + b, i0[2] - 1 + c), ry);
+            rx = fma(w[2][c], ry, rx);
+        }
+        r = fma(w[0][a], rx, r);
+    }
+    return r;
+}
+
+/* library-independent sin and cos (the kernel's dbspm_sincos stated independently): rint(x * 2/pi) by the
+   1.5 * 2^52 shift, three-piece Cody-Waite reduction with fused multiply-adds, fdlibm's __kernel_sin / __kernel_cos
+   polynomials in Horner form with fused multiply-adds, quadrant from the two low bits of the rounded multiple */
+static void det_sincos(double x, double *sn, double *cs)
+{
+    if (!(fabs(x) <= 1.0e5)) { *sn = sin(x); *cs = cos(x); return; }
+    const double shift = 6755399441055744.0;
+    double t = fma(x, 0.63661977236758138, shift);
+    double k = t - shift;
+    long long bits; memcpy(&bits, &t, sizeof bits);
+    int q = (int)(bits & 3);
+    double r = fma(-k, 1.5707963267948966e+00, x);
+    r = fma(-k, 6.1232339957367574e-17, r);
+    r = fma(-k, 8.4784276603688985e-32, r);
+    double z = r * r;
+    static const double S[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                                2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+    static const double Cc[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                                 -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+    double ps = S[5], pc = Cc[5];
+    for (int i = 4; i >= 0; --i) { ps = fma(ps, z, S[i]); pc = fma(pc, z, Cc[i]); }
+    double s0 = fma(r * z, ps, r);
+    double hz = 0.5 * z, w = 1.0 - hz;
+    double c0 = w + fma(z * z, pc, (1.0 - w) - hz);
+    double sa = (q & 1) ? c0 : s0, ca = (q & 1) ? s0 : c0;
+    *sn = (q & 2) ? -sa : sa;
+    *cs = ((q + 1) & 2) ? -ca : ca;
+}
+
+void oracle_det_sincos(const double *x, double *s, double *c, long n)
+{
+    for (long i = 0; i < n; ++i) det_sincos(x[i], s + i, c + i);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -458,6 +533,7 @@ typedef struct {
     double kappa, rpivot, dr[3];
     int noortho;
     double Minv[9];            /* inv(dR.T) for Emin_norm */
+    int twin;                  /* 1: "kernel twin" mode (tc_ip_twin + det_sincos), see the file header */
 } emin_ctx_t;
 
 static double emin_obj(const double pol[2], void *vctx)
@@ -466,18 +542,21 @@ static double emin_obj(const double pol[2], void *vctx)
     double th = pol[0], az = pol[1];
     double d = M_PI - th;
     double spr = 0.5 * c->kappa * (d * d);                       /* interactions.py:49-52 */
-    double ox, oy, oz;
+    double ox, oy, oz, sth, cth, saz, caz;
+    if (c->twin) { det_sincos(th, &sth, &cth); det_sincos(az, &saz, &caz); }
+    else { sth = sin(th); cth = cos(th); saz = sin(az); caz = cos(az); }
     if (!c->noortho) {                                           /* grid.py:364-369 */
-        ox = c->rpivot * sin(th) * cos(az) / c->dr[0];
-        oy = c->rpivot * sin(th) * sin(az) / c->dr[1];
-        oz = c->rpivot * cos(th) / c->dr[2];
+        ox = c->rpivot * sth * caz / c->dr[0];
+        oy = c->rpivot * sth * saz / c->dr[1];
+        oz = c->rpivot * cth / c->dr[2];
     } else {                                                     /* grid.py:381-386 + :66 */
-        double X = c->rpivot * sin(th) * cos(az), Y = c->rpivot * sin(th) * sin(az), Z = c->rpivot * cos(th);
+        double X = c->rpivot * sth * caz, Y = c->rpivot * sth * saz, Z = c->rpivot * cth;
         ox = c->Minv[0] * X + c->Minv[1] * Y + c->Minv[2] * Z;
         oy = c->Minv[3] * X + c->Minv[4] * Y + c->Minv[5] * Z;
         oz = c->Minv[6] * X + c->Minv[7] * Y + c->Minv[8] * Z;
     }
-    return tc_ip(c->tc, (double)c->origin[0] + ox, (double)c->origin[1] + oy, (double)c->origin[2] + oz) + spr;
+    double px = (double)c->origin[0] + ox, py = (double)c->origin[1] + oy, pz = (double)c->origin[2] + oz;
+    return (c->twin ? tc_ip_twin(c->tc, px, py, pz) : tc_ip(c->tc, px, py, pz)) + spr;
 }
 
 static void inv3(const double m[9], double out[9])
@@ -492,11 +571,12 @@ static void inv3(const double m[9], double out[9])
 /* One lateral column.  zi: nz z-indices (ascending); sweep is zi[::-1] with warm start.
    out: (nz,3) rows [fun, theta, phi] in ascending-z order; nfev: (nz) or NULL.
    dR: 9 doubles (row-major 3x3) or NULL for the orthogonal path. */
-void oracle_relax_column(tc_t *tc, long i, long j, double kappa, double npivot,
-                         const long *zi, int nz, const double dr[3], const double *dR,
-                         double xtol, double ftol, int maxfev, double *out, int *nfev)
+static void relax_column_mode(tc_t *tc, long i, long j, double kappa, double npivot,
+                              const long *zi, int nz, const double dr[3], const double *dR,
+                              double xtol, double ftol, int maxfev, double *out, int *nfev, int twin)
 {
     emin_ctx_t c;
+    c.twin = twin;
     c.tc = tc; c.origin[0] = i; c.origin[1] = j; c.origin[2] = 0;
     c.kappa = kappa; c.rpivot = npivot * dr[2];                  /* interactions.py:73 */
     c.dr[0] = dr[0]; c.dr[1] = dr[1]; c.dr[2] = dr[2];
@@ -516,12 +596,19 @@ void oracle_relax_column(tc_t *tc, long i, long j, double kappa, double npivot,
     }
 }
 
+void oracle_relax_column(tc_t *tc, long i, long j, double kappa, double npivot,
+                         const long *zi, int nz, const double dr[3], const double *dR,
+                         double xtol, double ftol, int maxfev, double *out, int *nfev)
+{
+    relax_column_mode(tc, i, j, kappa, npivot, zi, nz, dr, dR, xtol, ftol, maxfev, out, nfev, 0);
+}
+
 /* whole lateral tile, plain loop (threads are added by the caller with processes) */
-void oracle_relax_tile(const double *static_win, int nx, int ny, int nzc,
-                       int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
-                       double kappa, double rpivot_param, const double dr[3], const double *dR,
-                       double xtol, double ftol, int maxfev,
-                       double *out /* (ni,nj,nz,3) */, int *nfev /* (ni,nj,nz) or NULL */)
+static void relax_tile_mode(const double *static_win, int nx, int ny, int nzc,
+                            int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                            double kappa, double rpivot_param, const double dr[3], const double *dR,
+                            double xtol, double ftol, int maxfev,
+                            double *out /* (ni,nj,nz,3) */, int *nfev /* (ni,nj,nz) or NULL */, int twin)
 {
     tc_t *tc = tc_create(static_win, nx, ny, nzc);
     long *zi = (long *)malloc(sizeof(long) * (size_t)nz_relax);
@@ -531,11 +618,41 @@ void oracle_relax_tile(const double *static_win, int nx, int ny, int nzc,
     for (int i = i_lo; i < i_hi; ++i)
         for (int j = j_lo; j < j_hi; ++j) {
             size_t col = (size_t)(i - i_lo) * nj + (j - j_lo);
-            oracle_relax_column(tc, i, j, kappa, npivot, zi, nz_relax, dr, dR, xtol, ftol, maxfev,
-                                out + col * nz_relax * 3, nfev ? nfev + col * nz_relax : NULL);
+            relax_column_mode(tc, i, j, kappa, npivot, zi, nz_relax, dr, dR, xtol, ftol, maxfev,
+                              out + col * nz_relax * 3, nfev ? nfev + col * nz_relax : NULL, twin);
         }
     free(zi);
     tc_destroy(tc);
+}
+
+void oracle_relax_tile(const double *static_win, int nx, int ny, int nzc,
+                       int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                       double kappa, double rpivot_param, const double dr[3], const double *dR,
+                       double xtol, double ftol, int maxfev, double *out, int *nfev)
+{
+    relax_tile_mode(static_win, nx, ny, nzc, i_lo, i_hi, j_lo, j_hi, nz_relax, kappa, rpivot_param, dr, dR,
+                    xtol, ftol, maxfev, out, nfev, 0);
+}
+
+/* "kernel twin" mode: what the CUDA kernel must reproduce bit for bit */
+void oracle_relax_tile_twin(const double *static_win, int nx, int ny, int nzc,
+                            int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                            double kappa, double rpivot_param, const double dr[3], const double *dR,
+                            double xtol, double ftol, int maxfev, double *out, int *nfev)
+{
+    relax_tile_mode(static_win, nx, ny, nzc, i_lo, i_hi, j_lo, j_hi, nz_relax, kappa, rpivot_param, dr, dR,
+                    xtol, ftol, maxfev, out, nfev, 1);
+}
+
+/* sph2cart of relaxed angles in twin mode (the kernel's relax_cart_body): (3, n) x, y, z */
+void oracle_sph2cart_twin(const double *th, const double *az, double r, long n, double *out)
+{
+    for (long i = 0; i < n; ++i) {
+        double sth, cth, saz, caz;
+        det_sincos(th[i], &sth, &cth);
+        det_sincos(az[i], &saz, &caz);
+        out[i] = r * sth * caz; out[n + i] = r * sth * saz; out[2 * n + i] = r * cth;
+    }
 }
 
 /* generic objective hook so tests can drive oracle_powell_minimize from Python */

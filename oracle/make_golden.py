@@ -80,6 +80,23 @@ def relax_cases():
     return {"kappa": kappa, "rpivot": rp, "nz": 24, "stiff": {"kappa": 0.5, "rpivot": 2.0, "nz": 10}}
 
 
+def relax_noortho_cases():
+    """The reference's relax_noortho_tip_z (interactions.py:88-105) with a genuinely non-orthogonal step matrix dR
+    (off-diagonal entries of a few per cent of the spacing: a monoclinic-like cell), which the orthorhombic examples
+    never exercise.  Own file so that the fixtures of round 1 stay byte-identical."""
+    static = synth.make_static_like((24, 20, 54), 11).numpy()
+    dr = np.array([0.0765306, 0.0765306, 0.075])
+    kappa, rp = 0.2, 3.02
+    npivot = rp / dr[2]
+    zi = np.arange(24)
+    interp = O.Tricubic(list(static), list(static.shape))
+    cols = [(0, 0), (5, 7), (12, 10), (11, 9), (23, 19), (7, 13)]
+    dR = np.array([[dr[0], 0.011, 0.0], [0.004, dr[1], 0.0], [0.002, -0.003, dr[2]]])
+    skew = np.array([RI.relax_noortho_tip_z(i, j, interp, kappa, npivot, zi, dr, dR, "Powell") for i, j in cols])
+    np.savez_compressed(os.path.join(OUT, "relax_noortho_reference.npz"), dR=dR, cols=np.array(cols), skew=skew)
+    return {"kappa": kappa, "rpivot": rp, "nz": 24, "static": "relax_reference.npz:static"}
+
+
 def geometry_cases():
     out = {}
     for name, path, shape, cell in [
@@ -142,10 +159,18 @@ def next_row_cases():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["noortho"]:          # round 2: add the skew-cell relax fixture without regenerating the others
+        with open(os.path.join(OUT, "manifest.json")) as fh:
+            manifest = json.load(fh)
+        manifest["relax_noortho"] = relax_noortho_cases()
+        with open(os.path.join(OUT, "manifest.json"), "w") as fh:
+            json.dump(manifest, fh, indent=1, sort_keys=True)
+        print("wrote relax_noortho_reference.npz")
+        raise SystemExit(0)
     manifest = {
         "generator": "oracle/make_golden.py", "reference": "/root/reference (SPMTH/DBSPM, unmodified)",
         "numpy": np.__version__, "scipy": scipy.__version__,
-        "overlap": overlap_cases(), "relax": relax_cases(), "geometry": geometry_cases(),
+        "overlap": overlap_cases(), "relax": relax_cases(), "relax_noortho": relax_noortho_cases(), "geometry": geometry_cases(),
         "nextrow": next_row_cases(),
     }
     with open(os.path.join(OUT, "manifest.json"), "w") as fh:

@@ -12,7 +12,8 @@ Contents (reference = /root/reference, read-only, absent on the GPU box):
                         shape).ip([x, y, z]); Lekien-Marsden, periodic, index units
   relax_tip_z_scipy     restatement of interactions.py:70-86 on top of the *installed* scipy
                         (what the reference actually runs, Python overheads included)
-  relax_tile            C restatement of the same (scipy's Powell restated in C)
+  relax_tile            C restatement of the same (scipy's Powell restated in C); twin=True swaps in the CUDA
+                        kernel's own stencil arithmetic and sin/cos (bit-exact target for the GPU tests)
 """
 from __future__ import annotations
 
@@ -62,6 +63,14 @@ def lib() -> C.CDLL:
                                         C.c_int, C.c_int, C.c_double, C.c_double, _dbl_p, _dbl_p,
                                         C.c_double, C.c_double, C.c_int, _dbl_p, _int_p]
         L.oracle_relax_tile.restype = None
+        L.oracle_relax_tile_twin.argtypes = L.oracle_relax_tile.argtypes
+        L.oracle_relax_tile_twin.restype = None
+        L.tc_ip_twin.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.tc_ip_twin.restype = C.c_double
+        L.oracle_det_sincos.argtypes = [_dbl_p, _dbl_p, _dbl_p, C.c_long]
+        L.oracle_det_sincos.restype = None
+        L.oracle_sph2cart_twin.argtypes = [_dbl_p, _dbl_p, C.c_double, C.c_long, _dbl_p]
+        L.oracle_sph2cart_twin.restype = None
         L.oracle_powell_minimize_cb.argtypes = [C.c_void_p, _dbl_p, C.c_double, C.c_double, C.c_int,
                                                 C.c_int, _dbl_p, _dbl_p, _int_p]
         L.oracle_powell_minimize_cb.restype = C.c_int
@@ -197,9 +206,11 @@ def relax_tip_z_scipy(i, j, interpE, kappa, npivot, zi, dr, method="Powell"):
 
 
 def relax_tile(static_win: np.ndarray, i_lo, i_hi, j_lo, j_hi, nz_relax, kappa, rpivot, dr,
-               dR=None, xtol=1e-4, ftol=1e-4, maxfev=2000, want_nfev=False):
+               dR=None, xtol=1e-4, ftol=1e-4, maxfev=2000, want_nfev=False, twin=False):
     """C restatement of the whole relax loop (dbspm:564-581) over a lateral tile.
-    Returns (ni,nj,nz,3) [fun, theta, phi] (+ nfev)."""
+    Returns (ni,nj,nz,3) [fun, theta, phi] (+ nfev).
+    twin=True: the "kernel twin" mode of dbspm_oracle.c (Catmull-Rom stencil in the kernel's summation order +
+    the fixed-sequence sin/cos) -- the arithmetic a GPU run must reproduce bit for bit."""
     s = np.ascontiguousarray(static_win, dtype=np.float64)
     nx, ny, nzc = s.shape
     ni, nj = i_hi - i_lo, j_hi - j_lo
@@ -210,9 +221,9 @@ def relax_tile(static_win: np.ndarray, i_lo, i_hi, j_lo, j_hi, nz_relax, kappa, 
     if dR is not None:
         dRv = np.ascontiguousarray(dR, dtype=np.float64).reshape(9)
         dRp = _p(dRv)
-    lib().oracle_relax_tile(_p(s), nx, ny, nzc, i_lo, i_hi, j_lo, j_hi, nz_relax, float(kappa),
-                            float(rpivot), _p(drv), dRp, xtol, ftol, maxfev, _p(out),
-                            nfev.ctypes.data_as(_int_p))
+    fn = lib().oracle_relax_tile_twin if twin else lib().oracle_relax_tile
+    fn(_p(s), nx, ny, nzc, i_lo, i_hi, j_lo, j_hi, nz_relax, float(kappa),
+       float(rpivot), _p(drv), dRp, xtol, ftol, maxfev, _p(out), nfev.ctypes.data_as(_int_p))
     return (out, nfev) if want_nfev else out
 
 
@@ -227,6 +238,21 @@ def powell_minimize(fun, x0, xtol=1e-4, ftol=1e-4, maxiter=2000, maxfun=2000):
     nfev = lib().oracle_powell_minimize_cb(C.cast(cb, C.c_void_p), _p(x0v), xtol, ftol, maxiter, maxfun,
                                            _p(xo), C.byref(f), C.byref(nit))
     return xo, f.value, nit.value, nfev
+
+
+def sph2cart_twin(th, az, r):
+    """sph2cart with the kernel twin's sin/cos: (3, ...) array of x, y, z."""
+    th = np.ascontiguousarray(th, dtype=np.float64); az = np.ascontiguousarray(az, dtype=np.float64)
+    out = np.empty((3,) + th.shape)
+    lib().oracle_sph2cart_twin(_p(th), _p(az), float(r), th.size, _p(out))
+    return out
+
+
+def det_sincos(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib().oracle_det_sincos(_p(x), _p(s), _p(c), x.size)
+    return s, c
 
 
 def sph2cart(th, az, r):

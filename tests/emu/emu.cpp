@@ -15,6 +15,8 @@
 
 double (*dbspm_emu_interp_hook)(double, double, double) = nullptr;
 extern "C" void emu_set_interp_hook(double (*f)(double, double, double)) { dbspm_emu_interp_hook = f; }
+void (*dbspm_emu_trace_hook)(long long, int, int, double, double) = nullptr;
+extern "C" void emu_set_trace_hook(void (*f)(long long, int, int, double, double)) { dbspm_emu_trace_hook = f; }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -389,7 +391,20 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
     P.out_etp = out_etp; P.out_cart = out_cart; P.out_nfev = out_nfev;
     const long long ncol = (long long)(i_hi - i_lo) * (j_hi - j_lo);
     std::vector<double> tr;
-    if (transposed) {
+    if (transposed == 2) {
+        // quad_yz_kernel block by block.  The body has one block barrier; the 32 x 1 "threads" of a block are run one
+        // after the other, twice: the first round fills the shared tile, the second one stores from the complete tile
+        tr.resize((size_t)nx * ny * nzc * 4);
+        std::vector<double> tile(35 * 33);
+        for (int x = 0; x < nx; ++x)
+            for (int by = 0; by < (ny + 31) / 32; ++by)
+                for (int bx = 0; bx < (nzc + 31) / 32; ++bx)
+                    for (int round = 0; round < 2; ++round)
+                        for (int tx = 0; tx < 32; ++tx)
+                            quad_yz_tile(static_win, tr.data(), ny, nzc, tile.data(), bx, by, x, tx, 0, 1);
+        P.grid = tr.data();
+        for (long long c = 0; c < ncol; ++c) relax_column_body<2, 1>(P, c, ncol, powell_sm, 0);
+    } else if (transposed) {
         // what transpose_yz_kernel does, block by block: the body has one block barrier, so it is run
         // as a 32 x 1 thread block with each phase completed for all tx before the next starts --
         // done here by calling the body per tx with a private tile copy of phase 1 (tile is filled
@@ -420,6 +435,11 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
     }
     if (out_cart) relax_cart_body(out_etp, out_cart, ncol * nz_relax, rpivot, 0, 1);
     return 0;
+}
+
+extern "C" void emu_sincos(const double *x, double *s, double *c, long long n)
+{
+    for (long long i = 0; i < n; ++i) dbspm_sincos(x[i], s + i, c + i);
 }
 
 extern "C" double emu_tricubic(const double *g, int nx, int ny, int nz, double x, double y, double z)

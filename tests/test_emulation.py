@@ -280,6 +280,94 @@ def test_relax_transposed_layout_is_bit_identical(emu, relax_golden):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
 
 
+def test_relax_quad_layout_is_bit_identical(emu, relax_golden):
+    """LAYOUT 2 (the four y neighbours of a stencil row as one 32-byte sector, 256-bit loads on the GPU) through
+    quad_yz_tile, including grids whose edges do not fill the 32 x 32 transpose tiles."""
+    static, dr = relax_golden["static"], relax_golden["dr"]
+    a = emu.relax(static, (0, 24, 0, 20), 8, 0.2, 3.02, dr)
+    b = emu.relax(static, (0, 24, 0, 20), 8, 0.2, 3.02, dr, transposed=2)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+    rng = np.random.default_rng(4)
+    big = np.ascontiguousarray(np.tile(static, (1, 2, 1))[:, :37, :41]) + 1e-3 * rng.random((24, 37, 41))   # ny = 37, nz = 41
+    a = emu.relax(big, (3, 9, 0, 37), 5, 0.2, 3.02, dr)
+    b = emu.relax(big, (3, 9, 0, 37), 5, 0.2, 3.02, dr, transposed=2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+
+
+def test_kernel_body_equals_the_oracle_twin_bit_for_bit(emu, relax_golden):
+    """The kernel body (state machine, stencil, fixed-sequence sin/cos, correctly rounded division) against the
+    INDEPENDENT restatement in oracle/dbspm_oracle.c ("kernel twin": scipy's Powell in C + tc_ip_twin + det_sincos):
+    every E, theta, phi, nfev and Cartesian tip position must have the same bits.  The GPU test of the same name
+    (tests/test_gpu_parity.py) then pins the sm_100a kernel to the twin; what remains between the twin and the
+    reference-faithful mode is measured below, on the CPU alone."""
+    static, dr = relax_golden["static"], relax_golden["dr"]
+    tw, nf = O.relax_tile(static, 0, 24, 0, 20, 24, 0.2, 3.02, dr, want_nfev=True, twin=True)
+    for layout in (0, 1, 2):
+        etp, cart, nfev = emu.relax(static, (0, 24, 0, 20), 24, 0.2, 3.02, dr, transposed=layout)
+        assert np.array_equal(etp, tw) and np.array_equal(nfev, nf), layout
+        assert np.array_equal(cart, O.sph2cart_twin(tw[..., 1], tw[..., 2], 3.02))
+    # stiff spring, short lever, maxfev exhaustion
+    tw2, nf2 = O.relax_tile(static, 2, 9, 1, 12, 10, 0.5, 2.0, dr, want_nfev=True, twin=True, maxfev=23)
+    etp, _, nfev = emu.relax(static, (2, 9, 1, 12), 10, 0.5, 2.0, dr, maxfev=23)
+    assert np.array_equal(etp, tw2) and np.array_equal(nfev, nf2)
+    # twin vs reference-faithful mode (Lekien-Marsden + libm): E to 1e-6, positions to 1e-6 * rpivot except for a
+    # few Powell branch flips -- this is the whole difference between the GPU result and the reference's arithmetic
+    ref, nfr = O.relax_tile(static, 0, 24, 0, 20, 24, 0.2, 3.02, dr, want_nfev=True)
+    assert np.abs(tw[..., 0] - ref[..., 0]).max() <= 1e-6 * np.abs(ref[..., 0]).max()
+    d = np.abs(O.sph2cart_twin(tw[..., 1], tw[..., 2], 3.02) - np.stack(O.sph2cart(ref[..., 1], ref[..., 2], 3.02))).max(axis=0) / 3.02
+    assert (d > 1e-6).mean() <= 1e-3 and d.max() <= 3e-5, ((d > 1e-6).mean(), d.max())
+
+
+def test_noortho_skew_cell_matches_reference_golden_and_twin(emu, relax_golden, manifest):
+    """relax_noortho_tip_z (interactions.py:88-105) with a genuinely non-orthogonal dR: the fixture was produced by
+    the reference's own function (oracle/make_golden.py noortho); the kernel body must agree with it to the
+    north_star tolerances and with the oracle twin bit for bit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "relax_noortho_reference.npz"))
+    m = manifest["relax_noortho"]
+    static, dr, dR = relax_golden["static"], relax_golden["dr"], g["dR"]
+    assert np.abs(dR - np.diag(np.diag(dR))).max() > 1e-3                  # really skew
+    devs = []
+    for c, (i, j) in enumerate(g["cols"]):
+        i, j = int(i), int(j)
+        ref = g["skew"][c]
+        orc = O.relax_tile(static, i, i + 1, j, j + 1, m["nz"], m["kappa"], m["rpivot"], dr, dR=dR)[0, 0]
+        # the reference inverts dR.T with LAPACK (np.linalg.inv) and multiplies with BLAS on every evaluation; a cofactor
+        # inverse differs from that in the last bits, so for a skew cell the C restatement is pinned to the tolerance, not
+        # to the bit (with dR = diag(dr) it IS bit-identical: tests/test_oracle.py)
+        assert np.abs(orc[:, 0] - ref[:, 0]).max() <= 1e-6 * np.abs(ref[:, 0]).max(), (i, j)
+        etp, cart, _ = emu.relax(static, (i, i + 1, j, j + 1), m["nz"], m["kappa"], m["rpivot"], dr, dR=dR)
+        tw = O.relax_tile(static, i, i + 1, j, j + 1, m["nz"], m["kappa"], m["rpivot"], dr, dR=dR, twin=True)
+        assert np.array_equal(etp, tw)
+        assert np.abs(etp[0, 0, :, 0] - ref[:, 0]).max() <= 1e-6 * np.abs(ref[:, 0]).max()
+        want = np.stack(O.sph2cart(ref[:, 1], ref[:, 2], m["rpivot"]))
+        devs.append(np.abs(cart[:, 0, 0] - want).max(axis=0) / m["rpivot"])
+    devs = np.concatenate(devs)
+    assert devs.max() <= 1e-6, devs.max()                              # every position (measured: 4.7e-8)
+    # the skew really matters: the orthogonal path gives a different answer
+    etp_o, _, _ = emu.relax(static, (5, 6, 7, 8), m["nz"], m["kappa"], m["rpivot"], dr)
+    assert np.abs(etp_o[0, 0, :, 0] - g["skew"][1][:, 0]).max() > 1e-5 * np.abs(g["skew"][1][:, 0]).max()
+
+
+def test_fixed_sequence_sincos(emu):
+    """dbspm_sincos: within one ulp of the host libm over the range a relaxation visits (and far beyond), exact at the
+    special angles of the start point, and the kernel's statement equals the oracle's bit for bit."""
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-10, 10, 400000), rng.uniform(-1e5, 1e5, 400000), np.pi + rng.uniform(-1e-6, 1e-6, 50000),
+                        np.array([np.pi, 0.0, -np.pi, np.pi / 2, 1e-300, -0.0, 3 * np.pi / 4, 2e5, -3.7e8])])
+    s, c = np.empty_like(x), np.empty_like(x)
+    f = emu.L.emu_sincos
+    f.argtypes = [C.POINTER(C.c_double)] * 3 + [C.c_longlong]
+    f(emu._p(x), emu._p(s), emu._p(c), x.size)
+    ulp = lambda a, b: np.abs(a - b) / np.spacing(np.abs(b))
+    assert ulp(s, np.sin(x)).max() <= 1.0 and ulp(c, np.cos(x)).max() <= 1.0
+    assert s[850000] == np.sin(np.pi) and c[850000] == -1.0 and s[850001] == 0.0 and c[850001] == 1.0
+    so, co = O.det_sincos(x)
+    assert np.array_equal(s, so) and np.array_equal(c, co)
+
+
 def test_relax_empty_tile_and_periodic_wrap(emu, relax_golden):
     static, dr = relax_golden["static"], relax_golden["dr"]
     etp, cart, nfev = emu.relax(static, (3, 3, 0, 5), 4, 0.2, 3.02, dr)

@@ -280,7 +280,8 @@ def test_relax_matches_reference_goldens(ops, relax_golden, manifest):
         got = np.stack(O.sph2cart(out[:, 1], out[:, 2], rp))
         dev.append(np.abs(got - want).max(axis=0) / rp)
     dev = np.concatenate(dev)
-    assert (dev > 1e-6).mean() <= 0.05 and dev.max() <= 1e-4, (dev.max(), (dev > 1e-6).mean())
+    # every position of the reference-produced columns within north_star's 1e-6 * rpivot (measured: 2.3e-8)
+    assert dev.max() <= 1e-6, dev.max()
     for c, (i, j) in enumerate(cols[:3]):
         out = ops.relax_noortho_tip_z(int(i), int(j), field, m["kappa"], rp / dr[2], np.arange(m["nz"]), dr, np.diag(dr))
         assert np.abs(out[:, 0] - g["noortho"][c][:, 0]).max() <= 1e-6 * np.abs(g["noortho"][c][:, 0]).max()
@@ -297,7 +298,10 @@ def test_relax_tile_against_oracle(ops, relax_golden):
     assert res["E"].shape == (24, 20, 24) and isinstance(res["E"], np.ndarray)
     assert _rel(res["E"], ref[..., 0]) <= 1e-6
     dev = _dev_positions(res, ref, 3.02)
-    assert (dev > 1e-6).mean() < 2e-3 and dev.max() < 1e-3, ((dev > 1e-6).mean(), dev.max())
+    # 480 columns x 24 heights against the reference-faithful oracle (Lekien-Marsden + libm): the kernel's Catmull-Rom
+    # form and fixed-sequence sin/cos differ from it at 1e-14, which the loosely converged Powell (xtol 1e-4, line-search
+    # tolerance 0.01) amplifies on a few positions.  Measured (CPU, twin vs reference mode): 7.8e-4 outliers, max 1.9e-5
+    assert (dev > 1e-6).mean() <= 1e-3 and dev.max() <= 3e-5, ((dev > 1e-6).mean(), dev.max())
     assert abs(res["nfev"].mean() - nf_ref.mean()) < 1.0
     # sub-tile == the same columns of the full run (what a multi-GPU rank computes)
     sub = ops.relax_grid(static, 0.2, 3.02, dr, 24, tile=(5, 11, 3, 17))
@@ -331,8 +335,54 @@ def test_relax_full_size_subsample(ops):
         devs.append(np.abs(got - want).max(axis=0) / 3.02)
     devs = np.concatenate(devs)
     assert max(errs) <= 1e-6, max(errs)
-    assert (devs > 1e-6).mean() < 5e-3, (devs > 1e-6).mean()
+    # smooth field: measured 2.6e-4 outliers, max 3.0e-6 * rpivot (twin vs reference mode on the CPU)
+    assert (devs > 1e-6).mean() <= 1e-3 and devs.max() <= 1e-5, ((devs > 1e-6).mean(), devs.max())
     assert 15 < float(res["nfev"].float().mean()) < 120
+    # the same columns against the oracle's kernel twin: identical bits
+    for i, j in rng.integers(0, 196, size=(60, 2)):
+        tw, nf = O.relax_tile(host, int(i), int(i) + 1, int(j), int(j) + 1, 24, 0.2, 3.02, dr, want_nfev=True, twin=True)
+        got = torch.stack([res["E"][i, j], res["theta"][i, j], res["phi"][i, j]], dim=-1).cpu().numpy()
+        assert np.array_equal(got, tw[0, 0]) and np.array_equal(res["nfev"][i, j].cpu().numpy(), nf[0, 0]), (i, j)
+
+
+def test_relax_kernel_equals_the_oracle_twin_bit_for_bit(ops, relax_golden, manifest):
+    """The sm_100a relax kernel against the independent CPU restatement of its arithmetic (oracle "kernel twin": scipy's
+    Powell in C + Catmull-Rom stencil in the kernel's summation order + fixed-sequence sin/cos): E, theta, phi, nfev and
+    the Cartesian tip positions must be IDENTICAL, in all three memory layouts, for the orthogonal and the skew-cell path,
+    and on the maxfev exception path.  Whatever separates a GPU result from the reference is therefore the CPU-measured
+    difference between the twin and the reference-faithful mode (tests/test_emulation.py) and nothing else."""
+    static, dr = relax_golden["static"], relax_golden["dr"]
+    tw, nf = O.relax_tile(static, 0, 24, 0, 20, 24, 0.2, 3.02, dr, want_nfev=True, twin=True)
+    cart = O.sph2cart_twin(tw[..., 1], tw[..., 2], 3.02)
+    for layout in (0, 1, 2):
+        res = ops.relax_grid(static, 0.2, 3.02, dr, 24, want_nfev=True, layout=layout)
+        for q, key in enumerate(("E", "theta", "phi")):
+            assert np.array_equal(res[key], tw[..., q]), (layout, key)
+        assert np.array_equal(res["nfev"], nf), layout
+        for q, key in enumerate(("tip_x", "tip_y", "tip_z")):
+            assert np.array_equal(res[key], cart[q]), (layout, key)
+    tw2, nf2 = O.relax_tile(static, 2, 9, 1, 12, 10, 0.5, 2.0, dr, want_nfev=True, twin=True, maxfev=23)
+    res = ops.relax_grid(static, 0.5, 2.0, dr, 10, tile=(2, 9, 1, 12), maxfev=23, want_nfev=True)
+    assert np.array_equal(res["E"], tw2[..., 0]) and np.array_equal(res["nfev"], nf2)
+    # genuinely non-orthogonal cell (interactions.py:88-105, selected at dbspm:520)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "relax_noortho_reference.npz"))
+    m = manifest["relax_noortho"]
+    dR = g["dR"]
+    tws = O.relax_tile(static, 0, 24, 0, 20, m["nz"], m["kappa"], m["rpivot"], dr, dR=dR, twin=True)
+    for layout in (0, 2):
+        res = ops.relax_grid(static, m["kappa"], m["rpivot"], dr, m["nz"], dR=dR, layout=layout)
+        assert np.array_equal(res["E"], tws[..., 0]) and np.array_equal(res["theta"], tws[..., 1]) and np.array_equal(res["phi"], tws[..., 2])
+    field = ops.TricubicField(static)
+    devs = []
+    for c, (i, j) in enumerate(g["cols"]):
+        out = ops.relax_noortho_tip_z(int(i), int(j), field, m["kappa"], m["rpivot"] / dr[2], np.arange(m["nz"]), dr, dR)
+        ref = g["skew"][c]                                            # produced by the reference's relax_noortho_tip_z
+        assert np.abs(out[:, 0] - ref[:, 0]).max() <= 1e-6 * np.abs(ref[:, 0]).max()
+        want = np.stack(O.sph2cart(ref[:, 1], ref[:, 2], m["rpivot"]))
+        got = np.stack(O.sph2cart(out[:, 1], out[:, 2], m["rpivot"]))
+        devs.append(np.abs(got - want).max(axis=0) / m["rpivot"])
+    devs = np.concatenate(devs)
+    assert devs.max() <= 1e-6, devs.max()                              # every position (measured: 4.7e-8)
 
 
 # ------------------------------------------------------------------------------------ glue
