@@ -212,12 +212,9 @@ def run_gpu_arm(args):
     from dbspm_b200.input_parser import default_params
     from argparse import Namespace
 
-    # keep stdout to the one JSON line: NCCL prints its version banner there at any NCCL_DEBUG level
-    if "DBSPM_NCCL_DEBUG" in os.environ:
-        os.environ["NCCL_DEBUG"] = os.environ["DBSPM_NCCL_DEBUG"]
-    else:
-        os.environ.pop("NCCL_DEBUG", None)
-        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+    # NCCL_DEBUG is left as the caller set it (the driver reads the rank count from NCCL's INFO lines); its log goes to
+    # stderr unless the caller chose a file, so that stdout stays the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, dev = parallel.init_from_env()
     assert dev.type == "cuda", "bench.py needs a GPU (use --impl reference for the CPU arm)"
     if world != args.gpus and rank == 0:

@@ -39,7 +39,9 @@ def _parser() -> ArgumentParser:
     p.add_argument("-V", dest="V", type=float, help="Pauli-repulsion (SR) scaling parameter.")
     p.add_argument("-k", "--kappa", dest="K", type=float, help="Probe torsion spring constant. [eV/rad]")
     p.add_argument("-r", "--rpivot", dest="RPIVOT", type=float, help="Length of the probe lever. [Ang]")
-    p.add_argument("--min-method", dest="MINMETHOD", type=str, help="Minimization method (only Powell).")
+    p.add_argument("--min-method", dest="MINMETHOD", type=str,
+                   help="Minimization method.  Only 'Powell' (the reference's default, restated step for step on the GPU) is "
+                        "available; any other scipy method name raises NotImplementedError.")
     p.add_argument("-b", "--bias", action="store", type=float, default=0.5, help="STM bias (V) (brstm step).")
     p.add_argument("-w", "--weight", action="store", type=float, default=0.5,
                    help="weight of the s orbital in the BRSTM calculation.")
@@ -62,10 +64,19 @@ def _merge_params(options: Namespace, say) -> Namespace:
     for k in default_params:
         src = "c" if getattr(options, k, None) is not None else ("i" if file_params.get(k) is not None else "d")
         say(f"{k:10s} = {str(merged[k]):20s} ({src})")
+    # LABEL stays the raw capture of the parser (the reference's regex keeps blanks before a `#` comment, so
+    # `LABEL = foo  # c` names its files 'foo  _es.npz'): files written here carry the reference's names
     merged.setdefault("LABEL", "dbspm")
-    if isinstance(merged["LABEL"], str):
-        merged["LABEL"] = merged["LABEL"].strip()
     return Namespace(**merged)
+
+
+def _existing(name: str) -> str:
+    """A file the reference (or this program) wrote under LABEL; tolerates a LABEL with stray blanks on either side."""
+    import os
+    if os.path.exists(name):
+        return name
+    alt = name.replace(" ", "")
+    return alt if os.path.exists(alt) else name
 
 
 def main(argv=None) -> int:
@@ -125,6 +136,9 @@ def main(argv=None) -> int:
             calc.grid.set_density(label, win.cpu().numpy(), safe=False)
             say(f"- Saving {filename}")
             calc.grid.save_density(label, filename=filename)
+        # the reference calls comm.Barrier() after every step (dbspm:335,354): the next step of the same invocation
+        # (relax) reads this file on every rank, so nobody may run ahead of rank 0's write
+        parallel.barrier()
 
     if steps.sr:
         say("> Calculating SR interaction.")
@@ -146,9 +160,9 @@ def main(argv=None) -> int:
         for name in params.COMPONENTS:
             name = str(name).lower()
             if name == "sr":
-                comps.append((np.load(params.LABEL + f"_sr_a{params.ALPHA:.2f}.npz")["sr"], params.V))
+                comps.append((np.load(_existing(params.LABEL + f"_sr_a{params.ALPHA:.2f}.npz"))["sr"], params.V))
             else:
-                comps.append((np.load(params.LABEL + f"_{name}.npz")[name], 1.0))
+                comps.append((np.load(_existing(params.LABEL + f"_{name}.npz"))[name], 1.0))
         static = ops.build_static(comps, device=device)
         gridS = calc.gridS
         relax_grid, _, nbox = get_grid_from_params(params, gridS, nidx=True, nbox=True, numbers=gridS.numbers,
@@ -173,6 +187,7 @@ def main(argv=None) -> int:
             for key in ("E", "tip_x", "tip_y", "tip_z"):
                 relax_grid.set_density(key, res[key].cpu().numpy(), safe=False)
             relax_grid.save_density("E", "tip_x", "tip_y", "tip_z", filename=fname)
+        parallel.barrier()                                   # dbspm:619
         steptime["relax"] = dt.now() - t0
     if steps.brstm:
         # dbspm:644-667: s/p-wave STM signal gathered at the relaxed tip-apex positions.  The stm file
@@ -194,6 +209,7 @@ def main(argv=None) -> int:
             out.save_density("data", filename=f"brstm_{params.LABEL}_V{options.bias:.3f}_ws{ws_:.2f}.npz")
             say("BRSTM calculated.")
             steptime["brstm"] = dt.now() - t0
+        parallel.barrier()
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     t_end = dt.now()
@@ -204,6 +220,7 @@ def main(argv=None) -> int:
     for k, v in steptime.items():
         say(f"{k:7s} | {v}")
     say("Done.")
+    parallel.shutdown()
     return 0
 
 

@@ -428,7 +428,7 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
         pow_fast_bounds(alpha0, &P.pow_lo[0], &P.pow_hi[0]);
         pow_fast_bounds(alpha1, &P.pow_lo[1], &P.pow_hi[1]);
         P.pow_tab_off = (int)align_up(smem, 16);
-        smem = (size_t)P.pow_tab_off + DBSPM_POW_TABLE_LEN * sizeof(double);
+        smem = (size_t)P.pow_tab_off + DBSPM_POW_TABLE_LEN * POW_TAB_COPIES * sizeof(double);   // 12 KB: 16 bank-disjoint copies
     }
     P.tiles = (inner + (1LL << P.tshift) - 1) >> P.tshift;
     const long long nblocks = outer * P.tiles;

@@ -159,11 +159,19 @@ HD size_t axis_smem_bytes(int n, int tshift)
     return (size_t)n * 16 + (size_t)n * 4 + ((size_t)n << tshift) * 16;
 }
 
-HD double pow_nonneg(double v, double alpha)
+// v^alpha as numpy's `**` gives it for the cases a density array can hold: rho >= 0 upstream (grid.py:450-464
+// filter_neg) -> exp(alpha log v), 0 -> exp(-inf) = 0; a negative value (unfiltered noise) -> NaN for a fractional
+// alpha, like numpy, and the signed finite power for an integer-valued alpha (numpy: (-2.0)**2.0 = 4.0)
+HD double pow_signed(double v, double alpha)
 {
-    // rho >= 0 upstream (grid.py:450-464 filter_neg); 0 -> exp(-inf) = 0; v < 0 -> NaN like numpy
+    if (v < 0.0 && alpha == trunc(alpha) && fabs(alpha) < 9007199254740992.0) {
+        const double r = exp(alpha * log(-v));
+        return (fmod(alpha, 2.0) != 0.0) ? -r : r;
+    }
     return exp(alpha * log(v));
 }
+
+HD double pow_nonneg(double v, double alpha) { return pow_signed(v, alpha); }
 
 // ---- table-driven v^alpha: 21 FP64 operations instead of the 46 of exp(alpha * log(v)) ----------------------
 // The powered first pass is FP64-issue bound, so the operation count is what matters.
@@ -201,7 +209,7 @@ __host__ __device__ __noinline__
 #else
 __attribute__((noinline))
 #endif
-static double pow_cold(double v, double alpha) { return exp(alpha * log(v)); }
+static double pow_cold(double v, double alpha) { return pow_signed(v, alpha); }
 
 // inputs for which pow_fast_core is valid: normal numbers whose result stays inside 2^+-1000
 HD void pow_fast_bounds(double alpha, double *lo, double *hi)
@@ -211,15 +219,20 @@ HD void pow_fast_bounds(double alpha, double *lo, double *hi)
     *hi = exp2(1000.0 / a);
 }
 
-HD double pow_fast_core(double v, double alpha, const double *tab);
+// Table addressing: entry e of copy c sits at tab[e * pstride + c].  On the device the block stages POW_TAB_COPIES = 16
+// copies (pstride = 16) and a lane reads copy (lane & 15): a 64-bit shared-memory load is served per half-warp, and the 16
+// lanes of a half-warp then hit 16 different bank pairs whatever entries they ask for.  With one copy the 32 random
+// entries of a warp collided two- to four-fold (ncu, round 1: 43 % of the pass's shared-memory wavefronts were conflicts).
+#define POW_TAB_COPIES 16
+HD double pow_fast_core(double v, double alpha, const double *tab, int pstride, int pcopy);
 HD double pow_fast(double v, double alpha, const double *tab)
 {
     double lo, hi;
     pow_fast_bounds(alpha, &lo, &hi);
-    return (v >= lo && v <= hi) ? pow_fast_core(v, alpha, tab) : pow_cold(v, alpha);
+    return (v >= lo && v <= hi) ? pow_fast_core(v, alpha, tab, 1, 0) : pow_cold(v, alpha);
 }
 
-HD double pow_fast_core(double v, double alpha, const double *tab)
+HD double pow_fast_core(double v, double alpha, const double *tab, int pstride, int pcopy)
 {
     const long long b = dbspm_d2ll(v);
     const int hi = (int)(b >> 32);
@@ -227,13 +240,7 @@ HD double pow_fast_core(double v, double alpha, const double *tab)
     const double m = dbspm_ll2d((b & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL);
     // exponent as a double without a conversion instruction: (1.5 * 2^52 + e) - 1.5 * 2^52
     const double ed = dbspm_ll2d(0x4338000000000000LL + (long long)((hi >> 20) - 1023)) - 6755399441055744.0;
-    // one 16-byte look-up for (invc_i, t_i): the table is 16-byte aligned in shared memory
-#if defined(__CUDA_ARCH__)
-    const double2 lt = *reinterpret_cast<const double2 *>(tab + 2 * i);
-    const double invc = lt.x, ti = lt.y;
-#else
-    const double invc = tab[2 * i], ti = tab[2 * i + 1];
-#endif
+    const double invc = tab[(2 * i) * pstride + pcopy], ti = tab[(2 * i + 1) * pstride + pcopy];
     const double r = fma(m, invc, -1.0);
     double p = 0.2060992915555662;
     p = fma(p, r, -0.2404491734814939);
@@ -254,7 +261,7 @@ HD double pow_fast_core(double v, double alpha, const double *tab)
     q = fma(q, t, 0.24022650695910072);
     q = fma(q, t, 0.6931471805599453);
     q = q * t;
-    const double E = tab[64 + (ki & 31)];
+    const double E = tab[(64 + (ki & 31)) * pstride + pcopy];
     const double res = fma(E, q, E);
     return dbspm_ll2d(dbspm_d2ll(res) + ((long long)(ki >> 5) << 52));
 }
@@ -386,10 +393,15 @@ HD void axis2_first(const AxisParams &P, cplx *s, const cplx *tw, const cplx *gi
             if (do_pow) {
                 if (ptab) {
                     const double plo = P.pow_lo[which], phi = P.pow_hi[which];
+#if defined(__CUDA_ARCH__)
+                    const int pstride = POW_TAB_COPIES, pcopy = tid & (POW_TAB_COPIES - 1);
+#else
+                    const int pstride = 1, pcopy = 0;
+#endif
 #pragma unroll
                     for (int k = 0; k < R; ++k) {
-                        v[k].x = (v[k].x >= plo && v[k].x <= phi) ? pow_fast_core(v[k].x, alpha, ptab) : pow_cold(v[k].x, alpha);
-                        v[k].y = (v[k].y >= plo && v[k].y <= phi) ? pow_fast_core(v[k].y, alpha, ptab) : pow_cold(v[k].y, alpha);
+                        v[k].x = (v[k].x >= plo && v[k].x <= phi) ? pow_fast_core(v[k].x, alpha, ptab, pstride, pcopy) : pow_cold(v[k].x, alpha);
+                        v[k].y = (v[k].y >= plo && v[k].y <= phi) ? pow_fast_core(v[k].y, alpha, ptab, pstride, pcopy) : pow_cold(v[k].y, alpha);
                     }
                 } else {
 #pragma unroll
@@ -492,7 +504,7 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
     if (do_pow && P.pow_tab_off >= 0) {
 #if defined(__CUDA_ARCH__)
         double *pt = (double *)(smem_raw + P.pow_tab_off);
-        for (int e = tid; e < DBSPM_POW_TABLE_LEN; e += nthr) pt[e] = dbspm_pow_table_d[e];
+        for (int e = tid; e < DBSPM_POW_TABLE_LEN * POW_TAB_COPIES; e += nthr) pt[e] = dbspm_pow_table_d[e / POW_TAB_COPIES];
         ptab = pt;
 #else
         ptab = dbspm_pow_table_h;

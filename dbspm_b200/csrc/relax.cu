@@ -3,14 +3,20 @@
 // bookkeeping must use separate multiply and add like numpy/scipy; the interpolation stencil
 // asks for fused multiply-adds explicitly (fma()).
 // Replaces dbspm:479-486, dbspm:558-605, pydbspm/interactions.py:49-105, grid.py:325-386.
+#include <stdlib.h>
 #include "capi_common.h"
 #include "relax_body.h"
 
+// One warp per block: the kernel has no block barrier, so a slot of the SM frees when its warp finishes instead of when
+// the slowest of four does (B200, 1024x1024x24, y-quad layout: 4 x 128 threads 72.5 ms, 16 x 32 threads 70.3 ms).
+// 16 blocks = 128 registers, no spills; 96 registers (21 warps) and 80 (25 warps) measured slower (75.6 / 89.2 ms) even with
+// the bracket / Brent state moved to shared memory (RELAX_SMEM_STATE): fewer stencil loads in flight per warp cost more
+// than the extra warps hide.
 #ifndef RELAX_THREADS
-#define RELAX_THREADS 128
+#define RELAX_THREADS 32
 #endif
 #ifndef RELAX_MIN_BLOCKS
-#define RELAX_MIN_BLOCKS 4   /* measured on B200 (1024x1024x24): 3 / 4 / 5 / 6 CTAs of 128 -> 139 / 129 / 141 / 146 ms; 4 = 128 registers, no spills */
+#define RELAX_MIN_BLOCKS 16
 #endif
 
 __global__ void __launch_bounds__(256) relax_cart_kernel(const double *etp, double *cart, long long npos, double rpivot)
@@ -23,7 +29,7 @@ template <int LAYOUT>
 __global__ void __launch_bounds__(RELAX_THREADS, RELAX_MIN_BLOCKS) relax_kernel(const __grid_constant__ RelaxParams P, long long ncol)
 {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    __shared__ double powell_sm[PS_COUNT * RELAX_THREADS];       // Powell-level state, one column per thread
+    __shared__ double powell_sm[(RELAX_SMEM_STATE == 0 ? PS_COUNT : (RELAX_SMEM_STATE == 1 ? PS_P_0 : PS_TOTAL)) * RELAX_THREADS];       // Powell-level state, one column per thread
     relax_column_body<LAYOUT, RELAX_THREADS>(P, col, ncol, powell_sm, threadIdx.x);      // lanes past the end idle inside (warp barrier)
 }
 
@@ -56,10 +62,10 @@ __global__ void __launch_bounds__(256) accumulate_kernel(double *acc, const doub
 __global__ void __launch_bounds__(256) gather_kernel(const double *data, int nx, int ny, int nz,
                                                      const double *pts, size_t npts, double *out)
 {
-    const double inv_n[3] = {1.0 / nx, 1.0 / ny, 1.0 / nz};
+    const double inv_n[3] = {1.0 / nx, 1.0 / ny, 1.0 / nz}, nd[3] = {(double)nx, (double)ny, (double)nz};
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += stride)
-        out[i] = tricubic_eval<0>(data, nx, ny, nz, 0, inv_n, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+        out[i] = tricubic_eval<0>(data, nx, ny, nz, 0, nd, inv_n, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
 }
 
 // np.gradient(E, -dz, axis=2): central differences inside, one-sided first order at the ends
@@ -166,6 +172,7 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
     P.dr[0] = dr[0]; P.dr[1] = dr[1]; P.dr[2] = dr[2];
     for (int q = 0; q < 3; ++q) P.inv_dr[q] = 1.0 / dr[q];
     P.inv_n[0] = 1.0 / nx; P.inv_n[1] = 1.0 / ny; P.inv_n[2] = 1.0 / nzc;
+    P.nd[0] = nx; P.nd[1] = ny; P.nd[2] = nzc;
     P.noortho = dR != nullptr;
     for (int q = 0; q < 9; ++q) P.Minv[q] = 0.0;
     if (dR) {
@@ -178,6 +185,12 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
     if (ncol == 0 || nz_relax == 0) return DBSPM_OK;
     const long long blocks = (ncol + RELAX_THREADS - 1) / RELAX_THREADS;
     DBSPM_REQUIRE(blocks < 2147483647LL, DBSPM_EUNSUPPORTED, "tile too large");
+    // Heights per launch (default: the whole sweep in one launch).  A launch can also continue a sweep: it finds its warm
+    // start in out_etp.  One launch per height keeps every resident warp on the same few z rows (L2-resident working set
+    // with the y-quad layout, which otherwise reads 21 GB from HBM), but measured slower on B200 (77.9 against 72.5 ms:
+    // 24 launch tails cost more than the L2 misses); DBSPM_RELAX_HEIGHTS_PER_LAUNCH keeps the experiment reproducible.
+    int hpl = nz_relax;
+    if (const char *e = getenv("DBSPM_RELAX_HEIGHTS_PER_LAUNCH")) { const int v = atoi(e); if (v >= 1) hpl = v; }
     if (workspace) {
         // re-lay the potential once per call (~2-5 passes over the window): the largest layout the workspace holds
         const size_t need1 = dbspm_relax_workspace_bytes_layout(nx, ny, nzc, 1), need2 = dbspm_relax_workspace_bytes_layout(nx, ny, nzc, 2);
@@ -190,14 +203,21 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
             dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 31) / 32), (unsigned)nx);
             quad_yz_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_win, (double *)workspace, ny, nzc);
             DBSPM_CUDA_TRY(cudaGetLastError());
-            relax_kernel<2><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
+            for (int kh = nz_relax - 1; kh >= 0; kh -= hpl) {
+                P.k_hi = kh; P.k_lo = kh - hpl + 1 > 0 ? kh - hpl + 1 : 0;
+                relax_kernel<2><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
+            }
         } else {
             dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 3 + 31) / 32), (unsigned)nx);
             transpose_yz_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_win, (double *)workspace, ny, nzc);
             DBSPM_CUDA_TRY(cudaGetLastError());
-            relax_kernel<1><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
+            for (int kh = nz_relax - 1; kh >= 0; kh -= hpl) {
+                P.k_hi = kh; P.k_lo = kh - hpl + 1 > 0 ? kh - hpl + 1 : 0;
+                relax_kernel<1><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
+            }
         }
     } else {
+        P.k_hi = nz_relax - 1; P.k_lo = 0;
         relax_kernel<0><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
     }
     DBSPM_CUDA_TRY(cudaGetLastError());

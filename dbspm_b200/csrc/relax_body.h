@@ -30,6 +30,8 @@ struct RelaxParams {
     int nyp;                  // LAYOUT 1: row length ny + 3 (periodic halo: stored index t holds y = t - 1)
     int i_lo, i_hi, j_lo, j_hi;
     int nz_relax;
+    int k_hi, k_lo;           // this launch sweeps the heights k_hi, k_hi - 1, ..., k_lo (whole sweep: nz_relax - 1 ... 0); the start
+                              // point of height k_hi < nz_relax - 1 is the relaxed (theta, phi) of height k_hi + 1 in out_etp
     double kappa;
     double rpivot;            // params.RPIVOT (used by sph2cart, dbspm:605)
     double npivot;            // rpivot / dr[2]                     (dbspm:558)
@@ -37,6 +39,7 @@ struct RelaxParams {
     double dr[3];
     double inv_dr[3];         // RN(1/dr): division by dr as multiply + two fused corrections (div_by)
     double inv_n[3];          // 1/nx, 1/ny, 1/nzc
+    double nd[3];             // nx, ny, nzc as doubles
     int noortho;
     double Minv[9];           // inv(dR^T), row-major
     double xtol, ftol;
@@ -46,14 +49,70 @@ struct RelaxParams {
     int *out_nfev;            // (ni,nj,nz) or null
 };
 
-// ---- sin and cos of one argument, same bits on the device and on the host ---------------
+// ---- sin and cos, same bits on the device and on the host -----------------------------------
 // A fixed sequence of IEEE operations (explicit fma, no library call): Cody-Waite reduction by pi/2 in three
 // pieces, then the classical degree-13 / degree-14 minimax kernels on [-pi/4, pi/4] (coefficients of fdlibm's
-// __kernel_sin / __kernel_cos).  <= 1.5 ulp for |x| <= 1e5 (tests/test_emulation.py), which is what CUDA's
-// own sincos() delivers; unlike a library call the result does not depend on who compiled the caller, so
-// the CPU twin of this kernel (oracle/dbspm_oracle.c, "kernel twin" mode) reproduces it bit for bit, and
-// it costs a third of the instructions of two libdevice sincos calls.  Larger or non-finite arguments
-// (never produced by a relaxation) go to the library.
+// __kernel_sin / __kernel_cos; the cosine with fdlibm's compensated 1 - z/2).  Within one ulp of glibc for
+// |x| <= 1e5 (tests/test_emulation.py), which is what CUDA's own sincos() delivers; unlike a library call the
+// result does not depend on who compiled the caller, so the CPU twin of this kernel (oracle/dbspm_oracle.c,
+// "kernel twin" mode) reproduces it bit for bit.  Larger or non-finite arguments (never produced by a
+// relaxation) go to the library.  On the device the 16 constants come from constant memory (two per 128-bit
+// uniform load) instead of two 32-bit immediate moves each: a third of the instructions of the first version.
+#define DBSPM_SC_TABLE {0.63661977236758138, 1.5707963267948966e+00, 6.1232339957367574e-17, 8.4784276603688985e-32,            \
+                        1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,                   \
+                        -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,                  \
+                        -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,                  \
+                        2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02}
+static const double dbspm_sc_h[16] = DBSPM_SC_TABLE;
+#if defined(__CUDACC__)
+static __constant__ double dbspm_sc_d[16] = DBSPM_SC_TABLE;
+#endif
+#if defined(__CUDA_ARCH__)
+#define SCC(i) dbspm_sc_d[i]
+#else
+#define SCC(i) dbspm_sc_h[i]
+#endif
+
+// reduced argument r in [-pi/4, pi/4] and quadrant q of x (|x| <= 1e5)
+HD double dbspm_sc_reduce(double x, int *q)
+{
+    const double magic = 6755399441055744.0;                       // 1.5 * 2^52: (v + magic) - magic = rint(v)
+    const double t = fma(x, SCC(0), magic);
+    const double k = t - magic;
+#if defined(__CUDA_ARCH__)
+    *q = __double2loint(t);
+#else
+    long long tb; memcpy(&tb, &t, sizeof tb);
+    *q = (int)(tb & 0xffffffffLL);
+#endif
+    double r = fma(-k, SCC(1), x);
+    r = fma(-k, SCC(2), r);
+    return fma(-k, SCC(3), r);
+}
+
+HD void dbspm_sc_kernel(double r, int q, double *sn, double *cs)
+{
+    const double z = r * r;
+    double ps = SCC(4);
+    ps = fma(ps, z, SCC(5));
+    ps = fma(ps, z, SCC(6));
+    ps = fma(ps, z, SCC(7));
+    ps = fma(ps, z, SCC(8));
+    ps = fma(ps, z, SCC(9));
+    const double s0 = fma(r * z, ps, r);
+    double pc = SCC(10);
+    pc = fma(pc, z, SCC(11));
+    pc = fma(pc, z, SCC(12));
+    pc = fma(pc, z, SCC(13));
+    pc = fma(pc, z, SCC(14));
+    pc = fma(pc, z, SCC(15));
+    const double hz = 0.5 * z, w = 1.0 - hz;                       // fdlibm's compensated 1 - z/2
+    const double c0 = w + fma(z * z, pc, (1.0 - w) - hz);
+    const double sa = (q & 1) ? c0 : s0, ca = (q & 1) ? s0 : c0;
+    *sn = (q & 2) ? -sa : sa;
+    *cs = ((q + 1) & 2) ? -ca : ca;
+}
+
 HD void dbspm_sincos(double x, double *sn, double *cs)
 {
     if (!(fabs(x) <= 1.0e5)) {
@@ -64,37 +123,24 @@ HD void dbspm_sincos(double x, double *sn, double *cs)
 #endif
         return;
     }
-    const double magic = 6755399441055744.0;                       // 1.5 * 2^52: (v + magic) - magic = rint(v)
-    const double t = fma(x, 0.63661977236758138, magic);
-    const double k = t - magic;
-#if defined(__CUDA_ARCH__)
-    const int q = __double2loint(t);
-#else
-    long long tb; memcpy(&tb, &t, sizeof tb);
-    const int q = (int)(tb & 0xffffffffLL);
-#endif
-    double r = fma(-k, 1.5707963267948966e+00, x);
-    r = fma(-k, 6.1232339957367574e-17, r);
-    r = fma(-k, 8.4784276603688985e-32, r);
-    const double z = r * r;
-    double ps = 1.58969099521155010221e-10;
-    ps = fma(ps, z, -2.50507602534068634195e-08);
-    ps = fma(ps, z, 2.75573137070700676789e-06);
-    ps = fma(ps, z, -1.98412698298579493134e-04);
-    ps = fma(ps, z, 8.33333333332248946124e-03);
-    ps = fma(ps, z, -1.66666666666666324348e-01);
-    const double s0 = fma(r * z, ps, r);
-    double pc = -1.13596475577881948265e-11;
-    pc = fma(pc, z, 2.08757232129817482790e-09);
-    pc = fma(pc, z, -2.75573143513906633035e-07);
-    pc = fma(pc, z, 2.48015872894767294178e-05);
-    pc = fma(pc, z, -1.38888888888741095749e-03);
-    pc = fma(pc, z, 4.16666666666666019037e-02);
-    const double hz = 0.5 * z, w = 1.0 - hz;                       // fdlibm's compensated 1 - z/2
-    const double c0 = w + fma(z * z, pc, (1.0 - w) - hz);
-    const double sa = (q & 1) ? c0 : s0, ca = (q & 1) ? s0 : c0;
-    *sn = (q & 2) ? -sa : sa;
-    *cs = ((q + 1) & 2) ? -ca : ca;
+    int q;
+    const double r = dbspm_sc_reduce(x, &q);
+    dbspm_sc_kernel(r, q, sn, cs);
+}
+
+// both angles of an evaluation in one basic block (one range test, the constants loaded once, four independent
+// polynomial chains for the scheduler); same bits as two dbspm_sincos calls
+HD void dbspm_sincos2(double a, double b, double *sa, double *ca, double *sb, double *cb)
+{
+    if (!(fabs(a) <= 1.0e5 && fabs(b) <= 1.0e5)) {
+        dbspm_sincos(a, sa, ca);
+        dbspm_sincos(b, sb, cb);
+        return;
+    }
+    int qa, qb;
+    const double ra = dbspm_sc_reduce(a, &qa), rb = dbspm_sc_reduce(b, &qb);
+    dbspm_sc_kernel(ra, qa, sa, ca);
+    dbspm_sc_kernel(rb, qb, sb, cb);
 }
 
 // ---- periodic Catmull-Rom (a = -1/2) tricubic stencil in index units ---------------------
@@ -102,7 +148,11 @@ HD void dbspm_sincos(double x, double *sn, double *cs)
 // exact by definition; q = trunc(p/n) computed with a reciprocal can be off by one, the
 // fused p - q*n is still exact (Sterbenz) and one +-n correction restores fmod's range.
 HD double wrap_coord(double p, double n, double inv_n)
-{   // selects only, no branches: the 64-point stencil that follows must stay warp-converged
+{
+    // inside the cell (every probe except those of columns within a lever length of the border, and the bottom
+    // height, whose pivot plane index is -0.27): fmod(p, n) is p itself.  One almost always uniform branch instead
+    // of a truncation, a fused multiply-add and nine selects on doubles
+    if (p >= 0.0 && p < n) return p;
     const double q = trunc(p * inv_n);
     const double r = fma(-q, n, p);
     const double pos = (r < 0.0) ? r + n : ((r >= n) ? r - n : r);          // p >= 0: fmod in [0,n)
@@ -133,17 +183,33 @@ HD void stencil_idx(int i0, int n, int *idx)
     idx[3] = (idx[2] + 1 == n) ? 0 : idx[2] + 1;
 }
 
-HD void cr_axis(double p, int n, double inv_n, int *i0, double *w)
+// cell index and offset inside the cell
+HD double cr_cell(double p, double nd, double inv_n, int *i0)
 {
-    const double d = wrap_coord(p, (double)n, inv_n);
+    const double d = wrap_coord(p, nd, inv_n);
     const double fl = floor(d);
-    const double u = d - fl, u2 = u * u, u3 = u2 * u;
     *i0 = (int)fl;
+    return d - fl;
+}
+
+HD void cr_weights(double u, double *w)
+{
+    const double u2 = u * u, u3 = u2 * u;
     w[0] = -0.5 * u3 + u2 - 0.5 * u;
     w[1] = 1.5 * u3 - 2.5 * u2 + 1.0;
     w[2] = -1.5 * u3 + 2.0 * u2 + 0.5 * u;
     w[3] = 0.5 * u3 - 0.5 * u2;
 }
+
+HD void cr_axis(double p, int n, double inv_n, int *i0, double *w)
+{
+    cr_weights(cr_cell(p, (double)n, inv_n, i0), w);
+}
+
+#ifndef RELAX_PF
+#define RELAX_PF 0     /* 1 / 2: prefetch.global.L1 / .L2 of the 16 stencil sectors as soon as their addresses are known (layout 2).
+                          Measured on B200: 105 ms against 72.6 ms without -- the CCTL prefetches cost more than the waits they hide */
+#endif
 
 // LAYOUT 0: g[(x*ny + y)*nz + z] (the caller's array, z fastest)
 // LAYOUT 1: g[(x*nz + z)*nyp + (y + 1)], nyp = ny + 3 (y fastest with a periodic halo: the 32 lanes of a
@@ -166,13 +232,13 @@ HD void ld_quad(const double *p, double *q)
 }
 
 template <int LAYOUT>
-HD double tricubic_eval(const double *g, int nx, int ny, int nz, int nyp, const double *inv_n, double x, double y, double z)
+HD double tricubic_eval(const double *g, int nx, int ny, int nz, int nyp, const double *nd, const double *inv_n, double x, double y, double z)
 {
     int ix, iy, iz;
     double wx[4], wy[4], wz[4];
-    cr_axis(x, nx, inv_n[0], &ix, wx);
-    cr_axis(y, ny, inv_n[1], &iy, wy);
-    cr_axis(z, nz, inv_n[2], &iz, wz);
+    const double ux = cr_cell(x, nd[0], inv_n[0], &ix);
+    const double uy = cr_cell(y, nd[1], inv_n[1], &iy);
+    const double uz = cr_cell(z, nd[2], inv_n[2], &iz);
     // 32-bit element offsets (the C ABI guarantees the element count < 2^31)
     int xo[4], yo[4], zo[4];
     stencil_idx(ix, nx, xo);
@@ -185,11 +251,28 @@ HD double tricubic_eval(const double *g, int nx, int ny, int nz, int nyp, const 
         const int y1 = (iy >= ny) ? iy - ny : iy;
 #pragma unroll
         for (int c = 0; c < 4; ++c) { xo[c] *= 4 * ny * nz; zo[c] *= 4 * ny; yo[c] = 4 * y1; }
+#if defined(__CUDA_ARCH__) && RELAX_PF
+        // The 16 loads below do not fit in the register file at once (128 registers of results): the compiler issues
+        // them two or three at a time and every batch costs a trip to the L2 (ncu: five serialised waits per
+        // evaluation).  Prefetches need no registers -- but measured slower (see RELAX_PF), so this is off.
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#if RELAX_PF == 2
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (xo[a] + zo[c] + yo[0])));
+#else
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(g + (xo[a] + zo[c] + yo[0])));
+#endif
+#endif
     } else {
         const int y1 = (iy >= ny) ? iy - ny : iy;          // stored index of plane y1 - 1
 #pragma unroll
         for (int c = 0; c < 4; ++c) { xo[c] *= nyp * nz; zo[c] *= nyp; yo[c] = y1 + c; }
     }
+    cr_weights(ux, wx);
+    cr_weights(uy, wy);
+    cr_weights(uz, wz);
     double r = 0.0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -239,8 +322,7 @@ HD double relax_objective(const RelaxParams &P, int oi, int oj, int ok, double t
     const double d = M_PI - th;
     const double spr = 0.5 * P.kappa * (d * d);
     double sth, cth, saz, caz;
-    dbspm_sincos(th, &sth, &cth);
-    dbspm_sincos(az, &saz, &caz);
+    dbspm_sincos2(th, az, &sth, &cth, &saz, &caz);
     double ox, oy, oz;
     if (!P.noortho) {
         ox = div_by(P.rpivot_rt * sth * caz, P.dr[0], P.inv_dr[0]);
@@ -258,7 +340,7 @@ HD double relax_objective(const RelaxParams &P, int oi, int oj, int ok, double t
     if (dbspm_emu_interp_hook)
         return dbspm_emu_interp_hook((double)oi + ox, (double)oj + oy, (double)ok + oz) + spr;
 #endif
-    return tricubic_eval<LAYOUT>(P.grid, P.nx, P.ny, P.nzc, P.nyp, P.inv_n, (double)oi + ox, (double)oj + oy, (double)ok + oz) + spr;
+    return tricubic_eval<LAYOUT>(P.grid, P.nx, P.ny, P.nzc, P.nyp, P.nd, P.inv_n, (double)oi + ox, (double)oj + oy, (double)ok + oz) + spr;
 }
 
 // ---- Powell / Brent / bracket state machine -----------------------------------------------
@@ -290,41 +372,66 @@ enum RelaxShared {
     PS_X1_0, PS_X1_1,              // point at the start of the iteration
     PS_D0_0, PS_D0_1, PS_D1_0, PS_D1_1,   // direction set
     PS_FVAL, PS_FX, PS_FX2, PS_DELTA,
-    PS_COUNT
+    PS_COUNT,
+    // optional residents (RELAX_SMEM_STATE): the bracket / Brent variables, then the line-search origin and direction
+    PS_S0 = PS_COUNT, PS_P_0 = PS_S0 + 11, PS_P_1, PS_XI_0, PS_XI_1,
+    PS_TOTAL
 };
 
+// Which optimiser state lives in the thread's shared-memory column instead of registers (occupancy against LDS/STS
+// traffic): 0 = Powell-level state only; 1 = + the 11 bracket / Brent variables; 2 = + line-search origin and direction
+#ifndef RELAX_SMEM_STATE
+#define RELAX_SMEM_STATE 0
+#endif
+
 struct PowellRegs {
+#if RELAX_SMEM_STATE < 2
     double p[2], xi[2];            // line search: origin and direction
+#endif
+#if RELAX_SMEM_STATE < 1
     double s[11];                  // bracket (xa xb xc fa fb fc w) and Brent (x w v fx fw fv a b deltax rat u) share storage
+#endif
     int pc, which, bigind, iter, nfev, it;
 };
+#if RELAX_SMEM_STATE < 1
+#define RS(i) R.s[i]
+#else
+#define RS(i) sm[(PS_S0 + (i)) * NTHR + tid]
+#endif
+#if RELAX_SMEM_STATE < 2
+#define RP(i) R.p[i]
+#define RXI(i) R.xi[i]
+#else
+#define RP(i) sm[(PS_P_0 + (i)) * NTHR + tid]
+#define RXI(i) sm[(PS_XI_0 + (i)) * NTHR + tid]
+#endif
 // bracket view
-#define BR_XA R.s[0]
-#define BR_XB R.s[1]
-#define BR_XC R.s[2]
-#define BR_FA R.s[3]
-#define BR_FB R.s[4]
-#define BR_FC R.s[5]
-#define BR_W  R.s[6]
+#define BR_XA RS(0)
+#define BR_XB RS(1)
+#define BR_XC RS(2)
+#define BR_FA RS(3)
+#define BR_FB RS(4)
+#define BR_FC RS(5)
+#define BR_W  RS(6)
 // Brent view
-#define BT_X   R.s[1]
-#define BT_FX  R.s[4]
-#define BT_W   R.s[0]
-#define BT_V   R.s[2]
-#define BT_FW  R.s[3]
-#define BT_FV  R.s[5]
-#define BT_A   R.s[6]
-#define BT_B   R.s[7]
-#define BT_DX  R.s[8]
-#define BT_RAT R.s[9]
-#define BT_U   R.s[10]
+#define BT_X   RS(1)
+#define BT_FX  RS(4)
+#define BT_W   RS(0)
+#define BT_V   RS(2)
+#define BT_FW  RS(3)
+#define BT_FV  RS(5)
+#define BT_A   RS(6)
+#define BT_B   RS(7)
+#define BT_DX  RS(8)
+#define BT_RAT RS(9)
+#define BT_U   RS(10)
 
 #ifndef RELAX_DRIFT
 #define RELAX_DRIFT 0
 #endif
 
 // ---- one lateral column: sweep z from the top with warm start ------------------------------
-// NTHR = threads per block (the stride of the shared-memory columns); sm = PS_COUNT*NTHR doubles.
+// NTHR = threads per block (the stride of the shared-memory columns); sm = PS_TOTAL*NTHR doubles.
 template <int LAYOUT, int NTHR>
 HDN inline void relax_column_body(const RelaxParams &P, long long col, long long ncol, double *sm, int tid)
 {
@@ -339,18 +446,24 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
     const long long c = done ? 0 : col;
     const int ci = (int)(c / nj), cj = (int)(c - (long long)ci * nj);
     const int oi = P.i_lo + ci, oj = P.j_lo + cj;
-    int k = P.nz_relax - 1;
+    int k = P.k_hi;
     int ok = (int)((double)k + P.npivot);                    // int64 store truncates
     PowellRegs R;
     // start of a minimisation at the current point (scipy: x = asarray(x0); fval = func(x)); the
-    // request "p + 0*0" is x itself
-    PS(PS_X_0) = M_PI; PS(PS_X_1) = 0.0;
+    // request "p + 0*0" is x itself.  The top height starts from (pi, 0); a launch that continues a sweep starts
+    // from the relaxed angles of the height above (warm start, interactions.py:83), written by the previous launch
+    double th0 = M_PI, az0 = 0.0;
+    if (!done && k < P.nz_relax - 1) {
+        const size_t o = (size_t)col * P.nz_relax + (k + 1);
+        th0 = P.out_etp[3 * o + 1]; az0 = P.out_etp[3 * o + 2];
+    }
+    PS(PS_X_0) = th0; PS(PS_X_1) = az0;
     PS(PS_D0_0) = 1.0; PS(PS_D0_1) = 0.0; PS(PS_D1_0) = 0.0; PS(PS_D1_1) = 1.0;
-    R.p[0] = M_PI; R.p[1] = 0.0; R.xi[0] = 0.0; R.xi[1] = 0.0;
+    RP(0) = th0; RP(1) = az0; RXI(0) = 0.0; RXI(1) = 0.0;
     R.nfev = 1; R.iter = 0; R.which = 0; R.bigind = 0; R.it = 0;
     R.pc = done ? PC_IDLE : PC_INIT;
 #pragma unroll
-    for (int q = 0; q < 11; ++q) R.s[q] = 0.0;
+    for (int q = 0; q < 11; ++q) RS(q) = 0.0;
     double alpha = 0.0;
     for (;;) {
         // expensive part: the warp is converged here and all unfinished lanes evaluate the 64-point
@@ -369,9 +482,9 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
         const bool hold = false;
 #endif
 #if defined(DBSPM_EMU_INTERP_HOOK) && !defined(__CUDA_ARCH__)
-        if (!done && !hold && dbspm_emu_trace_hook) dbspm_emu_trace_hook(col, k, R.pc, R.p[0] + alpha * R.xi[0], R.p[1] + alpha * R.xi[1]);
+        if (!done && !hold && dbspm_emu_trace_hook) dbspm_emu_trace_hook(col, k, R.pc, RP(0) + alpha * RXI(0), RP(1) + alpha * RXI(1));
 #endif
-        if (!done && !hold) fe = relax_objective<LAYOUT>(P, oi, oj, ok, R.p[0] + alpha * R.xi[0], R.p[1] + alpha * R.xi[1]);
+        if (!done && !hold) fe = relax_objective<LAYOUT>(P, oi, oj, ok, RP(0) + alpha * RXI(0), RP(1) + alpha * RXI(1));
         WARP_SYNC();
 
         // ---- dispatch on the entry state (cheap, per state) ----
@@ -547,8 +660,8 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
                 }
             }
             if (pc == PC_LS_FINISH) {
-                R.xi[0] = alpha_min * R.xi[0]; R.xi[1] = alpha_min * R.xi[1];
-                PS(PS_X_0) = R.p[0] + R.xi[0]; PS(PS_X_1) = R.p[1] + R.xi[1];
+                RXI(0) = alpha_min * RXI(0); RXI(1) = alpha_min * RXI(1);
+                PS(PS_X_0) = RP(0) + RXI(0); PS(PS_X_1) = RP(1) + RXI(1);
                 PS(PS_FVAL) = fret;
                 pc = PC_AFTER_LS;
             }
@@ -559,9 +672,9 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
                     if (R.which == 0) { R.which = 1; pc = PC_LS_BEGIN; }
                     else pc = PC_ITER_END;
                 } else {
-                    if (R.xi[0] != 0.0 || R.xi[1] != 0.0) {
+                    if (RXI(0) != 0.0 || RXI(1) != 0.0) {
                         if (R.bigind == 0) { PS(PS_D0_0) = PS(PS_D1_0); PS(PS_D0_1) = PS(PS_D1_1); }
-                        PS(PS_D1_0) = R.xi[0]; PS(PS_D1_1) = R.xi[1];
+                        PS(PS_D1_0) = RXI(0); PS(PS_D1_1) = RXI(1);
                     }
                     pc = PC_ITER_BEGIN;
                 }
@@ -574,9 +687,9 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
                     pc = PC_FINISHED;
                 } else {
                     const double x0 = PS(PS_X_0), x1 = PS(PS_X_1);
-                    R.xi[0] = x0 - PS(PS_X1_0); R.xi[1] = x1 - PS(PS_X1_1);         /* direc1 */
+                    RXI(0) = x0 - PS(PS_X1_0); RXI(1) = x1 - PS(PS_X1_1);         /* direc1 */
                     PS(PS_X1_0) = x0; PS(PS_X1_1) = x1;
-                    R.p[0] = x0; R.p[1] = x1;
+                    RP(0) = x0; RP(1) = x1;
                     alpha = 1.0; next = PC_EXTRAP; pc = PC_REQUEST;                   /* x + 1*direc1 */
                 }
             }
@@ -589,13 +702,13 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
                 P.out_etp[3 * o + 1] = x0;
                 P.out_etp[3 * o + 2] = x1;
                 if (P.out_nfev) P.out_nfev[o] = R.nfev;
-                if (--k < 0) {
+                if (--k < P.k_lo) {
                     done = true; pc = PC_IDLE;
                 } else {
                     ok = (int)((double)k + P.npivot);
                     R.nfev = 0; R.iter = 0;
                     PS(PS_D0_0) = 1.0; PS(PS_D0_1) = 0.0; PS(PS_D1_0) = 0.0; PS(PS_D1_1) = 1.0;
-                    R.p[0] = x0; R.p[1] = x1; R.xi[0] = 0.0; R.xi[1] = 0.0;
+                    RP(0) = x0; RP(1) = x1; RXI(0) = 0.0; RXI(1) = 0.0;
                     alpha = 0.0; next = PC_INIT; fresh = true; pc = PC_REQUEST;
                 }
             }
@@ -605,14 +718,14 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
                 pc = PC_LS_BEGIN;
             }
             if (pc == PC_LS_BEGIN) {
-                if (R.which == 0) { R.xi[0] = PS(PS_D0_0); R.xi[1] = PS(PS_D0_1); }
-                else if (R.which == 1) { R.xi[0] = PS(PS_D1_0); R.xi[1] = PS(PS_D1_1); }
+                if (R.which == 0) { RXI(0) = PS(PS_D0_0); RXI(1) = PS(PS_D0_1); }
+                else if (R.which == 1) { RXI(0) = PS(PS_D1_0); RXI(1) = PS(PS_D1_1); }
                 /* which == 2: xi already holds the extrapolation direction */
                 if (R.which < 2) PS(PS_FX2) = PS(PS_FVAL);
-                if (R.xi[0] == 0.0 && R.xi[1] == 0.0) {
+                if (RXI(0) == 0.0 && RXI(1) == 0.0) {
                     pc = PC_AFTER_LS; repeat = true;
                 } else {
-                    R.p[0] = PS(PS_X_0); R.p[1] = PS(PS_X_1);
+                    RP(0) = PS(PS_X_0); RP(1) = PS(PS_X_1);
                     BR_XA = 0.0; BR_XB = 1.0;
                     // bracket's first call is f(p + 0*xi) = f(x), the point whose value is fval: the
                     // objective is a pure function, so the call is counted (the maxfun wrapper may
@@ -644,8 +757,7 @@ HD void relax_cart_body(const double *etp, double *cart, long long npos, double 
     for (long long o = gid; o < npos; o += gstride) {
         const double th = etp[3 * o + 1], az = etp[3 * o + 2];
         double sth, cth, saz, caz;
-        dbspm_sincos(th, &sth, &cth);
-        dbspm_sincos(az, &saz, &caz);
+        dbspm_sincos2(th, az, &sth, &cth, &saz, &caz);
         cart[o] = rpivot * sth * caz;
         cart[npos + o] = rpivot * sth * saz;
         cart[2 * npos + o] = rpivot * cth;

@@ -49,6 +49,18 @@ def _world():
     return (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
 
 
+def barrier() -> None:
+    """All ranks wait for each other (the reference's comm.Barrier() between steps); no-op for one process.  With NCCL
+    the host blocks until the barrier collective has run on the device, i.e. after everything enqueued before it."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
+def shutdown() -> None:
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.broadcast(t, src)
@@ -174,21 +186,35 @@ def x_slab(nx: int, G: int, h: int):
 _SYMM: dict = {}
 
 
+MAX_PEERS = 8          # DBSPM_MAX_PEERS of csrc/corr_body.h: pointer slots of the fused-exchange kernels
+
+
+def _agreed(ok: bool, pg, device) -> bool:
+    """True only if `ok` holds on EVERY rank of the group: the choice between the peer-store path and the NCCL
+    exchange must be collective, or some ranks would sit in a symmetric-memory barrier while the others call
+    all_to_all_single."""
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=pg)
+    return bool(int(flag.item()))
+
+
 def peer_buffer(key, dims, pg, device):
     """A float64 buffer of shape `dims` in symmetric memory, mapped into every process of group `pg` (cached under
-    `key`): (buffer, handle) or None when symmetric memory is unavailable."""
-    if device.type != "cuda" or os.environ.get("DBSPM_NO_PEER"):
+    `key`): (buffer, handle) or None when symmetric memory is unavailable on any rank of the group or the group has
+    more ranks than the kernels have peer-pointer slots.  Collective over the group on first use."""
+    if device.type != "cuda" or os.environ.get("DBSPM_NO_PEER") or dist.get_world_size(pg) > MAX_PEERS:
         return None
     key = (key, tuple(int(v) for v in dims), id(pg), device.index)
     if key not in _SYMM:
+        got = None
         try:
             import torch.distributed._symmetric_memory as symm
             buf = symm.empty(tuple(int(v) for v in dims), dtype=torch.float64, device=device)
             hdl = symm.rendezvous(buf, pg)
-            _SYMM[key] = (buf, hdl)
+            got = (buf, hdl)
         except Exception as exc:                                   # noqa: BLE001 -- any failure = no peer path
             print(f"dbspm_b200: symmetric memory unavailable ({exc!r}); exchanging through NCCL", flush=True)
-            _SYMM[key] = None
+        _SYMM[key] = got if _agreed(got is not None, pg, device) else None
     return _SYMM[key]
 
 
@@ -196,20 +222,8 @@ def peer_receive_buffer(shape, G: int, pg, device):
     """This rank's (2, nx, ny/G, nz) float64 receive buffer of the fused exchange, allocated in symmetric memory and
     mapped into every process of the group (torch.distributed._symmetric_memory): returns (buffer, handle) or None
     when symmetric memory is unavailable (CPU tests, no peer access) -- the callers then exchange through NCCL."""
-    if device.type != "cuda" or os.environ.get("DBSPM_NO_PEER"):
-        return None
-    key = (tuple(int(v) for v in shape), int(G), id(pg), device.index)
-    if key not in _SYMM:
-        try:
-            import torch.distributed._symmetric_memory as symm
-            nx, ny, nz = key[0]
-            buf = symm.empty((2, nx, ny // G, nz), dtype=torch.float64, device=device)
-            hdl = symm.rendezvous(buf, pg)
-            _SYMM[key] = (buf, hdl)
-        except Exception as exc:                                   # noqa: BLE001 -- any failure = no peer path
-            print(f"dbspm_b200: symmetric memory unavailable ({exc!r}); exchanging through NCCL", flush=True)
-            _SYMM[key] = None
-    return _SYMM[key]
+    nx, ny, nz = (int(v) for v in shape)
+    return peer_buffer("recv", (2, nx, ny // int(G), nz), pg, device)
 
 
 def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, groups, dst: int = 0, on_stage=None,

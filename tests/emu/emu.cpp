@@ -373,7 +373,7 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
                                     double xtol, double ftol, int maxfev,
                                     double *out_etp, double *out_cart, int *out_nfev, int transposed)
 {
-    double powell_sm[PS_COUNT];
+    double powell_sm[PS_TOTAL];
     RelaxParams P;
     P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc; P.nyp = ny + 3;
     P.i_lo = i_lo; P.i_hi = i_hi; P.j_lo = j_lo; P.j_hi = j_hi; P.nz_relax = nz_relax;
@@ -381,6 +381,7 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
     P.dr[0] = dr[0]; P.dr[1] = dr[1]; P.dr[2] = dr[2];
     for (int q = 0; q < 3; ++q) P.inv_dr[q] = 1.0 / dr[q];
     P.inv_n[0] = 1.0 / nx; P.inv_n[1] = 1.0 / ny; P.inv_n[2] = 1.0 / nzc;
+    P.nd[0] = nx; P.nd[1] = ny; P.nd[2] = nzc;
     P.noortho = dR != nullptr;
     for (int q = 0; q < 9; ++q) P.Minv[q] = 0.0;
     if (dR) {
@@ -388,6 +389,7 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
         if (!inv3(dRT, P.Minv)) return -1;
     }
     P.xtol = xtol; P.ftol = ftol; P.maxfev = maxfev; P.maxiter = 2000;
+    P.k_hi = nz_relax - 1; P.k_lo = 0;
     P.out_etp = out_etp; P.out_cart = out_cart; P.out_nfev = out_nfev;
     const long long ncol = (long long)(i_hi - i_lo) * (j_hi - j_lo);
     std::vector<double> tr;
@@ -403,7 +405,11 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
                         for (int tx = 0; tx < 32; ++tx)
                             quad_yz_tile(static_win, tr.data(), ny, nzc, tile.data(), bx, by, x, tx, 0, 1);
         P.grid = tr.data();
-        for (long long c = 0; c < ncol; ++c) relax_column_body<2, 1>(P, c, ncol, powell_sm, 0);
+        // one "launch" per height, as the library does for large tiles: the warm start travels through out_etp
+        for (int kh = nz_relax - 1; kh >= 0; --kh) {
+            P.k_hi = P.k_lo = kh;
+            for (long long c = 0; c < ncol; ++c) relax_column_body<2, 1>(P, c, ncol, powell_sm, 0);
+        }
     } else if (transposed) {
         // what transpose_yz_kernel does, block by block: the body has one block barrier, so it is run
         // as a 32 x 1 thread block with each phase completed for all tx before the next starts --
@@ -429,7 +435,11 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
                         }
                 }
         P.grid = tr.data();
-        for (long long c = 0; c < ncol; ++c) relax_column_body<1, 1>(P, c, ncol, powell_sm, 0);
+        // launches of five heights
+        for (int kh = nz_relax - 1; kh >= 0; kh -= 5) {
+            P.k_hi = kh; P.k_lo = kh - 4 > 0 ? kh - 4 : 0;
+            for (long long c = 0; c < ncol; ++c) relax_column_body<1, 1>(P, c, ncol, powell_sm, 0);
+        }
     } else {
         for (long long c = 0; c < ncol; ++c) relax_column_body<0, 1>(P, c, ncol, powell_sm, 0);
     }
@@ -444,8 +454,8 @@ extern "C" void emu_sincos(const double *x, double *s, double *c, long long n)
 
 extern "C" double emu_tricubic(const double *g, int nx, int ny, int nz, double x, double y, double z)
 {
-    const double inv_n[3] = {1.0 / nx, 1.0 / ny, 1.0 / nz};
-    return tricubic_eval<0>(g, nx, ny, nz, 0, inv_n, x, y, z);
+    const double inv_n[3] = {1.0 / nx, 1.0 / ny, 1.0 / nz}, nd[3] = {(double)nx, (double)ny, (double)nz};
+    return tricubic_eval<0>(g, nx, ny, nz, 0, nd, inv_n, x, y, z);
 }
 
 // div_by(x, d, RN(1/d)) against x / d on random operands: returns the number of mismatching bit patterns

@@ -184,6 +184,15 @@ def test_pow_fast_accuracy(emu):
     with np.errstate(all="ignore"):
         want = np.power(x, 1.08)
     assert np.array_equal(emu.pow_fast(x, 1.08), want, equal_nan=True)
+    # unfiltered densities with small negative noise: numpy's `**` stays finite for an integer-valued exponent
+    x = np.array([-2.0, -1e-7, -0.5, 3.0, 0.0])
+    for alpha in (2.0, 3.0):
+        got = emu.pow_fast(x, alpha)
+        assert np.allclose(got, np.power(x, alpha), rtol=1e-14, atol=0) and np.array_equal(np.sign(got), np.sign(np.power(x, alpha)))
+    a = np.random.default_rng(5).standard_normal((6, 4, 8)) * 0.1
+    b = np.random.default_rng(6).random((6, 4, 8))
+    ref = O.density_overlap_fft(a ** 2.0, b ** 2.0, np.ones(3))
+    assert np.abs(emu.corr3d(a, b, np.ones(3), alpha0=2.0, alpha1=2.0) - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
 def test_corr3d_tiny_config_window(emu, overlap_golden):

@@ -59,18 +59,26 @@ def test_overlap_edge_shapes(ops, shape, window):
     assert _rel(got, ref) <= 1e-9
 
 
-def _dist_on_one_gpu(ops, a, b, dr, z_lo, z_hi, G, alpha=1.0, peer=False):
+def _dist_on_one_gpu(ops, a, b, dr, z_lo, z_hi, G, alpha=1.0, peer=False, tip_support=None):
     """The distributed sr/es step with its G ranks run one after the other on this GPU: the three kernels stages
-    per rank, the all-to-all and the gather as block copies (what parallel.sr_es_distributed does over NCCL)."""
+    per rank, the all-to-all and the gather as block copies (what parallel.sr_es_distributed does over NCCL).
+    tip_support = (s_lo, s_len): compact tip -- the forward pass reads the z-ranges of the pruned problem in place
+    (dbspm_corr3d_dist_fwd*_cut_f64) and every later stage runs on the pruned z length."""
     dev = torch.device("cuda", 0)
     A, B = torch.as_tensor(a, device=dev), torch.as_tensor(b, device=dev)
     nx, ny, nz = A.shape
     nxl = nx // G
+    cut = ops.pruned_cut(nz, z_lo, z_hi, tip_support)
+    kw = {}
+    if cut is not None:
+        kw = {"cut": cut}
+        nz = int(cut[1])
+        z_lo, z_hi = int(cut[6]), int(cut[6]) + (z_hi - z_lo)
     if peer:
         # fused exchange: the "peers" are G receive buffers on this GPU; every rank's y pass stores into all of them
         recv = [torch.full((2, nx, ny // G, nz), float("nan"), dtype=torch.float64, device=dev) for _ in range(G)]
         for g in range(G):
-            ops.dist_forward_peer(A[g * nxl:(g + 1) * nxl], B[g * nxl:(g + 1) * nxl], G, g, [r.data_ptr() for r in recv], alpha, alpha)
+            ops.dist_forward_peer(A[g * nxl:(g + 1) * nxl], B[g * nxl:(g + 1) * nxl], G, g, [r.data_ptr() for r in recv], alpha, alpha, **kw)
         # second exchange fused into the inverse x pass: rows go straight into the buffer of the x-slab's owner
         nwh = (z_hi - z_lo + 1) // 2
         w2 = [torch.full((G, nxl, ny // G, 2 * nwh), float("nan"), dtype=torch.float64, device=dev) for _ in range(G)]
@@ -78,7 +86,7 @@ def _dist_on_one_gpu(ops, a, b, dr, z_lo, z_hi, G, alpha=1.0, peer=False):
             ops.dist_middle_peer(recv[h][0], recv[h][1], dr, (nx, ny, nz), G, h, z_lo, z_hi, [w.data_ptr() for w in w2])
         slabs = [ops.dist_finish(w2[q], (nxl, ny, nz), G, z_lo, z_hi) for q in range(G)]
         return torch.cat(slabs, dim=0).cpu().numpy()
-    sends = [ops.dist_forward(A[g * nxl:(g + 1) * nxl], B[g * nxl:(g + 1) * nxl], G, alpha, alpha) for g in range(G)]
+    sends = [ops.dist_forward(A[g * nxl:(g + 1) * nxl], B[g * nxl:(g + 1) * nxl], G, alpha, alpha, **kw) for g in range(G)]
     Ws = []
     for h in range(G):
         recvA = torch.stack([sends[g][0][h] for g in range(G)]).contiguous()
@@ -105,6 +113,35 @@ def test_overlap_distributed_x_slabs(ops, shape, window, G):
     # compute + exchange in one kernel (peer stores) gives the same bits as send buffer + all-to-all
     fused = _dist_on_one_gpu(ops, a, b, dr, window[0], window[1], G, alpha=1.08, peer=True)
     assert np.array_equal(fused, got)
+
+
+@pytest.mark.parametrize("shape,window,support,G", [
+    ((8, 8, 64), (20, 30), (60, 9), 2), ((6, 12, 48), (10, 22), (44, 8), 3), ((8, 16, 40), (3, 9), (0, 5), 4),
+    ((12, 8, 96), (40, 61), (90, 13), 2), ((8, 8, 64), (20, 30), (60, 9), 1), ((64, 96, 120), (30, 57), (112, 17), 4),
+    ((128, 128, 160), (76, 130), (148, 25), 8), ((256, 384, 64), (20, 31), (61, 8), 2),
+])
+def test_overlap_distributed_compact_tip(ops, shape, window, support, G):
+    """Compact tip on the distributed path (what `dbspm sr es` runs under torchrun when the tip array is exactly zero
+    outside a z-range): the forward y pass reads the z-ranges of the pruned problem in place -- AxisParams::gather with one
+    source slab per x -- and every later stage runs on the pruned z length.  Both the send-buffer form and the fused
+    peer-store form (dbspm_corr3d_dist_fwd_peer_cut_f64) against the numpy oracle and the single-GPU full-length path."""
+    rng = np.random.default_rng(sum(shape) + window[0] + G)
+    nz = shape[2]
+    a = rng.random(shape)
+    b = np.zeros(shape)
+    s_lo, s_len = support
+    planes = (s_lo + np.arange(s_len)) % nz
+    b[:, :, planes] = rng.random(shape[:2] + (s_len,)) + 0.1
+    dr = np.array([0.1, 0.2, 0.3])
+    assert ops.pruned_cut(nz, window[0], window[1], support) is not None          # the pruned path is really taken
+    assert ops.tip_zsupport(b) == support
+    ref = O.density_overlap_fft(a ** 1.08, b ** 1.08, dr)[:, :, window[0]:window[1]]
+    one = ops.density_overlap_window(a, b, dr, window[0], window[1], 1.08, 1.08)
+    for peer in (False, True):
+        got = _dist_on_one_gpu(ops, a, b, dr, window[0], window[1], G, alpha=1.08, peer=peer, tip_support=support)
+        assert got.shape == ref.shape
+        assert _rel(got, ref) <= 1e-9, (shape, window, G, peer, _rel(got, ref))
+        assert _rel(got, one) <= 1e-12, (shape, window, G, peer)
 
 
 def test_overlap_distributed_goldens_and_unsupported(ops, overlap_golden, manifest):
@@ -149,6 +186,19 @@ for peer in (False, True):
             assert err <= 1e-12, (peer, rep, err)
         else:
             assert wins is None
+# compact tip (exactly zero outside 17 planes that wrap through z = 0): the cut forward pass, NCCL and peer-store forms
+Bc = np.zeros(shape); planes = (33 + np.arange(17)) % shape[2]
+Bc[:, :, planes] = rng.random(shape[:2] + (17,)) + 0.1
+bc = torch.as_tensor(Bc, device=dev)
+sup = ops.tip_zsupport(bc)
+assert sup == (33, 17) and ops.pruned_cut(shape[2], 14, 23, sup) is not None
+one_c = ops.density_overlap_window(a, bc, dr, 14, 23, 1.08, 1.08)
+for peer in (False, True):
+    for rep in range(2):
+        wins = parallel.sr_es_distributed(ops, a[x0:x1], bc[x0:x1], 1.08, shape, dr, 14, 23, [list(range(world))], peer=peer, tip_support=sup)
+        if rank == 0:
+            err = float((wins[0] - one_c).abs().max() / one_c.abs().max())
+            assert err <= 1e-12, ("compact", peer, rep, err)
 torch.cuda.synchronize()
 if rank == 0:
     print("DIST_OK", "symm" if parallel.peer_receive_buffer(shape, world, parallel._process_groups([list(range(world))])[0], dev) else "nccl-only")
@@ -256,6 +306,66 @@ def test_overlap_full_size_properties(ops, name):
         # odd number of window planes (a multi-GPU z-slab) goes through the compaction kernel
         odd = ops.density_overlap_window(A, B, dr, 82, 89)
         assert _rel(odd.cpu().numpy(), ref[:, :, 6:13]) <= 1e-9
+
+
+@pytest.mark.parametrize("name", ["triangulene", "tma_cu111"])
+def test_overlap_against_oracle_at_config_sizes(ops, name):
+    """BASELINE configs 2 (240x320x240) and 3 (384x384x160): sr (alpha = 1.08 on both densities) and es on the synthetic
+    densities of SURVEY 8d, whole window against the numpy restatement of get_density_overlap (interactions.py:9-22)."""
+    from dbspm_b200 import synth
+    cfg = synth.CONFIGS[name]
+    dev = torch.device("cuda", 0)
+    dr = np.array(cfg.cell) / np.array(cfg.shape)
+    rhoS, potS, _ = synth.make_sample(cfg, device=dev)
+    rhoT, nrhoT = synth.make_tip(cfg, device=dev, variant="noisy")
+    z_lo, z_hi = (73, 127) if name == "triangulene" else (76, 130)
+    sr = ops.density_overlap_window(rhoS, rhoT, dr, z_lo, z_hi, cfg.alpha, cfg.alpha)
+    es = ops.density_overlap_window(potS, nrhoT, dr, z_lo, z_hi)
+    ref_sr = O.density_overlap_fft(rhoS.cpu().numpy() ** cfg.alpha, rhoT.cpu().numpy() ** cfg.alpha, dr)[:, :, z_lo:z_hi]
+    assert _rel(sr.cpu().numpy(), ref_sr) <= 1e-9
+    del ref_sr
+    ref_es = O.density_overlap_fft(potS.cpu().numpy(), nrhoT.cpu().numpy(), dr)[:, :, z_lo:z_hi]
+    assert _rel(es.cpu().numpy(), ref_es) <= 1e-9
+
+
+def test_overlap_large_slab_sampled_direct_sum(ops):
+    """BASELINE configs[4], the benchmarked 1024x1024x256 slab: the FFT oracle needs ~26 GB of complex temporaries per
+    interaction, so the check is the definition itself -- E[R] = dV * sum_r A[r] * B[(r - R) mod N] evaluated as a direct
+    periodic sum at sampled window points: 8 points per interaction in numpy on the host (the oracle's arithmetic, in
+    x-chunks) and 64 more with a float64 torch dot product of A with the rolled B (independent of any FFT)."""
+    from dbspm_b200 import synth
+    cfg = synth.CONFIGS["large_slab"]
+    dev = torch.device("cuda", 0)
+    nx, ny, nz = cfg.shape
+    dr = np.array(cfg.cell) / np.array(cfg.shape)
+    dV = float(np.prod(dr))
+    z_lo, z_hi = 76, 130
+    rhoS, potS, _ = synth.make_sample(cfg, device=dev)
+    rhoT, nrhoT = synth.make_tip(cfg, device=dev, variant="noisy")
+    sr = ops.density_overlap_window(rhoS, rhoT, dr, z_lo, z_hi, cfg.alpha, cfg.alpha)
+    es = ops.density_overlap_window(potS, nrhoT, dr, z_lo, z_hi)
+    ops.release_workspace()
+    rng = np.random.default_rng(20260104)
+    pts = np.stack([rng.integers(0, nx, 72), rng.integers(0, ny, 72), rng.integers(z_lo, z_hi, 72)], axis=1)
+    pts[0] = (0, 0, z_lo); pts[1] = (nx - 1, ny - 1, z_hi - 1)                  # corners of the window
+    for name, A, B, alpha, win in (("sr", rhoS, rhoT, cfg.alpha, sr), ("es", potS, nrhoT, 1.0, es)):
+        scale = float(win.abs().max())
+        Ap = A if alpha == 1.0 else A ** alpha
+        Bp = B if alpha == 1.0 else B ** alpha
+        got = np.array([float(win[x, y, z - z_lo]) for x, y, z in pts])
+        # (r - R) mod N on every axis == roll of B by +R
+        want = np.array([float(torch.dot(Ap.reshape(-1), torch.roll(Bp, shifts=(int(x), int(y), int(z)), dims=(0, 1, 2)).reshape(-1))) * dV
+                         for x, y, z in pts[8:]])
+        assert np.abs(got[8:] - want).max() <= 1e-9 * scale, (name, np.abs(got[8:] - want).max() / scale)
+        Ah, Bh = Ap.cpu().numpy(), Bp.cpu().numpy()
+        for q, (x, y, z) in enumerate(pts[:8]):
+            acc = 0.0
+            for x0 in range(0, nx, 64):                                          # A[x0:x0+64] against B[(x - R_x) mod nx]
+                xs = (np.arange(x0, x0 + 64) - x) % nx
+                blk = np.roll(Bh[xs], shift=(int(y), int(z)), axis=(1, 2))
+                acc += float(np.vdot(Ah[x0:x0 + 64].ravel(), blk.ravel()))
+            assert abs(got[q] - acc * dV) <= 1e-9 * scale, (name, q, abs(got[q] - acc * dV) / scale)
+        del Ah, Bh, Ap, Bp
 
 
 # ------------------------------------------------------------------------------------ relax
