@@ -165,26 +165,69 @@ def cpu_reference_pass(sample_shape=(256, 256, 128), relax_cols=(64, 64), seed=2
     }
 
 
+def cpu_full_size_overlap(shape, z_lo, z_hi, alpha, seed=20260104):
+    """sr and es ONCE at the benchmarked shape with the numpy restatement of get_density_overlap (interactions.py:9-22,
+    complex fftn of the whole grid, index reversal, roll, slice), one process as the reference runs them (dbspm:320,339).
+    Random positive densities: the cost of the transform does not depend on the values.  ~20 GB of temporaries."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(seed)
+    dr = np.array([0.075, 0.075, 0.075])
+    a = rng.random(shape)
+    b = rng.random(shape)
+    t0 = time.perf_counter()
+    sr = O.density_overlap_fft(a ** alpha, b ** alpha, dr)[:, :, z_lo:z_hi].copy()
+    t1 = time.perf_counter()
+    b -= 0.5
+    es = O.density_overlap_fft(a, b, dr)[:, :, z_lo:z_hi].copy()
+    t2 = time.perf_counter()
+    return {"t_sr": t1 - t0, "t_es": t2 - t1, "grid_pts": int(np.prod(shape)), "checksum": float(sr.sum() + es.sum())}
+
+
 def run_reference_arm(args):
+    """CPU arm: the oracle port of the reference's own algorithm on this box's host cores (the reference is pure Python
+    with no compiled part, DESIGN.md section 5).  sr+es: ONE pass at the benchmarked grid (same config as the GPU arm);
+    relax: a bounded sample of lateral columns on all cores; the bounded sr+es sample of round 1 stays as a secondary field."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    from dbspm_b200 import synth
+    cfg = synth.CONFIGS[args.workload]
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_pass(sample_shape=(64, 64, 64), relax_cols=(8, 8))
-    res = [cpu_reference_pass() for _ in range(args.steps)]
-    t_corr = float(np.mean([r["t_sr"] + r["t_es"] for r in res]))
-    t_rel = float(np.mean([r["t_relax"] for r in res]))
-    r0 = res[0]
-    value = 2 * r0["grid_pts"] / t_corr
+    small = cpu_reference_pass()
+    full = None
+    note = "bounded sample only"
+    try:
+        import psutil
+        need = 12 * 8 * int(np.prod(cfg.shape))
+        if args.reference_full and psutil.virtual_memory().available > 1.3 * need:
+            full = cpu_full_size_overlap(cfg.shape, 76, 130, cfg.alpha)
+            note = "one full-size pass"
+    except Exception as exc:                                   # noqa: BLE001
+        note = f"full-size pass failed ({exc!r}); bounded sample only"
+    if full is not None:
+        t_corr = full["t_sr"] + full["t_es"]
+        value = 2 * full["grid_pts"] / t_corr
+        sample = (f"sr+es: numpy complex fftn restatement of get_density_overlap on the full {cfg.shape[0]}x{cfg.shape[1]}x{cfg.shape[2]} "
+                  f"f64 grid, ONE pass, 1 process (as the reference); relax: " + small["sample"].split("relax: ")[1])
+    else:
+        t_corr = small["t_sr"] + small["t_es"]
+        value = small["pts_per_s"]
+        sample = small["sample"]
+    t_rel_full = cfg.shape[0] * cfg.shape[1] * 24 / small["pos_per_s"]     # relax of the whole grid, extrapolated from the sample
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * (t_corr + t_rel), "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1e3 * (t_corr + t_rel_full), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "cpu_sample": r0["sample"]},
-        "relax": {"value": r0["positions"] / t_rel, "unit": "tip positions/s"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": r0["sample"],
-                         "relax_value": r0["positions"] / t_rel, "relax_unit": "tip positions/s",
-                         "relax_cores": r0["cores_relax"]},
+        "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "cpu_sample": sample, "same_config_as_gpu_arm": full is not None,
+                   "passes": note, "steps_run": 1,
+                   "ms_per_step_note": "sr+es measured" + (" at full size" if full is not None else " on the sample")
+                                       + " + relax of the whole grid extrapolated linearly from the sampled columns"},
+        "relax": {"value": small["pos_per_s"], "unit": "tip positions/s"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "ms_sr": 1e3 * (full or small)["t_sr"], "ms_es": 1e3 * (full or small)["t_es"],
+                         "bounded_sample_value": small["pts_per_s"], "bounded_sample": small["sample"],
+                         "relax_value": small["pos_per_s"], "relax_unit": "tip positions/s", "relax_cores": small["cores_relax"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -246,18 +289,28 @@ def run_gpu_arm(args):
     jobs = plan[rank]
     # N >= 4: the transform itself is distributed inside each group (x-slabs, one all-to-all, gather of the packed
     # window rows); N = 2 has one rank per interaction and N = 1 runs both, so they keep the single-GPU five-pass path
-    groups = None if args.no_dist else parallel.dist_groups(world)
-    if groups is not None and not ops.dist_supported(cfg.shape, len(groups[0])):
-        groups = None
+    # N >= 2 (round 2): ONE group of all N ranks computes sr, then es, with the transform distributed over x-slabs; every rank
+    # ends with the same x-slab of both windows, assembles its static tile, fetches a halo of the lever length from its two
+    # neighbours and relaxes its tile -- the windows travel to rank 0 only for the .npz, beside the relax kernel.
+    slab_mode = (world > 1 and not args.no_dist and not args.legacy_groups and nx % world == 0
+                 and ops.dist_supported(cfg.shape, world))
+    groups = None
+    if slab_mode:
+        groups = [list(range(world))]
+    elif not args.no_dist:
+        groups = parallel.dist_groups(world)
+        if groups is not None and not ops.dist_supported(cfg.shape, len(groups[0])):
+            groups = None
     if groups is not None:
         G = len(groups[0])
         my_which, my_h = rank // G, rank % G
         sx0, sx1 = parallel.x_slab(nx, G, my_h)
+    halo = ops.relax_slab_halo(cfg.rpivot, dr) if slab_mode else 0
     dist_marks = []
     tiles = parallel.split_range(0, nx, world)
     my_il, my_ih = tiles[rank]
     inputs = {0: (rhoS, rhoT, cfg.alpha), 1: (potS, nrhoT, 1.0)}
-    bufs = [torch.empty((nx, ny, zh - zl), dtype=torch.float64, device=dev) for (_, zl, zh) in jobs]
+    bufs = [] if slab_mode else [torch.empty((nx, ny, zh - zl), dtype=torch.float64, device=dev) for (_, zl, zh) in jobs]
     launches = {"n": 0}
 
     def ev():
@@ -287,7 +340,41 @@ def run_gpu_arm(args):
                 marks.append(ev())
         return parallel.gather_windows(plan, bufs, nx, ny, z_lo, z_hi, dev)        # rank 0: [sr, es]
 
+    def slab_interaction(which, rec=None, src=None, supports=None, sliced=False):
+        a, b, al = (src or inputs)[which]
+        if not sliced:
+            a, b = a[sx0:sx1], b[sx0:sx1]
+        return parallel.sr_es_distributed(ops, a, b, al, cfg.shape, dr, z_lo, z_hi, groups, gather=False,
+                                          on_stage=(lambda name: rec.append((name, ev()))) if rec is not None else None,
+                                          peer=not args.no_peer, tip_support=supports[which] if supports else None)
+
+    def slab_step(timed, src=None, vdw_slab=None, sliced=False):
+        """sr, es (x-slabs of all ranks), static tile + halo, relax of the tile; the windows go to rank 0 beside the relax"""
+        e0 = ev()
+        rec = [("start", e0)]
+        sr_slab = slab_interaction(0, rec, src, sliced=sliced)
+        e1 = ev()
+        rec.append(("start", e1))
+        es_slab = slab_interaction(1, rec, src, sliced=sliced)
+        e2 = ev()
+        launches["n"] += 10                                        # per interaction: y fwd | x fwd, z, x inv | y inv
+        w_sr, work_sr = parallel.gather_x_slabs(sr_slab, nx, async_op=True)      # only the .npz needs them on rank 0
+        w_es, work_es = parallel.gather_x_slabs(es_slab, nx, async_op=True)
+        static_slab = ops.build_static([(sr_slab, cfg.V), (es_slab, 1.0), (vdw[sx0:sx1] if vdw_slab is None else vdw_slab, 1.0)])
+        static_loc = parallel.exchange_halo(static_slab, halo)
+        r = ops.relax_grid(static_loc, cfg.kappa, cfg.rpivot, dr, nz_relax, tile=(sx0, sx1, 0, ny), x_slab=((sx0 - halo) % nx, nx))
+        launches["n"] += 6                                         # 3 x accumulate, y-quad re-layout, relax, sph2cart
+        res = parallel.relax_sharded(lambda il, ih: {k: r[k] for k in ("E", "tip_x", "tip_y", "tip_z")}, nx, dev)
+        work_sr.wait(); work_es.wait()
+        e3 = ev()
+        if timed is not None:
+            timed.append((e0, e1, e2, e3))
+            dist_marks.append(rec)
+        return {"static": static_loc, "w_sr": w_sr, "w_es": w_es, "res": res, "r": r, "ev": (e0, e2, e3)}
+
     def step(timed):
+        if slab_mode:
+            return slab_step(timed)["static"]
         e0 = ev()
         mid = []
         wins = corr_phase(inputs, mid)
@@ -325,7 +412,25 @@ def run_gpu_arm(args):
     barrier()
     # distributed transform: rank 0 checks the assembled es window against the single-GPU five-pass path once
     dist_check = None
-    if groups is not None:
+    relax_check = None
+    if slab_mode:
+        # once per run: the es window assembled on rank 0 against the single-GPU five-pass path, and this rank's relaxed
+        # energies (tile + halo form) against the same tile relaxed on the whole static window (must be the same bits)
+        keep = slab_step(None)
+        if rank == 0:
+            one = ops.density_overlap_window(potS, nrhoT, dr, z_lo, z_hi)
+            dist_check = float((keep["w_es"] - one).abs().max() / one.abs().max())
+            sr1 = ops.density_overlap_window(rhoS, rhoT, dr, z_lo, z_hi, cfg.alpha, cfg.alpha)
+            full_static = ops.build_static([(keep["w_sr"], cfg.V), (keep["w_es"], 1.0), (vdw, 1.0)])
+            sub = ops.relax_grid(full_static, cfg.kappa, cfg.rpivot, dr, nz_relax, tile=(sx0, sx0 + 8, 0, ny))
+            relax_check = bool(torch.equal(sub["E"], keep["r"]["E"][:8]) and torch.equal(sub["tip_x"], keep["r"]["tip_x"][:8]))
+            dist_check_sr = float((keep["w_sr"] - sr1).abs().max() / sr1.abs().max())
+            dist_check = max(dist_check, dist_check_sr)
+            del one, sr1, full_static, sub
+        keep.clear()
+        ops.release_workspace(); torch.cuda.empty_cache()
+        barrier()
+    elif groups is not None:
         wins = corr_phase(inputs, None)
         if rank == 0:
             one = ops.density_overlap_window(potS, nrhoT, dr, z_lo, z_hi)
@@ -356,7 +461,7 @@ def run_gpu_arm(args):
     stages = {}
     relax_ms = None
     which0, zl0, zh0 = jobs[0]
-    if zh0 > zl0:
+    if zh0 > zl0 and not slab_mode:
         allskip = sum(SKIP.values())
         for name, bit in SKIP.items():
             ts = []
@@ -379,7 +484,8 @@ def run_gpu_arm(args):
     ts = []
     for it in range(3):
         a = ev()
-        r = ops.relax_grid(static, cfg.kappa, cfg.rpivot, dr, nz_relax, tile=(my_il, my_ih, 0, ny), want_nfev=(it == 0))
+        r = ops.relax_grid(static, cfg.kappa, cfg.rpivot, dr, nz_relax, tile=(my_il, my_ih, 0, ny), want_nfev=(it == 0),
+                           x_slab=((sx0 - halo) % nx, nx) if slab_mode else None)
         b = ev(); torch.cuda.synchronize()
         if it == 0:
             nfev_mean = float(r["nfev"].float().mean()) if r["nfev"].numel() else 0.0
@@ -394,13 +500,19 @@ def run_gpu_arm(args):
         rhoTc, nrhoTc = synth.make_tip(cfg, dev, "compact")
         sup = {0: ops.tip_zsupport(rhoTc), 1: ops.tip_zsupport(nrhoTc)}
         src_c = {0: (rhoS, rhoTc, cfg.alpha), 1: (potS, nrhoTc, 1.0)}
+        def compact_pass():
+            if slab_mode:          # the distributed transform with the z-range cut (dbspm_corr3d_dist_fwd_peer_cut_f64)
+                slab_interaction(0, None, src_c, sup)
+                slab_interaction(1, None, src_c, sup)
+            else:
+                corr_phase(src_c, None, sup)
         for _ in range(2):
-            corr_phase(src_c, None, sup)
+            compact_pass()
         barrier()
         ts = []
         for _ in range(args.steps):
             a = ev()
-            corr_phase(src_c, None, sup)
+            compact_pass()
             b = ev(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
         barrier()
@@ -413,12 +525,41 @@ def run_gpu_arm(args):
         del rhoTc, nrhoTc, src_c
         torch.cuda.empty_cache()
 
+    # ---- same-box yardstick (not the product, outside every timed region): the es window through cuFFT -----------
+    comparators = None
+    if world == 1 and not args.no_cufft:
+        try:
+            dV = float(np.prod(dr))
+
+            def cufft_es():
+                return (torch.fft.irfftn(torch.fft.rfftn(potS) * torch.conj(torch.fft.rfftn(nrhoT)), s=potS.shape)[:, :, z_lo:z_hi] * dV)
+            ref_c = cufft_es()
+            mine = ops.density_overlap_window(potS, nrhoT, dr, z_lo, z_hi)
+            err_c = float((mine - ref_c).abs().max() / ref_c.abs().max())
+            del ref_c, mine
+            ts = []
+            for _ in range(3):
+                a = ev(); cufft_es(); b = ev(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            comparators = {"cufft": {"ms_es": float(np.median(ts)), "value_es_only": N / (float(np.median(ts)) * 1e-3), "unit": UNIT,
+                                     "rel_diff_vs_ours": err_c,
+                                     "what": "torch.fft (cuFFT) float64: rfftn of both arrays, spectrum product with the conjugate, irfftn, "
+                                             "window slice -- the straightforward library implementation of one interaction on the same GPU; "
+                                             "compare with roofline.ms_es"}}
+        except Exception as exc:                                   # noqa: BLE001 -- a comparator must never fail the bench
+            comparators = {"cufft": {"error": repr(exc)[:200]}}
+        torch.cuda.empty_cache()
+
     # ---- end to end: pinned host inputs in, results out, inside the timed region -----------
     e2e = None
     if not args.no_e2e:
         names = {0: ("rhoS", "rhoT", cfg.alpha), 1: ("potS", "nrhoT", 1.0)}
         dev_src = {"rhoS": rhoS, "potS": potS, "rhoT": rhoT, "nrhoT": nrhoT, "vdw": vdw}
-        if groups is not None:
+        if slab_mode:
+            # a rank uploads its x-slab of the four input grids and of the vdW window
+            hosts = {k: torch.empty(v[sx0:sx1].shape, dtype=torch.float64).pin_memory().copy_(v[sx0:sx1]) for k, v in dev_src.items()}
+            outs_h = [torch.empty((nx, ny, nzw), dtype=torch.float64).pin_memory() for _ in range(2)] if rank == 0 else []
+        elif groups is not None:
             # distributed transform: a rank uploads only its x-slab of its interaction's two arrays
             need = set(names[my_which][:2])
             hosts = {k: torch.empty(dev_src[k][sx0:sx1].shape, dtype=torch.float64).pin_memory().copy_(dev_src[k][sx0:sx1])
@@ -437,7 +578,25 @@ def run_gpu_arm(args):
 
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
+        def e2e_slab_step(rec):
+            e0 = ev()
+            for k in hosts:
+                d_in[k].copy_(hosts[k], non_blocking=True)
+            src = {0: (d_in["rhoS"], d_in["rhoT"], cfg.alpha), 1: (d_in["potS"], d_in["nrhoT"], 1.0)}
+            out = slab_step(None, src=src, vdw_slab=d_in["vdw"], sliced=True)     # static is rebuilt from this step's own windows
+            for w, oh in zip((out["w_sr"], out["w_es"]) if rank == 0 else (), outs_h):
+                oh.copy_(w, non_blocking=True)
+            for q, key in enumerate(("E", "tip_x", "tip_y", "tip_z")):
+                out_rel[q].copy_(out["r"][key], non_blocking=True)
+            e_end = ev()
+            torch.cuda.synchronize()
+            if rec is not None:
+                # sr+es: uploads -> both slabs finished; the rest: static, halo, relax, gathers, downloads
+                rec.append((e0.elapsed_time(out["ev"][1]), out["ev"][1].elapsed_time(e_end)))
+
         def e2e_step(rec):
+            if slab_mode:
+                return e2e_slab_step(rec)
             e0 = ev()
             if groups is not None:
                 na, nb, al = names[my_which]
@@ -490,7 +649,10 @@ def run_gpu_arm(args):
             e2e_step(rec)
         barrier()
         tc, tr = max_over_ranks([float(np.mean([x[0] for x in rec])), float(np.mean([x[1] for x in rec]))])
-        if groups is not None:
+        if slab_mode:
+            h2d = 8 * (4 * N // G + Nw // G)
+            d2h = 8 * (sum(int(o.numel()) for o in outs_h) + 4 * ni * ny * nz_relax)
+        elif groups is not None:
             h2d = 8 * (2 * N // G + Nw)
             d2h = 8 * (sum(int(o.numel()) for o in outs_h) + 4 * ni * ny * nz_relax)
         else:
@@ -498,7 +660,11 @@ def run_gpu_arm(args):
             d2h = 8 * (sum(int(b.numel()) for b in bufs) + 4 * ni * ny * nz_relax)
         e2e = {"value": 2 * N / (tc * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_sr_es": tc, "relax_value": nx * ny * nz_relax / (tr * 1e-3), "relax_unit": "tip positions/s",
-               "ms_relax": tr, "note": ("per rank: pinned host -> HBM copies of its x-slab of its interaction's two input "
+               "ms_relax": tr, "note": ("per rank: pinned host -> HBM copies of its x-slab of the four input grids and of the vdW window; "
+                                        "sr, es, static (rebuilt from this step's own windows), halo exchange and relax as in the "
+                                        "device-resident step; rank 0 copies both gathered windows back, every rank its relax tile; "
+                                        "all inside the timed region; byte counts are rank 0's" if slab_mode else
+                                        "per rank: pinned host -> HBM copies of its x-slab of its interaction's two input "
                                         "grids + vdw; rank 0 copies both windows back, every rank its relax tile; all "
                                         "inside the timed region; byte counts are rank 0's" if groups is not None else
                                         "per rank: pinned host -> HBM copies of the input grids of its interaction(s) "
@@ -527,13 +693,18 @@ def run_gpu_arm(args):
             "traffic": (2 * profiled_traffic(args.workload) if world == 1 and profiled_traffic(args.workload) else None),
             "traffic_note": "dram bytes read+write of sr+es (2 x 5 launches), ncu --set full, profiles/traffic.json",
             "peak_source": peak_src,
-            "kernel": ("dbspm_corr3d_dist_{fwd_peer,mid,fin}_f64 = 5 launches per rank (axis_pass y_fwd with peer stores | "
+            "kernel": ("dbspm_corr3d_dist_{fwd_peer,mid_peer,fin}_f64 = 5 launches per rank and interaction (axis_pass y_fwd with peer "
+                       "stores | x_fwd, zfused, x_inv with peer stores | y_inv of the rank's x-slab); no gather inside the timed sr+es "
+                       "region: every rank keeps its x-slab" if slab_mode else
+                       "dbspm_corr3d_dist_{fwd_peer,mid,fin}_f64 = 5 launches per rank (axis_pass y_fwd with peer stores | "
                        "x_fwd, zfused, x_inv | y_inv of the rank's x-slab) + small all-to-all + gather" if groups is not None else
                        "dbspm_corr3d_f64 = 5 launches (axis_pass x_fwd, y_fwd, zfused, axis_pass y_inv, x_inv)"),
             "algorithmic_bytes_per_interaction": balg, "ms_sr_plus_es": t_corr,
-            "ms_sr": t_sr if world == 1 else None, "ms_es": t_es if world == 1 else None,
+            "ms_sr": t_sr if (world == 1 or slab_mode) else None, "ms_es": t_es if (world == 1 or slab_mode) else None,
             "note": "frac = algorithmic bytes of sr+es / (time * n_gpus * peak)"
                     + ("; es alone: %.4f of peak" % (balg / (t_es * 1e-3) / 1e9 / peak) if world == 1 else
+                       "; sr then es, each over all ranks (x-slabs); time = inputs resident -> every rank holds its x-slab of the window"
+                       if slab_mode else
                        "; sr and es run concurrently on disjoint rank groups, time includes the gather to rank 0")}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -548,7 +719,13 @@ def run_gpu_arm(args):
                    "window_z": [z_lo, z_hi], "relax_shape": [nx, ny, nz_relax], "alpha": cfg.alpha, "V": cfg.V,
                    "kappa": cfg.kappa, "rpivot": cfg.rpivot, "tip": "noisy (non-compact, full-z path)",
                    "l2": "inputs are %.2f GB each, far larger than the 126 MB L2 (no flush needed)" % (8 * N / 1e9),
-                   "parallelism": ((f"sr | es on disjoint groups of {G} ranks; inside a group the transform is distributed "
+                   "parallelism": ((f"sr then es over all {G} ranks: x-slab decomposition of the transform (y pass whose stores go straight "
+                                    f"into the owners' buffers over NVLink, x pass + z kernel + inverse x with the second exchange fused "
+                                    f"the same way, inverse y); every rank keeps its x-slab of both windows, adds vdW, fetches a halo of "
+                                    f"{halo} planes from its two neighbours and relaxes its x-tile in slab mode (bit-identical to the whole "
+                                    f"window); windows and relax tiles gathered to rank 0 for the .npz, the window gather beside the relax kernel")
+                                   if slab_mode else
+                                   (f"sr | es on disjoint groups of {G} ranks; inside a group the transform is distributed "
                                     f"over x-slabs (y pass " + ("+ all-to-all through NCCL" if args.no_peer else
                                     "whose stores go straight into the owners' buffers over NVLink (symmetric memory)")
                                     + f", x pass + z kernel + inverse x, small all-to-all of the packed window rows back to "
@@ -564,9 +741,16 @@ def run_gpu_arm(args):
                   "stencil_gbs": nx * ny * nz_relax * nfev_mean * 512 / (relax_ms_max * 1e-3) / 1e9,
                   "l1_nominal_gbs": world * 148 * 128 * 1.965,
                   "hbm_bytes_per_position": 8.0 * nzw / nz_relax + 56.0},
-        "stages_ms": stages, "dist_stages_ms": dist_stages, "dist_check_rel_err_es": dist_check, "compact_tip": compact, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+        "stages_ms": stages, "dist_stages_ms": dist_stages, "dist_check_rel_err": dist_check,
+        "dist_relax_tile_bit_identical": relax_check, "compact_tip": compact, "roofline": roof, "comparators": comparators,
+        "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": n_launch, "clocks": clk.summary(), "wall_s_timed_region": t_wall,
     }
+    # numbers first, prose last (a truncated tail of the line keeps the free-text config, a truncated head the figures)
+    order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "dist_check_rel_err", "dist_relax_tile_bit_identical", "dist_stages_ms", "relax", "roofline", "e2e",
+             "gpu_launches", "clocks", "stages_ms", "comparators", "cpu_baseline", "compact_tip", "wall_s_timed_region", "config"]
+    line = {k: line[k] for k in order if k in line} | {k: v for k, v in line.items() if k not in order}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -584,7 +768,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peer", action="store_true", help="distributed transform: NCCL all-to-all instead of the fused peer-store exchange")
     ap.add_argument("--no-dist", action="store_true", help="N >= 4: replicated inputs + z-slab split instead of the distributed transform")
+    ap.add_argument("--legacy-groups", action="store_true",
+                    help="N >= 4: round-1 plan (an sr group and an es group, windows gathered to rank 0 and broadcast back for relax)")
     ap.add_argument("--no-compact", action="store_true", help="skip the compact-tip (z-pruned path) measurement")
+    ap.add_argument("--no-reference-full", dest="reference_full", action="store_false",
+                    help="--impl reference: skip the one full-size sr+es pass (about 3 minutes of numpy fftn), bounded sample only")
+    ap.add_argument("--no-cufft", action="store_true", help="skip the cuFFT (torch.fft) comparator")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

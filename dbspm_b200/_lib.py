@@ -59,6 +59,11 @@ _SIGNATURES = {
                                          C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
                                          C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int,
                                          _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "dbspm_relax_slab_halo": (C.c_int, [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "dbspm_relax_powell_slab_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                              C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int,
+                                              _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "dbspm_relax_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "dbspm_relax_workspace_bytes_layout": (C.c_size_t, [C.c_int] * 4),
     "dbspm_tricubic_gather_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp, _vp]),

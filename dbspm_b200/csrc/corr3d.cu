@@ -105,10 +105,12 @@ axis_tma_kernel(const __grid_constant__ AxisTmaParams P, const __grid_constant__
 #ifndef ZF2_WAVES
 #define ZF2_WAVES 2
 #endif
+// MAXR = largest radix the kernel is built for (8 or 16): the radix-16 butterfly costs 166 registers, taken or not
+template <int MAXR>
 __global__ void __launch_bounds__(ZF2_THREADS, ZF2_MIN_BLOCKS) zfused2_kernel(const __grid_constant__ ZFusedParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    zfused_body_v2<ZF2_PAIRS>(P, smem, (long long)blockIdx.x, (long long)gridDim.x, (int)threadIdx.x, (int)blockDim.x);
+    zfused_body_v2<ZF2_PAIRS, MAXR>(P, smem, (long long)blockIdx.x, (long long)gridDim.x, (int)threadIdx.x, (int)blockDim.x);
 }
 
 __global__ void __launch_bounds__(DBSPM_THREADS) compact_kernel(const double *W, double *E, long long ncol, int nzw, int ldw)
@@ -510,7 +512,7 @@ static int launch_zfused(const cplx *WA, const cplx *WB, cplx *W, int nx, int ny
 {
     const int n = nz / 2;
     DevPlan *pl = nullptr, *plN = nullptr;
-    int rc = get_plan(n, st, &pl, ZF2_MAX_RADIX);
+    int rc = get_plan(n, st, &pl, (flags & DBSPM_CORR_Z_RADIX8) ? 8 : ZF2_MAX_RADIX);
     if (rc) return rc;
     rc = get_plan(nz, st, &plN);
     if (rc) return rc;
@@ -528,13 +530,16 @@ static int launch_zfused(const cplx *WA, const cplx *WB, cplx *W, int nx, int ny
         const long long ngroups = (P.npairs + ZF2_PAIRS - 1) / ZF2_PAIRS;
         const size_t smem = zfused2_smem_bytes<ZF2_PAIRS>(n);
         // persistent blocks: a few per SM (148 SMs), each walking over its share of the pair groups
-        int per_sm = (int)((220 * 1024) / (smem + 1024));
+        int per_sm = (int)((228 * 1024) / (smem + 1024));          // 228 KB per SM, 1 KB reserved per resident block
         per_sm = per_sm < 1 ? 1 : (per_sm > ZF2_MAX_PER_SM ? ZF2_MAX_PER_SM : per_sm);
         long long nblocks = 148LL * per_sm * ZF2_WAVES;
         if (nblocks > ngroups) nblocks = ngroups;
-        DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DBSPM_CUDA_TRY(cudaFuncSetAttribute(zfused2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        zfused2_kernel<<<(unsigned)nblocks, ZF2_THREADS, smem, st>>>(P);
+        int maxr = 0;
+        for (int i = 0; i < P.plan.nstages; ++i) maxr = P.plan.radix[i] > maxr ? P.plan.radix[i] : maxr;
+        auto kern = maxr <= 8 ? zfused2_kernel<8> : zfused2_kernel<16>;
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        kern<<<(unsigned)nblocks, ZF2_THREADS, smem, st>>>(P);
     } else {
         const long long nblocks = (P.npairs + ZL - 1) / ZL;
         const size_t smem = zfused_smem_bytes(n);

@@ -223,7 +223,9 @@ HD void pow_fast_bounds(double alpha, double *lo, double *hi)
 // copies (pstride = 16) and a lane reads copy (lane & 15): a 64-bit shared-memory load is served per half-warp, and the 16
 // lanes of a half-warp then hit 16 different bank pairs whatever entries they ask for.  With one copy the 32 random
 // entries of a warp collided two- to four-fold (ncu, round 1: 43 % of the pass's shared-memory wavefronts were conflicts).
+#ifndef POW_TAB_COPIES
 #define POW_TAB_COPIES 16
+#endif
 HD double pow_fast_core(double v, double alpha, const double *tab, int pstride, int pcopy);
 HD double pow_fast(double v, double alpha, const double *tab)
 {
@@ -557,7 +559,7 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
 #define AXIS3_MAX_SMEM (225 * 1024)
 #endif
 
-template <int D>
+template <int D, int MAXR = 16>
 HD void fft_stages_from(cplx *s, int ld, int tshift, const FftPlanDev &pl, int first, const cplx *tw, int tid, int nthr);
 
 struct AxisTmaParams {
@@ -909,7 +911,9 @@ HD void zfused_body(const ZFusedParams &P, unsigned char *smem_raw, long long bi
 // ------------------------------------------------------------------------------------------
 template <int ZLV> HD size_t zfused2_smem_bytes(int n)
 {
-    return (size_t)n * 16 * 2 + (size_t)n * (4 * ZLV + 1) * 16 + (size_t)n * (2 * ZLV + 1) * 16 + (size_t)n * 8 + ZLV * 6 * 4 + 16;
+    // twiddles of length n; the half-length table exp(-2 pi i k / nz) is read through L1 (once per pointwise item): with it
+    // in shared memory four CTAs of the n = 128 kernel miss the 228 KB of an SM by 1 KB
+    return (size_t)n * 16 + (size_t)n * (4 * ZLV + 1) * 16 + (size_t)n * (2 * ZLV + 1) * 16 + (size_t)n * 8 + ZLV * 6 * 4 + 16;
 }
 
 template <int D, int R, int ZLV>
@@ -946,7 +950,7 @@ HD void zfused2_first(const ZFusedParams &P, cplx *U, const cplx *tw, const int 
     }
 }
 
-template <int D>
+template <int D, int MAXR>
 HD void fft_stages_from(cplx *s, int ld, int tshift, const FftPlanDev &pl, int first, const cplx *tw, int tid, int nthr)
 {
     int m = pl.n;
@@ -954,14 +958,14 @@ HD void fft_stages_from(cplx *s, int ld, int tshift, const FftPlanDev &pl, int f
     for (int st = first; st < pl.nstages; ++st) {
         const int r = pl.radix[st];
 #define CALL_(R) fft_stage<R, D>(s, ld, tshift, pl.n, m, tw, tid, nthr)
-        DBSPM_FAST_RADIX_SWITCH(r, CALL_)
+        DBSPM_RADIX_SWITCH_MAX(r, CALL_, MAXR)
 #undef CALL_
         m /= r;
         BLOCK_SYNC();
     }
 }
 
-template <int ZLV>
+template <int ZLV, int MAXR = 16>
 HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long bid0, long long bstride, int tid, int nthr)
 {
     constexpr int TF = 4 * ZLV, TI = 2 * ZLV, LDF = TF + 1, LDI = TI + 1;
@@ -969,8 +973,7 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
     constexpr int TSI = TSF - 1;
     const int n = P.n;
     cplx *tw = (cplx *)smem_raw;
-    cplx *twh = tw + n;
-    cplx *U = twh + n;
+    cplx *U = tw + n;
     cplx *S = U + (size_t)n * LDF;
     int *pos_of = (int *)(S + (size_t)n * LDI);
     int *freq_of = pos_of + n;
@@ -978,7 +981,6 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
 
     for (int e = tid; e < n; e += nthr) {
         tw[e] = ldg_c(P.tw + e);
-        twh[e] = ldg_c(P.twN + e);
         pos_of[e] = LDG(P.pos_of + e);
         freq_of[e] = LDG(P.freq_of + e);
     }
@@ -1005,10 +1007,10 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
     }
 #endif
 #define CALL_(R) zfused2_first<-1, R, ZLV>(P, U, tw, pinfo, tid, nthr)
-    DBSPM_FAST_RADIX_SWITCH(P.plan.radix[0], CALL_)
+    DBSPM_RADIX_SWITCH_MAX(P.plan.radix[0], CALL_, MAXR)
 #undef CALL_
     BLOCK_SYNC();
-    fft_stages_from<-1>(U, LDF, TSF, P.plan, 1, tw, tid, nthr);
+    fft_stages_from<-1, MAXR>(U, LDF, TSF, P.plan, 1, tw, tid, nthr);
 
     // pointwise stage in POSITION order: one work item = (pair l, tile row p) owns frequency
     // k = freq_of[p].  Consecutive threads read consecutive rows (bank-conflict free); only the
@@ -1024,7 +1026,7 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
         const int ps = pos_of[ks];
         const cplx *Uk = U + (p * LDF + 4 * l);
         const cplx *Us = U + (ps * LDF + 4 * l);
-        const cplx w = twh[k];                                    // exp(-2 pi i k / nz)
+        const cplx w = ldg_c(P.twN + k);                          // exp(-2 pi i k / nz)
         const cplx miw = cmake(w.y, -w.x);                        // -i * w
         const cplx a1 = Uk[0], a2 = cconj(Us[1]);
         const cplx b1 = Uk[2], b2 = cconj(Us[3]);
@@ -1044,7 +1046,7 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
         S[ps * LDI + 2 * l + 1] = cmake(G1.x + G2.y, -G1.y + G2.x);
     }
     BLOCK_SYNC();
-    fft_tile_t<1>(S, LDI, TSI, P.plan, tw, tid, nthr);
+    fft_tile_t<1, MAXR>(S, LDI, TSI, P.plan, tw, tid, nthr);
 
     for (int idx = tid; idx < P.nwh * TI; idx += nthr) {
         const int line = idx / P.nwh, j = idx - line * P.nwh;

@@ -230,6 +230,18 @@ HD bool fast_radix(int r)
     default: CALL(16); break;                                                                       \
     }
 
+// the same with the instantiations above a compile-time cap left out: a kernel built for plans of radix <= MAXR does not
+// carry the registers of the radix-16 butterfly (ptxas allocates for the largest path, taken or not)
+#define DBSPM_RADIX_SWITCH_MAX(r, CALL, MAXR)                                                                   \
+    switch (r) {                                                                                                \
+    case 2: CALL(2); break;   case 3: CALL(3); break;   case 4: CALL(4); break;   case 5: CALL(5); break;       \
+    case 6: CALL(6); break;   case 7: CALL(7); break;   case 8: CALL(8); break;                                 \
+    case 9: if (MAXR >= 9) CALL(9); break;    case 10: if (MAXR >= 10) CALL(10); break;                         \
+    case 12: if (MAXR >= 12) CALL(12); break; case 14: if (MAXR >= 14) CALL(14); break;                         \
+    case 15: if (MAXR >= 15) CALL(15); break;                                                                   \
+    default: if (MAXR >= 16) CALL(16); break;                                                                   \
+    }
+
 // ---- one DIF stage over the whole tile ----------------------------------------------------
 // m = current sub-transform length, R | m.  tw[e] = exp(-2 pi i e / n), e in [0,n).
 template <int R, int D>
@@ -337,7 +349,7 @@ HD void fft_stage_t(cplx *s, int ld, int tshift, int n, int m, const cplx *tw, i
 }
 
 // all stages, last to first; fast radices only (callers check the plan)
-template <int D>
+template <int D, int MAXR = 16>
 HD void fft_tile_t(cplx *s, int ld, int tshift, const FftPlanDev &pl, const cplx *tw, int tid, int nthr)
 {
     int m = 1;
@@ -345,7 +357,7 @@ HD void fft_tile_t(cplx *s, int ld, int tshift, const FftPlanDev &pl, const cplx
         const int r = pl.radix[st];
         m *= r;
 #define CALL_(R) fft_stage_t<R, D>(s, ld, tshift, pl.n, m, tw, tid, nthr)
-        DBSPM_FAST_RADIX_SWITCH(r, CALL_)
+        DBSPM_RADIX_SWITCH_MAX(r, CALL_, MAXR)
 #undef CALL_
         BLOCK_SYNC();
     }

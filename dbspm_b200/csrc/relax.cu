@@ -149,6 +149,13 @@ extern "C" size_t dbspm_relax_workspace_bytes(int nx, int ny, int nzc)
     return q ? q : dbspm_relax_workspace_bytes_layout(nx, ny, nzc, 1);
 }
 
+static int relax_launch(const double *static_win, int nx, int ny, int nzc, int x_base, int nx_local,
+                        int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                        double kappa, double rpivot, const double dr[3], const double *dR,
+                        double xtol, double ftol, int maxfev,
+                        double *out_E_theta_phi, double *out_cart, int *out_nfev,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
 extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
                                       int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
                                       double kappa, double rpivot, const double dr[3], const double *dR,
@@ -156,15 +163,65 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
                                       double *out_E_theta_phi, double *out_cart, int *out_nfev,
                                       void *workspace, size_t workspace_bytes, void *stream)
 {
+    return relax_launch(static_win, nx, ny, nzc, 0, 0, i_lo, i_hi, j_lo, j_hi, nz_relax, kappa, rpivot, dr, dR, xtol, ftol, maxfev,
+                        out_E_theta_phi, out_cart, out_nfev, workspace, workspace_bytes, stream);
+}
+
+// lateral halo (planes) a slab needs on each side of its tile: the lever reaches rpivot/dx planes (|sin| <= 1; row norms
+// of inv(dR^T) for a skew cell) and the stencil two more
+extern "C" int dbspm_relax_slab_halo(double rpivot, const double dr[3], const double *dR)
+{
+    if (!dr || !(dr[0] > 0) || !(dr[2] > 0) || !(rpivot >= 0)) return -1;
+    double reach = (rpivot / dr[2]) * dr[2] / dr[0];
+    if (dR) {
+        const double dRT[9] = {dR[0], dR[3], dR[6], dR[1], dR[4], dR[7], dR[2], dR[5], dR[8]};
+        double M[9];
+        if (!inv3(dRT, M)) return -1;
+        reach = (rpivot / dr[2]) * dr[2] * sqrt(M[0] * M[0] + M[1] * M[1] + M[2] * M[2]);
+    }
+    return (int)ceil(reach) + 2;
+}
+
+extern "C" int dbspm_relax_powell_slab_f64(const double *static_slab, int nx, int ny, int nzc, int x_base, int nx_local,
+                                           int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                                           double kappa, double rpivot, const double dr[3], const double *dR,
+                                           double xtol, double ftol, int maxfev,
+                                           double *out_E_theta_phi, double *out_cart, int *out_nfev,
+                                           void *workspace, size_t workspace_bytes, void *stream)
+{
+    DBSPM_REQUIRE(nx >= 1 && nx_local >= 1 && nx_local <= nx && x_base >= 0 && x_base < nx, DBSPM_EINVAL,
+                  "bad slab: planes [%d, %d + %d) of %d", x_base, x_base, nx_local, nx);
+    DBSPM_REQUIRE(dr, DBSPM_EINVAL, "null pointer argument");
+    const int halo = dbspm_relax_slab_halo(rpivot, dr, dR);
+    DBSPM_REQUIRE(halo >= 0, DBSPM_EINVAL, "bad rpivot / dr / dR");
+    if (nx_local < nx) {
+        // every plane a probe of the tile [i_lo, i_hi) can touch must be in the slab
+        const int lo = ((i_lo - halo - x_base) % nx + nx) % nx, span = (i_hi - i_lo) + 2 * halo;
+        DBSPM_REQUIRE(i_hi > i_lo ? lo + span <= nx_local : true, DBSPM_EINVAL,
+                      "slab [%d, +%d) does not cover the tile [%d, %d) with its halo of %d planes", x_base, nx_local, i_lo, i_hi, halo);
+    }
+    return relax_launch(static_slab, nx, ny, nzc, x_base, nx_local, i_lo, i_hi, j_lo, j_hi, nz_relax, kappa, rpivot, dr, dR, xtol, ftol,
+                        maxfev, out_E_theta_phi, out_cart, out_nfev, workspace, workspace_bytes, stream);
+}
+
+static int relax_launch(const double *static_win, int nx, int ny, int nzc, int x_base, int nx_local,
+                        int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                        double kappa, double rpivot, const double dr[3], const double *dR,
+                        double xtol, double ftol, int maxfev,
+                        double *out_E_theta_phi, double *out_cart, int *out_nfev,
+                        void *workspace, size_t workspace_bytes, void *stream)
+{
     DBSPM_REQUIRE(static_win && dr && out_E_theta_phi, DBSPM_EINVAL, "null pointer argument");
     DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nzc >= 1, DBSPM_EINVAL, "bad grid shape (%d,%d,%d)", nx, ny, nzc);
     DBSPM_REQUIRE(i_lo <= i_hi && j_lo <= j_hi && nz_relax >= 0, DBSPM_EINVAL, "bad tile");
     DBSPM_REQUIRE(dr[0] > 0 && dr[1] > 0 && dr[2] > 0, DBSPM_EINVAL, "grid spacings must be positive");
     DBSPM_REQUIRE(maxfev >= 1, DBSPM_EINVAL, "maxfev must be >= 1");
-    DBSPM_REQUIRE((long long)nx * (ny + 3) * nzc < 2147483647LL, DBSPM_EUNSUPPORTED,
-                  "potential grid too large for 32-bit element offsets (%d x %d x %d)", nx, ny, nzc);
+    const int nxs = nx_local ? nx_local : nx;              // planes actually stored
+    DBSPM_REQUIRE((long long)nxs * (ny + 3) * nzc < 2147483647LL, DBSPM_EUNSUPPORTED,
+                  "potential grid too large for 32-bit element offsets (%d x %d x %d)", nxs, ny, nzc);
     RelaxParams P;
     P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc; P.nyp = ny + 3;
+    P.x_base = x_base; P.nx_local = nx_local;
     P.i_lo = i_lo; P.i_hi = i_hi; P.j_lo = j_lo; P.j_hi = j_hi; P.nz_relax = nz_relax;
     P.kappa = kappa; P.rpivot = rpivot;
     P.npivot = rpivot / dr[2];
@@ -193,14 +250,14 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
     if (const char *e = getenv("DBSPM_RELAX_HEIGHTS_PER_LAUNCH")) { const int v = atoi(e); if (v >= 1) hpl = v; }
     if (workspace) {
         // re-lay the potential once per call (~2-5 passes over the window): the largest layout the workspace holds
-        const size_t need1 = dbspm_relax_workspace_bytes_layout(nx, ny, nzc, 1), need2 = dbspm_relax_workspace_bytes_layout(nx, ny, nzc, 2);
+        const size_t need1 = dbspm_relax_workspace_bytes_layout(nxs, ny, nzc, 1), need2 = dbspm_relax_workspace_bytes_layout(nxs, ny, nzc, 2);
         DBSPM_REQUIRE(workspace_bytes >= need1 && ((uintptr_t)workspace & 31) == 0,
                       DBSPM_EWORKSPACE, "relax workspace needs %zu bytes (y-fastest copy) or %zu (y-quads), 32-byte aligned (got %zu)",
                       need1, need2, workspace_bytes);
-        DBSPM_REQUIRE(nx <= 65535, DBSPM_EUNSUPPORTED, "nx too large for the transpose grid");
+        DBSPM_REQUIRE(nxs <= 65535, DBSPM_EUNSUPPORTED, "nx too large for the transpose grid");
         P.grid = (const double *)workspace;
         if (need2 && workspace_bytes >= need2) {
-            dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 31) / 32), (unsigned)nx);
+            dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 31) / 32), (unsigned)nxs);
             quad_yz_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_win, (double *)workspace, ny, nzc);
             DBSPM_CUDA_TRY(cudaGetLastError());
             for (int kh = nz_relax - 1; kh >= 0; kh -= hpl) {
@@ -208,7 +265,7 @@ extern "C" int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, 
                 relax_kernel<2><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
             }
         } else {
-            dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 3 + 31) / 32), (unsigned)nx);
+            dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 3 + 31) / 32), (unsigned)nxs);
             transpose_yz_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_win, (double *)workspace, ny, nzc);
             DBSPM_CUDA_TRY(cudaGetLastError());
             for (int kh = nz_relax - 1; kh >= 0; kh -= hpl) {

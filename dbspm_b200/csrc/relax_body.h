@@ -27,6 +27,8 @@
 struct RelaxParams {
     const double *grid;       // static potential: (nx,ny,nzc) z fastest [LAYOUT 0] or (nx,nzc,nyp) [LAYOUT 1]
     int nx, ny, nzc;
+    int x_base, nx_local;     // x-slab mode: `grid` holds the nx_local planes x_base, x_base + 1, ... (mod nx) of the window (a rank's
+                              // x-tile plus a halo of the lever length on both sides); x_base = 0, nx_local = nx: the whole window
     int nyp;                  // LAYOUT 1: row length ny + 3 (periodic halo: stored index t holds y = t - 1)
     int i_lo, i_hi, j_lo, j_hi;
     int nz_relax;
@@ -232,7 +234,8 @@ HD void ld_quad(const double *p, double *q)
 }
 
 template <int LAYOUT>
-HD double tricubic_eval(const double *g, int nx, int ny, int nz, int nyp, const double *nd, const double *inv_n, double x, double y, double z)
+HD double tricubic_eval(const double *g, int nx, int ny, int nz, int nyp, const double *nd, const double *inv_n, double x, double y, double z,
+                        int x_base = 0, int nx_local = 0)
 {
     int ix, iy, iz;
     double wx[4], wy[4], wz[4];
@@ -243,6 +246,17 @@ HD double tricubic_eval(const double *g, int nx, int ny, int nz, int nyp, const 
     int xo[4], yo[4], zo[4];
     stencil_idx(ix, nx, xo);
     stencil_idx(iz, nz, zo);
+    if (nx_local) {
+        // x-slab mode: global (periodically wrapped) plane index -> plane of the local slab.  The cell index and the
+        // weights above come from the global coordinate, so the value is the one the whole window gives, bit for bit.
+        // A plane outside the slab cannot occur when the halo covers the lever length; it is clamped, never read out of bounds.
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int l = xo[c] - x_base;
+            l = l < 0 ? l + nx : l;
+            xo[c] = l < nx_local ? l : nx_local - 1;
+        }
+    }
     if (LAYOUT == 0) {
         stencil_idx(iy, ny, yo);
 #pragma unroll
@@ -340,7 +354,8 @@ HD double relax_objective(const RelaxParams &P, int oi, int oj, int ok, double t
     if (dbspm_emu_interp_hook)
         return dbspm_emu_interp_hook((double)oi + ox, (double)oj + oy, (double)ok + oz) + spr;
 #endif
-    return tricubic_eval<LAYOUT>(P.grid, P.nx, P.ny, P.nzc, P.nyp, P.nd, P.inv_n, (double)oi + ox, (double)oj + oy, (double)ok + oz) + spr;
+    return tricubic_eval<LAYOUT>(P.grid, P.nx, P.ny, P.nzc, P.nyp, P.nd, P.inv_n, (double)oi + ox, (double)oj + oy, (double)ok + oz,
+                                 P.x_base, P.nx_local) + spr;
 }
 
 // ---- Powell / Brent / bracket state machine -----------------------------------------------

@@ -322,11 +322,23 @@ class TricubicField:
         return float(self.gather(np.asarray([xyz], dtype=np.float64))[0])
 
 
+def relax_slab_halo(rpivot, dr, dR=None) -> int:
+    """Planes of the static window a rank needs on each side of its x-tile (lever length in planes + the stencil)."""
+    dr3 = (C.c_double * 3)(*[float(v) for v in dr])
+    dR9 = None if dR is None else (C.c_double * 9)(*[float(v) for v in np.asarray(dR, dtype=np.float64).reshape(9)])
+    h = int(_lib.lib().dbspm_relax_slab_halo(float(rpivot), dr3, dR9))
+    if h < 0:
+        raise ValueError("bad rpivot / dr / dR")
+    return h
+
+
 def relax_grid(static, kappa, rpivot, dr, nz_relax, dR=None, tile=None, xtol=1e-4, ftol=1e-4,
-               maxfev=2000, method="Powell", want_nfev=False, device=None, coalesce=True, layout=None):
+               maxfev=2000, method="Powell", want_nfev=False, device=None, coalesce=True, layout=None, x_slab=None):
     """Relax the probe at every (i, j, k) of a lateral tile (default: the whole window).
 
     static: (Nx,Ny,Nzc) window potential (numpy, CUDA tensor or TricubicField).
+    x_slab = (x_base, Nx): `static` holds only the planes x_base, x_base + 1, ... (mod Nx) of the window -- a rank's tile
+    plus relax_slab_halo() planes on both sides (multi-GPU); `tile` stays in window coordinates.  Same bits as the whole window.
     Returns dict with E (ni,nj,nz), theta, phi, tip_x, tip_y, tip_z (and nfev) -- CUDA tensors
     if `static` lives on the GPU, numpy arrays otherwise.  Equivalent to the loop at
     dbspm:564-581 followed by dbspm:597-605."""
@@ -338,6 +350,11 @@ def relax_grid(static, kappa, rpivot, dr, nz_relax, dR=None, tile=None, xtol=1e-
         field = TricubicField(static, device=device)
     dev = field.data.device
     nx, ny, nzc = field.shape
+    nx_local, x_base = 0, 0
+    if x_slab is not None:
+        nx_local, (x_base, nx) = nx, (int(v) for v in x_slab)
+        if tile is None:
+            raise ValueError("x_slab needs an explicit tile (window coordinates)")
     i_lo, i_hi, j_lo, j_hi = (0, nx, 0, ny) if tile is None else (int(v) for v in tile)
     ni, nj, nz = i_hi - i_lo, j_hi - j_lo, int(nz_relax)
     etp = torch.empty((ni, nj, nz, 3), dtype=torch.float64, device=dev)
@@ -356,17 +373,21 @@ def relax_grid(static, kappa, rpivot, dr, nz_relax, dR=None, tile=None, xtol=1e-
             ws = None
             if layout is None:
                 layout = -1 if (coalesce and ni * nj >= 1024) else 0
+            nxs = nx_local or nx
             if layout:
                 L = _lib.lib()
-                need = L.dbspm_relax_workspace_bytes(nx, ny, nzc) if layout < 0 else \
-                    L.dbspm_relax_workspace_bytes_layout(nx, ny, nzc, int(layout))
+                need = L.dbspm_relax_workspace_bytes(nxs, ny, nzc) if layout < 0 else \
+                    L.dbspm_relax_workspace_bytes_layout(nxs, ny, nzc, int(layout))
                 if need:
                     ws = torch.empty(need, dtype=torch.uint8, device=dev)
-            _lib.check(_lib.lib().dbspm_relax_powell_f64(
-                field.data.data_ptr(), nx, ny, nzc, i_lo, i_hi, j_lo, j_hi, nz, float(kappa), float(rpivot),
-                dr3, dR9, float(xtol), float(ftol), int(maxfev), etp.data_ptr(), cart.data_ptr(),
-                nfev.data_ptr() if nfev is not None else None,
-                ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, _stream_ptr(dev)))
+            tail = (i_lo, i_hi, j_lo, j_hi, nz, float(kappa), float(rpivot),
+                    dr3, dR9, float(xtol), float(ftol), int(maxfev), etp.data_ptr(), cart.data_ptr(),
+                    nfev.data_ptr() if nfev is not None else None,
+                    ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, _stream_ptr(dev))
+            if nx_local:
+                _lib.check(_lib.lib().dbspm_relax_powell_slab_f64(field.data.data_ptr(), nx, ny, nzc, x_base, nx_local, *tail))
+            else:
+                _lib.check(_lib.lib().dbspm_relax_powell_f64(field.data.data_ptr(), nx, ny, nzc, *tail))
     res = {"E": etp[..., 0], "theta": etp[..., 1], "phi": etp[..., 2],
            "tip_x": cart[0], "tip_y": cart[1], "tip_z": cart[2]}
     if want_nfev:

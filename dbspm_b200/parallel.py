@@ -227,7 +227,7 @@ def peer_receive_buffer(shape, G: int, pg, device):
 
 
 def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, groups, dst: int = 0, on_stage=None,
-                      peer: bool = True, tip_support=None):
+                      peer: bool = True, tip_support=None, gather: bool = True):
     """The distributed sr / es step (replaces the rank-0-only dbspm:320-352).
 
     groups[i] = the G ranks that compute interaction i; this rank, member h of its group, passes the x-slab
@@ -240,7 +240,9 @@ def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, grou
     on_stage(name) is called after each stage has been enqueued (bench.py records a CUDA event there).
     tip_support = (s_lo, s_len): the caller's claim that the second array is exactly zero outside those z-planes
     (interactions.tip_zsupport); when pruning pays, the forward pass reads only the z-ranges the window can see and
-    every later stage runs on the shorter z length (same result, see dbspm_corr3d_pruned_f64)."""
+    every later stage runs on the shorter z length (same result, see dbspm_corr3d_pruned_f64).
+    gather=False: no gather -- every rank returns its finished real x-slab (nx/G, ny, nzw) of its interaction's window
+    (the relax step that follows only needs the slab and a halo, exchange_halo)."""
     mark = on_stage or (lambda name: None)
     rank, world = _world()
     G = len(groups[0])
@@ -286,7 +288,7 @@ def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, grou
         hdl2.barrier(channel=0)
         slab = stages.dist_finish(W2, (nxl,) + tuple(int(v) for v in shape[1:]), G, z_lo, z_hi)
         mark("fin")
-        return _gather_slabs(slab, groups, G, nx, nxl, dst, mark)
+        return _gather_slabs(slab, groups, G, nx, nxl, dst, mark) if gather else slab
     W = stages.dist_middle(recvA, recvB, dr, shape, G, h, z_lo, z_hi)
     mark("mid")
     # second exchange (small: the packed window rows, 16 N_w / G bytes per rank): rank g receives the rows of x-slab g
@@ -296,11 +298,12 @@ def sr_es_distributed(stages, a_slab, b_slab, alpha, shape, dr, z_lo, z_hi, grou
     dist.all_to_all_single(W2, W, group=pg)
     slab = stages.dist_finish(W2.view((G, nxl) + tuple(W.shape[1:])), (nxl,) + tuple(int(v) for v in shape[1:]), G, z_lo, z_hi)
     mark("fin")
-    return _gather_slabs(slab, groups, G, nx, nxl, dst, mark)
+    return _gather_slabs(slab, groups, G, nx, nxl, dst, mark) if gather else slab
 
 
-def _gather_slabs(slab, groups, G, nx, nxl, dst, mark):
-    """Finished real x-slabs of every interaction -> the full windows on rank `dst` (received straight into place)."""
+def _gather_slabs(slab, groups, G, nx, nxl, dst, mark=None, async_op: bool = False):
+    """Finished real x-slabs of every interaction -> the full windows on rank `dst` (received straight into place).
+    async_op: returns (windows, work); the collective runs beside whatever is enqueued next (work.wait() joins it)."""
     rank, world = _world()
     wins = None
     gl = None
@@ -311,9 +314,53 @@ def _gather_slabs(slab, groups, G, nx, nxl, dst, mark):
         for i, g in enumerate(groups):
             for hh, r in enumerate(g):
                 gl[r] = wins[i][hh * nxl:(hh + 1) * nxl]
-    dist.gather(slab, gl, dst=dst)
-    mark("gather")
-    return wins
+    work = dist.gather(slab, gl, dst=dst, async_op=async_op)
+    if mark is not None:
+        mark("gather")
+    return (wins, work) if async_op else wins
+
+
+def gather_x_slabs(slab, nx, dst: int = 0, async_op: bool = False):
+    """One window from the x-slabs of ALL ranks (rank r holds planes [r*nx/W, (r+1)*nx/W)) onto rank `dst`."""
+    rank, world = _world()
+    if world == 1:
+        return (slab, None) if async_op else slab
+    out = _gather_slabs(slab, [list(range(world))], world, nx, nx // world, dst, None, async_op)
+    if async_op:
+        return (out[0][0] if out[0] is not None else None), out[1]
+    return out[0] if out is not None else None
+
+
+def exchange_halo(slab: torch.Tensor, halo: int) -> torch.Tensor:
+    """Rank r holds planes [r*nxl, (r+1)*nxl) of a periodic array split evenly along its first axis; returns the
+    (nxl + 2*halo, ...) array of its planes plus `halo` planes of each neighbour (periodic wrap): what the relax
+    kernel's x-slab mode needs of the static potential (interactions.relax_grid(x_slab=...)).  Two point-to-point
+    messages per rank (replaces the broadcast of the whole `static` to every rank, dbspm:540-556); when the halo is
+    wider than a slab the slabs are all-gathered instead."""
+    rank, world = _world()
+    nxl = int(slab.shape[0])
+    halo = int(halo)
+    if halo == 0:
+        return slab
+    if world == 1 or halo > nxl:
+        full = slab
+        if world > 1:
+            parts = [torch.empty_like(slab) for _ in range(world)]
+            dist.all_gather(parts, slab.contiguous())
+            full = torch.cat(parts, dim=0)
+        n = int(full.shape[0])
+        idx = (torch.arange(rank * nxl - halo, (rank + 1) * nxl + halo, device=full.device) % n)
+        return full.index_select(0, idx)
+    out = torch.empty((nxl + 2 * halo,) + tuple(slab.shape[1:]), dtype=slab.dtype, device=slab.device)
+    out[halo:halo + nxl] = slab
+    left, right = (rank - 1) % world, (rank + 1) % world
+    first, last = slab[:halo].contiguous(), slab[nxl - halo:].contiguous()
+    # order matters when left == right (two ranks): the peer's first receive (its left halo) must meet my LAST planes
+    ops = [dist.P2POp(dist.isend, last, right), dist.P2POp(dist.isend, first, left),
+           dist.P2POp(dist.irecv, out[:halo], left), dist.P2POp(dist.irecv, out[halo + nxl:], right)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return out
 
 
 def relax_sharded(compute_tile, nx, device):

@@ -62,6 +62,8 @@ extern "C" {
 #define DBSPM_CORR_SKIP_Z     (1 << 10)
 #define DBSPM_CORR_SKIP_YINV  (1 << 11)
 #define DBSPM_CORR_SKIP_XINV  (1 << 12)
+#define DBSPM_CORR_Z_RADIX8   (1 << 13)  /* fused z kernel: plan with radices <= 8 and the kernel built without the radix-16
+                                            butterfly (fewer registers, one more shared-memory stage; A/B timing) */
 
 /* library / build identification: "dbspm_b200 <version> sm_100a" */
 const char *dbspm_version(void);
@@ -161,6 +163,18 @@ int dbspm_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
                            double xtol, double ftol, int maxfev,
                            double *out_E_theta_phi, double *out_cart, int *out_nfev,
                            void *workspace, size_t workspace_bytes, void *stream);
+/* x-slab form (multi-GPU: a rank holds only its tile of the static window plus a halo): static_slab holds the nx_local
+ * planes x_base, x_base + 1, ... (mod nx) of the (nx,ny,nzc) window.  The slab must cover the tile [i_lo, i_hi) and
+ * dbspm_relax_slab_halo(rpivot, dr, dR) planes on both sides (the lever length in planes + the stencil).  Cell indices
+ * and interpolation weights are computed from the global coordinate, so the results are bit-identical to
+ * dbspm_relax_powell_f64 on the whole window.  Replaces the replicated `static` of dbspm:540-556.              */
+int dbspm_relax_slab_halo(double rpivot, const double dr[3], const double *dR);
+int dbspm_relax_powell_slab_f64(const double *static_slab, int nx, int ny, int nzc, int x_base, int nx_local,
+                                int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                                double kappa, double rpivot, const double dr[3], const double *dR,
+                                double xtol, double ftol, int maxfev,
+                                double *out_E_theta_phi, double *out_cart, int *out_nfev,
+                                void *workspace, size_t workspace_bytes, void *stream);
 /* workspace (nullable), 32-byte aligned: the potential is re-laid once per call so that the stencil loads of a warp
  * waste less of every cache line.  Layout 1 (dbspm_relax_workspace_bytes_layout(.., 1) bytes): y fastest with a periodic
  * halo.  Layout 2 (4x the window; returns 0 when 32-bit element offsets would overflow): the four y neighbours of every

@@ -148,6 +148,23 @@ class Emu:
             raise RuntimeError(f"emu_relax_powell_f64 -> {rc}")
         return etp, cart, nfev
 
+    def relax_slab(self, slab, nx, x_base, tile, nz, kappa, rpivot, dr, dR=None, maxfev=2000, transposed=0):
+        """x-slab mode: `slab` holds the planes x_base ... (mod nx) of the window; `tile` in window coordinates."""
+        s = np.ascontiguousarray(slab, dtype=np.float64)
+        nx_local, ny, nzc = s.shape
+        i_lo, i_hi, j_lo, j_hi = tile
+        ni, nj = i_hi - i_lo, j_hi - j_lo
+        etp = np.empty((ni, nj, nz, 3)); cart = np.empty((3, ni, nj, nz)); nfev = np.zeros((ni, nj, nz), dtype=np.int32)
+        drv = np.ascontiguousarray(dr, dtype=np.float64)
+        dRv = None if dR is None else np.ascontiguousarray(dR, dtype=np.float64).reshape(9)
+        f = self.L.emu_relax_powell_slab_f64
+        f.argtypes = [_dp] + [C.c_int] * 10 + [C.c_double, C.c_double, _dp, _dp, C.c_double, C.c_double, C.c_int, _dp, _dp, _ip, C.c_int]
+        rc = f(self._p(s), nx, ny, nzc, x_base, nx_local, i_lo, i_hi, j_lo, j_hi, nz, kappa, rpivot, self._p(drv),
+               None if dRv is None else self._p(dRv), 1e-4, 1e-4, maxfev, self._p(etp), self._p(cart), nfev.ctypes.data_as(_ip), transposed)
+        if rc:
+            raise RuntimeError(f"emu_relax_powell_slab_f64 -> {rc}")
+        return etp, cart, nfev
+
     def tricubic(self, g, x, y, z):
         g = np.ascontiguousarray(g, dtype=np.float64)
         return self.L.emu_tricubic(self._p(g), *g.shape, x, y, z)

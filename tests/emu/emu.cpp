@@ -367,21 +367,49 @@ static bool inv3(const double m[9], double out[9])
     return true;
 }
 
+static int emu_relax_impl(const double *static_win, int nx_global, int ny, int nzc, int x_base, int nx_local,
+                          int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                          double kappa, double rpivot, const double dr[3], const double *dR,
+                          double xtol, double ftol, int maxfev,
+                          double *out_etp, double *out_cart, int *out_nfev, int transposed);
+
 extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, int nzc,
                                     int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
                                     double kappa, double rpivot, const double dr[3], const double *dR,
                                     double xtol, double ftol, int maxfev,
                                     double *out_etp, double *out_cart, int *out_nfev, int transposed)
 {
+    return emu_relax_impl(static_win, nx, ny, nzc, 0, 0, i_lo, i_hi, j_lo, j_hi, nz_relax, kappa, rpivot, dr, dR, xtol, ftol, maxfev,
+                          out_etp, out_cart, out_nfev, transposed);
+}
+
+// x-slab mode: static_slab holds the planes x_base ... x_base + nx_local - 1 (mod nx) of the window
+extern "C" int emu_relax_powell_slab_f64(const double *static_slab, int nx, int ny, int nzc, int x_base, int nx_local,
+                                         int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                                         double kappa, double rpivot, const double dr[3], const double *dR,
+                                         double xtol, double ftol, int maxfev,
+                                         double *out_etp, double *out_cart, int *out_nfev, int transposed)
+{
+    return emu_relax_impl(static_slab, nx, ny, nzc, x_base, nx_local, i_lo, i_hi, j_lo, j_hi, nz_relax, kappa, rpivot, dr, dR, xtol, ftol,
+                          maxfev, out_etp, out_cart, out_nfev, transposed);
+}
+
+static int emu_relax_impl(const double *static_win, int nx_global, int ny, int nzc, int x_base, int nx_local,
+                          int i_lo, int i_hi, int j_lo, int j_hi, int nz_relax,
+                          double kappa, double rpivot, const double dr[3], const double *dR,
+                          double xtol, double ftol, int maxfev,
+                          double *out_etp, double *out_cart, int *out_nfev, int transposed)
+{
+    const int nx = nx_local ? nx_local : nx_global;          // planes stored (loops of the re-layout below)
     double powell_sm[PS_TOTAL];
     RelaxParams P;
-    P.grid = static_win; P.nx = nx; P.ny = ny; P.nzc = nzc; P.nyp = ny + 3;
+    P.grid = static_win; P.nx = nx_global; P.ny = ny; P.nzc = nzc; P.nyp = ny + 3;
     P.i_lo = i_lo; P.i_hi = i_hi; P.j_lo = j_lo; P.j_hi = j_hi; P.nz_relax = nz_relax;
     P.kappa = kappa; P.rpivot = rpivot; P.npivot = rpivot / dr[2]; P.rpivot_rt = P.npivot * dr[2];
     P.dr[0] = dr[0]; P.dr[1] = dr[1]; P.dr[2] = dr[2];
     for (int q = 0; q < 3; ++q) P.inv_dr[q] = 1.0 / dr[q];
-    P.inv_n[0] = 1.0 / nx; P.inv_n[1] = 1.0 / ny; P.inv_n[2] = 1.0 / nzc;
-    P.nd[0] = nx; P.nd[1] = ny; P.nd[2] = nzc;
+    P.inv_n[0] = 1.0 / nx_global; P.inv_n[1] = 1.0 / ny; P.inv_n[2] = 1.0 / nzc;
+    P.nd[0] = nx_global; P.nd[1] = ny; P.nd[2] = nzc;
     P.noortho = dR != nullptr;
     for (int q = 0; q < 9; ++q) P.Minv[q] = 0.0;
     if (dR) {
@@ -390,6 +418,7 @@ extern "C" int emu_relax_powell_f64(const double *static_win, int nx, int ny, in
     }
     P.xtol = xtol; P.ftol = ftol; P.maxfev = maxfev; P.maxiter = 2000;
     P.k_hi = nz_relax - 1; P.k_lo = 0;
+    P.x_base = x_base; P.nx_local = nx_local;
     P.out_etp = out_etp; P.out_cart = out_cart; P.out_nfev = out_nfev;
     const long long ncol = (long long)(i_hi - i_lo) * (j_hi - j_lo);
     std::vector<double> tr;

@@ -304,6 +304,22 @@ def test_relax_quad_layout_is_bit_identical(emu, relax_golden):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
 
 
+def test_relax_x_slab_mode_is_bit_identical(emu, relax_golden):
+    """Multi-GPU relax: a rank holds its x-tile of the static window plus a halo of the lever length; the kernel maps
+    the global (periodically wrapped) plane index into the slab.  Same bits as the whole window, across the wrap."""
+    static, dr = relax_golden["static"], relax_golden["dr"]
+    nx = static.shape[0]
+    rp, halo = 0.3, 6                                               # ceil(0.3 / 0.0765) + 2
+    full = emu.relax(static, (0, nx, 0, 20), 6, 0.2, rp, dr)
+    for i_lo, i_hi in ((20, 24), (0, 5), (9, 12)):
+        x_base = (i_lo - halo) % nx
+        planes = (x_base + np.arange((i_hi - i_lo) + 2 * halo)) % nx
+        for layout in (0, 1, 2):
+            got = emu.relax_slab(static[planes], nx, x_base, (i_lo, i_hi, 0, 20), 6, 0.2, rp, dr, transposed=layout)
+            for u, v in zip(got, full):
+                assert np.array_equal(u, v[:, i_lo:i_hi] if v.shape[0] == 3 else v[i_lo:i_hi]), (i_lo, layout)
+
+
 def test_kernel_body_equals_the_oracle_twin_bit_for_bit(emu, relax_golden):
     """The kernel body (state machine, stencil, fixed-sequence sin/cos, correctly rounded division) against the
     INDEPENDENT restatement in oracle/dbspm_oracle.c ("kernel twin": scipy's Powell in C + tc_ip_twin + det_sincos):

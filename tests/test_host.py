@@ -310,11 +310,29 @@ drr = np.array([0.1, 0.2, 0.3])
 x0, x1 = parallel.x_slab(shape[0], 2, rank)
 wins = parallel.sr_es_distributed(NumpyStages, torch.from_numpy(A[x0:x1].copy()), torch.from_numpy(B[x0:x1].copy()), 1.08,
                                   shape, drr, 2, 9, [[0, 1]])
+ref_all = (np.fft.ifftn(np.fft.fftn(A ** 1.08) * np.conj(np.fft.fftn(B ** 1.08))).real * np.prod(drr))[:, :, 2:9]
 if rank == 0:
-    ref = (np.fft.ifftn(np.fft.fftn(A ** 1.08) * np.conj(np.fft.fftn(B ** 1.08))).real * np.prod(drr))[:, :, 2:9]
+    ref = ref_all
     assert np.abs(wins[0].numpy() - ref).max() <= 1e-12 * np.abs(ref).max(), "distributed transform"
 else:
     assert wins is None
+# the multi-GPU step of round 2: every rank keeps its finished x-slab (no gather), builds its static tile, fetches a halo
+# of the lever length from its neighbours (periodic; with two ranks both neighbours are the same peer), and only the
+# .npz needs the window on rank 0 (asynchronous gather of the slabs)
+slab = parallel.sr_es_distributed(NumpyStages, torch.from_numpy(A[x0:x1].copy()), torch.from_numpy(B[x0:x1].copy()), 1.08,
+                                  shape, drr, 2, 9, [[0, 1]], gather=False)
+assert tuple(slab.shape) == (3, 8, 7) and np.abs(slab.numpy() - ref_all[x0:x1]).max() <= 1e-12 * np.abs(ref_all).max()
+for halo in (1, 2, 3, 5):                                   # 5 > slab: the all-gather fallback
+    loc = parallel.exchange_halo(slab, halo)
+    want = ref_all[(np.arange(x0 - halo, x1 + halo)) % shape[0]]
+    assert tuple(loc.shape) == (3 + 2 * halo, 8, 7) and np.abs(loc.numpy() - want).max() <= 1e-12 * np.abs(ref_all).max(), halo
+assert parallel.exchange_halo(slab, 0) is slab
+winx, work = parallel.gather_x_slabs(slab, shape[0], async_op=True)
+work.wait()
+if rank == 0:
+    assert np.abs(winx.numpy() - ref_all).max() <= 1e-12 * np.abs(ref_all).max()
+else:
+    assert winx is None
 assert parallel.dist_groups(8) == [[0, 1, 2, 3], [4, 5, 6, 7]] and parallel.dist_groups(2) is None
 assert parallel.dist_groups(6) == [[0, 1, 2], [3, 4, 5]] and parallel.dist_groups(5) is None
 t = torch.arange(3.0) if rank == 0 else torch.zeros(3)
