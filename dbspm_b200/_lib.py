@@ -36,6 +36,12 @@ _SIGNATURES = {
     "dbspm_corr3d_pruned_workspace_bytes": (C.c_size_t, [C.c_int] * 8),
     "dbspm_corr3d_pruned_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "dbspm_support_points_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "dbspm_corr3d_direct_workspace_bytes": (C.c_size_t, [C.c_int] * 6 + [C.POINTER(C.c_int)] * 3),
+    "dbspm_corr3d_direct_cost": (C.c_longlong, [C.c_int] * 6 + [C.POINTER(C.c_int)] * 3),
+    "dbspm_corr3d_direct_f64": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                          _vp, _vp, C.c_size_t, C.c_int, _vp]),
     "dbspm_corr3d_dist_supported": (C.c_int, [C.c_int] * 4),
     "dbspm_corr3d_dist_fwd_f64": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                             _vp, _vp, C.c_int, _vp]),

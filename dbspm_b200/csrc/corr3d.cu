@@ -8,6 +8,7 @@
 #include <vector>
 #include "capi_common.h"
 #include "corr_body.h"
+#include "direct_plan.h"
 #include "plan.h"
 
 #define DBSPM_THREADS 256
@@ -883,6 +884,146 @@ extern "C" int dbspm_zsupport_f64(const double *B, int nx, int ny, int nz, int *
     if ((size_t)nz > 48 * 1024)
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(zsupport_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nz));
     zsupport_kernel<<<(unsigned)blocks, 256, (size_t)nz, st>>>((const double2 *)B, npairs, nz / 2, plane_nonzero);
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    return DBSPM_OK;
+}
+
+
+// ---- direct real-space correlation for a tip with a few hundred support points (direct_body.h) ------------------------
+__global__ void __launch_bounds__(256) support_points_kernel(const double *B, long long n, int max_points, int *count,
+                                                              long long *idx, double *val)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = __ldcs(B + i);
+        if (v != 0.0) {
+            const int pos = atomicAdd(count, 1);
+            if (pos < max_points) { idx[pos] = i; val[pos] = v; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) direct_pad_kernel(const __grid_constant__ DirectPadParams Q)
+{
+    direct_pad_body(Q, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+// one block = one output tile: a single tensor-map load stages the sample box, then every thread runs its register tile
+__global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel(const __grid_constant__ DirectParams Q, const __grid_constant__ CUtensorMap map)
+{
+#if defined(__CUDA_ARCH__)
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *base = smem + ((128 - ((size_t)smem & 127)) & 127);      // keeps the shared address space (LDS, not generic LD)
+    double *box = (double *)base;
+    unsigned long long *bar = (unsigned long long *)(base + ((direct_box_bytes(Q.BX, Q.BY, Q.BZ) + 127) & ~(size_t)127));
+    const long long tile = blockIdx.x;
+    const unsigned bar_s = axis3_smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int tz = (int)(tile % Q.tiles_z);
+        const long long r = tile / Q.tiles_z;
+        const int ty = (int)(r % Q.tiles_y), tx = (int)(r / Q.tiles_y);
+        const unsigned bytes = (unsigned)direct_box_bytes(Q.BX, Q.BY, Q.BZ);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(axis3_smem_u32(box)), "l"(&map), "r"(tz * Q.Tz), "r"(ty * Q.Ty), "r"(tx * Q.Tx), "r"(bar_s) : "memory");
+    }
+    mbar_wait(bar_s, 0);
+    direct_tile_compute(Q, box, tile, (int)threadIdx.x);
+#endif
+}
+
+extern "C" int dbspm_support_points_f64(const double *B, int nx, int ny, int nz, int max_points, int *count_dev,
+                                        long long *idx_dev, double *val_dev, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    DBSPM_REQUIRE(B && count_dev && idx_dev && val_dev, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1 && max_points >= 1, DBSPM_EINVAL, "bad arguments");
+    DBSPM_CUDA_TRY(cudaMemsetAsync(count_dev, 0, sizeof(int), st));
+    const long long n = (long long)nx * ny * nz;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    support_points_kernel<<<(unsigned)blocks, 256, 0, st>>>(B, n, max_points, count_dev, idx_dev, val_dev);
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    return DBSPM_OK;
+}
+
+extern "C" size_t dbspm_corr3d_direct_workspace_bytes(int nx, int ny, int nz, int z_lo, int z_hi, int npts,
+                                                      const int *sx, const int *sy, const int *sz)
+{
+    if (!sx || !sy || !sz) return 0;
+    std::vector<double> w((size_t)(npts > 0 ? npts : 0), 1.0);
+    const DirectPlan D = direct_make_plan(nx, ny, nz, z_lo, z_hi, npts, sx, sy, sz, w.data(), 1.0);
+    return D.ok ? direct_workspace_bytes(D) : 0;
+}
+
+// fused multiply-adds per output point the direct kernel would execute (zero padding of the chunks included); 0 = the
+// support does not fit a shared-memory box.  The host compares N_w * this with the cost of the spectral path.
+extern "C" long long dbspm_corr3d_direct_cost(int nx, int ny, int nz, int z_lo, int z_hi, int npts,
+                                              const int *sx, const int *sy, const int *sz)
+{
+    if (!sx || !sy || !sz) return 0;
+    std::vector<double> w((size_t)(npts > 0 ? npts : 0), 1.0);
+    const DirectPlan D = direct_make_plan(nx, ny, nz, z_lo, z_hi, npts, sx, sy, sz, w.data(), 1.0);
+    return D.ok ? D.fma_per_output : 0;
+}
+
+extern "C" int dbspm_corr3d_direct_f64(const double *A, double alphaA, double dV, int nx, int ny, int nz, int z_lo, int z_hi,
+                                       int npts, const int *sx, const int *sy, const int *sz, const double *w,
+                                       double *E_win, void *workspace, size_t workspace_bytes, int flags, void *stream)
+{
+    (void)flags;
+    cudaStream_t st = (cudaStream_t)stream;
+    DBSPM_REQUIRE(A && E_win && workspace && sx && sy && sz && w, DBSPM_EINVAL, "null pointer argument");
+    DBSPM_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1, DBSPM_EINVAL, "bad shape (%d,%d,%d)", nx, ny, nz);
+    DBSPM_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= nz, DBSPM_EINVAL, "bad window [%d,%d) for nz=%d", z_lo, z_hi, nz);
+    DBSPM_REQUIRE(npts >= 1, DBSPM_EINVAL, "need at least one support point");
+    const DirectPlan D = direct_make_plan(nx, ny, nz, z_lo, z_hi, npts, sx, sy, sz, w, dV);
+    DBSPM_REQUIRE(D.ok, DBSPM_EUNSUPPORTED, "tip support too wide for the direct path (use dbspm_corr3d_f64)");
+    DBSPM_REQUIRE(workspace_bytes >= direct_workspace_bytes(D) && ((uintptr_t)workspace & 255) == 0, DBSPM_EWORKSPACE,
+                  "workspace needs %zu bytes, 256-byte aligned (got %zu)", direct_workspace_bytes(D), workspace_bytes);
+    TmapEncodeFn enc = tmap_encoder();
+    DBSPM_REQUIRE(enc != nullptr, DBSPM_EUNSUPPORTED, "cuTensorMapEncodeTiled unavailable");
+    unsigned char *ws = (unsigned char *)workspace;
+    double *P = (double *)ws;
+    int *off_d = (int *)(ws + direct_align((size_t)D.PX * D.PY * D.PZ * sizeof(double), 256));
+    double *w_d = (double *)((unsigned char *)off_d + direct_align(D.chunk_off.size() * sizeof(int), 256));
+    // pageable host -> device: the runtime stages the source before returning, the vectors may die with this frame
+    DBSPM_CUDA_TRY(cudaMemcpyAsync(off_d, D.chunk_off.data(), D.chunk_off.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    DBSPM_CUDA_TRY(cudaMemcpyAsync(w_d, D.chunk_w.data(), D.chunk_w.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    DirectPadParams Qp;
+    Qp.A = A; Qp.P = P; Qp.nx = nx; Qp.ny = ny; Qp.nz = nz; Qp.PX = D.PX; Qp.PY = D.PY; Qp.PZ = D.PZ;
+    Qp.x0 = D.start[0]; Qp.y0 = D.start[1]; Qp.z0 = (z_lo + D.start[2]) % nz; Qp.alpha = alphaA;
+    const long long np = (long long)D.PX * D.PY * D.PZ;
+    long long pb = (np + 255) / 256;
+    if (pb > 148LL * 32) pb = 148LL * 32;
+    direct_pad_kernel<<<(unsigned)pb, 256, 0, st>>>(Qp);
+    DBSPM_CUDA_TRY(cudaGetLastError());
+    CUtensorMap map;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)D.PZ, (cuuint64_t)D.PY, (cuuint64_t)D.PX};
+        cuuint64_t str[2] = {(cuuint64_t)D.PZ * 8, (cuuint64_t)D.PZ * D.PY * 8};
+        cuuint32_t box[3] = {(cuuint32_t)D.BZ, (cuuint32_t)D.BY, (cuuint32_t)D.BX};
+        cuuint32_t ones[3] = {1, 1, 1};
+        DBSPM_REQUIRE(enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)P, dims, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS,
+                      DBSPM_ECUDA, "cuTensorMapEncodeTiled failed for the direct correlation (P %d x %d x %d, box %d x %d x %d)",
+                      D.PX, D.PY, D.PZ, D.BX, D.BY, D.BZ);
+    }
+    DirectParams Q;
+    Q.P = P; Q.PX = D.PX; Q.PY = D.PY; Q.PZ = D.PZ; Q.E = E_win; Q.nx = nx; Q.ny = ny; Q.nzw = z_hi - z_lo;
+    Q.Tx = D.Tx; Q.Ty = D.Ty; Q.Tz = D.Tz; Q.BX = D.BX; Q.BY = D.BY; Q.BZ = D.BZ;
+    Q.tiles_y = D.tiles_y; Q.tiles_z = D.tiles_z; Q.nchunks = (int)D.chunk_off.size();
+    Q.chunk_off = off_d; Q.chunk_w = w_d;
+    const long long ntiles = (long long)D.tiles_x * D.tiles_y * D.tiles_z;
+    DBSPM_REQUIRE(ntiles < 2147483647LL, DBSPM_EUNSUPPORTED, "grid too large");
+    const size_t smem = ((direct_box_bytes(D.BX, D.BY, D.BZ) + 127) & ~(size_t)127) + 128 + 16;
+    DBSPM_CUDA_TRY(cudaFuncSetAttribute(direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    direct_kernel<<<(unsigned)ntiles, DIRECT_THREADS, smem, st>>>(Q, map);
     DBSPM_CUDA_TRY(cudaGetLastError());
     return DBSPM_OK;
 }

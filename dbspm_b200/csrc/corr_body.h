@@ -647,7 +647,9 @@ HD void axis_tma_body(const AxisTmaParams &P, const void *const *lmaps, const vo
 {
     const int n = P.n, T = 1 << P.tshift;
     const size_t tile_bytes = axis3_tile_bytes(n, P.tshift);
-    unsigned char *base = (unsigned char *)(((size_t)smem_raw + 127) & ~(size_t)127);
+    // pointer arithmetic, not a round trip through an integer: the compiler must keep knowing that this is shared memory
+    // (round 1 aligned through size_t and every access of the tile became a generic LD.E / ST.E instead of LDS / STS)
+    unsigned char *base = smem_raw + ((128 - ((size_t)smem_raw & 127)) & 127);
     cplx *tw = (cplx *)(base + AXIS3_NBUF * tile_bytes);
     unsigned long long *full = (unsigned long long *)(tw + n);
     unsigned long long *empty = full + AXIS3_NBUF;
@@ -911,9 +913,7 @@ HD void zfused_body(const ZFusedParams &P, unsigned char *smem_raw, long long bi
 // ------------------------------------------------------------------------------------------
 template <int ZLV> HD size_t zfused2_smem_bytes(int n)
 {
-    // twiddles of length n; the half-length table exp(-2 pi i k / nz) is read through L1 (once per pointwise item): with it
-    // in shared memory four CTAs of the n = 128 kernel miss the 228 KB of an SM by 1 KB
-    return (size_t)n * 16 + (size_t)n * (4 * ZLV + 1) * 16 + (size_t)n * (2 * ZLV + 1) * 16 + (size_t)n * 8 + ZLV * 6 * 4 + 16;
+    return (size_t)n * 16 * 2 + (size_t)n * (4 * ZLV + 1) * 16 + (size_t)n * (2 * ZLV + 1) * 16 + (size_t)n * 8 + ZLV * 6 * 4 + 16;
 }
 
 template <int D, int R, int ZLV>
@@ -973,7 +973,8 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
     constexpr int TSI = TSF - 1;
     const int n = P.n;
     cplx *tw = (cplx *)smem_raw;
-    cplx *U = tw + n;
+    cplx *twh = tw + n;
+    cplx *U = twh + n;
     cplx *S = U + (size_t)n * LDF;
     int *pos_of = (int *)(S + (size_t)n * LDI);
     int *freq_of = pos_of + n;
@@ -981,6 +982,7 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
 
     for (int e = tid; e < n; e += nthr) {
         tw[e] = ldg_c(P.tw + e);
+        twh[e] = ldg_c(P.twN + e);
         pos_of[e] = LDG(P.pos_of + e);
         freq_of[e] = LDG(P.freq_of + e);
     }
@@ -1026,7 +1028,7 @@ HD void zfused_body_v2(const ZFusedParams &P, unsigned char *smem_raw, long long
         const int ps = pos_of[ks];
         const cplx *Uk = U + (p * LDF + 4 * l);
         const cplx *Us = U + (ps * LDF + 4 * l);
-        const cplx w = ldg_c(P.twN + k);                          // exp(-2 pi i k / nz)
+        const cplx w = twh[k];                                    // exp(-2 pi i k / nz)
         const cplx miw = cmake(w.y, -w.x);                        // -i * w
         const cplx a1 = Uk[0], a2 = cconj(Us[1]);
         const cplx b1 = Uk[2], b2 = cconj(Us[3]);

@@ -98,8 +98,108 @@ def tip_zsupport(rho1, device=None) -> tuple[int, int]:
         return circular_support(flags.cpu().numpy() != 0)
 
 
+# ---- direct real-space path for a tip with a few hundred support points ---------------------------------------
+# measured on B200 (profiles/README.md, scripts/time_direct.py): the tile kernel sustains DIRECT_FMA_RATE fused
+# multiply-adds per second (a quarter of the FP64 peak: 64-bit shared-memory loads of neighbouring rows conflict two-fold)
+# after a padding pass that moves 16 bytes per padded sample point; the spectral path moves 80 N + 40 N_w bytes at
+# SPECTRAL_BYTES_RATE (its five passes average 45 % of copy bandwidth), with N shrunk to the pruned z length for a tip
+# that is compact in z.  Crossover against the pruned spectral path: K ~ 100 support points at 196x196x240, ~30 at 1024x1024x256
+DIRECT_FMA_RATE = 4.0e12
+SPECTRAL_BYTES_RATE = 2.9e12
+DIRECT_MAX_POINTS = 4096
+
+
+def tip_support_points(rho1, max_points=DIRECT_MAX_POINTS, device=None):
+    """The nonzero entries of the tip array, compacted on the device: (pts (K,3) int32 indices, values (K,)) sorted by
+    index, or None when there are more than max_points (a real CHGCAR tip: noise floor everywhere).  One streaming read
+    of the array and a synchronising copy of at most max_points entries; do it once per tip."""
+    on_device = isinstance(rho1, torch.Tensor) and rho1.is_cuda
+    dev = rho1.device if on_device else _device(device)
+    b = _to_dev(rho1, dev)
+    nx, ny, nz = (int(v) for v in b.shape)
+    with torch.cuda.device(dev):
+        count = torch.zeros(1, dtype=torch.int32, device=dev)
+        idx = torch.empty(int(max_points), dtype=torch.int64, device=dev)
+        val = torch.empty(int(max_points), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().dbspm_support_points_f64(b.data_ptr(), nx, ny, nz, int(max_points), count.data_ptr(),
+                                                       idx.data_ptr(), val.data_ptr(), _stream_ptr(dev)))
+        k = int(count.item())
+    if k > int(max_points) or k == 0:
+        return None
+    idx_h, val_h = idx[:k].cpu().numpy(), val[:k].cpu().numpy()
+    order = np.argsort(idx_h)                       # the device compaction is unordered
+    idx_h, val_h = idx_h[order], val_h[order]
+    pts = np.stack(np.unravel_index(idx_h, (nx, ny, nz)), axis=1).astype(np.int32)
+    return pts, val_h
+
+
+def _pts_args(pts):
+    pts = np.ascontiguousarray(pts, dtype=np.int32)
+    cols = [np.ascontiguousarray(pts[:, q]) for q in range(3)]
+    return cols, [c.ctypes.data_as(C.POINTER(C.c_int)) for c in cols]
+
+
+def direct_cost(shape, z_lo, z_hi, pts) -> int:
+    """Fused multiply-adds per output point of the direct kernel for this support (0: it does not fit a tile)."""
+    nx, ny, nz = (int(v) for v in shape)
+    keep, ptrs = _pts_args(pts)
+    return int(_lib.lib().dbspm_corr3d_direct_cost(nx, ny, nz, int(z_lo), int(z_hi), len(keep[0]), *ptrs))
+
+
+def points_zsupport(pts, nz):
+    """(s_lo, s_len) of a support given as points: what tip_zsupport finds by scanning the array."""
+    flags = np.zeros(int(nz), dtype=bool)
+    flags[np.asarray(pts)[:, 2]] = True
+    return circular_support(flags)
+
+
+def direct_is_faster(shape, z_lo, z_hi, pts) -> bool:
+    """Path choice per grid shape and tip support: padding pass + N_w * (multiply-adds per output) at the measured rate of
+    the tile kernel, against the bytes of the five spectral passes (on the z-pruned problem when the support allows it) at
+    their measured rate."""
+    nx, ny, nz = (int(v) for v in shape)
+    cost = direct_cost(shape, z_lo, z_hi, pts)
+    if cost == 0:
+        return False
+    nzw = int(z_hi) - int(z_lo)
+    nw = nx * ny * nzw
+    sup = points_zsupport(pts, nz)
+    cut = pruned_cut(nz, z_lo, z_hi, sup) if sup[1] < nz else None
+    n = nx * ny * (cut[1] if cut is not None else nz)
+    zext = sup[1] - 1
+    t_direct = 16.0 * nx * ny * (nzw + zext) / SPECTRAL_BYTES_RATE + nw * cost / DIRECT_FMA_RATE
+    return t_direct < (80.0 * n + 40.0 * nw) / SPECTRAL_BYTES_RATE
+
+
+def density_overlap_direct(rho0, pts, weights, dr, z_lo=0, z_hi=None, alpha0=1.0, out=None, device=None):
+    """dV * sum_k weights[k] * rho0[(R + pts[k]) mod N]^alpha0 on the window planes: the correlation with a tip that is
+    nonzero only at `pts` (tip_support_points) with weights = tip[pts]^alpha1, as a direct real-space sum."""
+    on_device = isinstance(rho0, torch.Tensor) and rho0.is_cuda
+    dev = rho0.device if on_device else _device(device)
+    a = _to_dev(rho0, dev)
+    nx, ny, nz = (int(v) for v in a.shape)
+    z_hi = nz if z_hi is None else int(z_hi)
+    z_lo = int(z_lo)
+    keep, ptrs = _pts_args(pts)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    if w.shape != (len(keep[0]),):
+        raise ValueError("weights must have one entry per support point")
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        need = L.dbspm_corr3d_direct_workspace_bytes(nx, ny, nz, z_lo, z_hi, len(w), *ptrs)
+        if need == 0:
+            raise ValueError("tip support too wide for the direct path (or bad window)")
+        ws = _workspace(need, dev)
+        if out is None:
+            out = torch.empty((nx, ny, z_hi - z_lo), dtype=torch.float64, device=dev)
+        _lib.check(L.dbspm_corr3d_direct_f64(a.data_ptr(), float(alpha0), float(np.prod(np.asarray(dr, dtype=np.float64))),
+                                             nx, ny, nz, z_lo, z_hi, len(w), *ptrs, w.ctypes.data_as(C.POINTER(C.c_double)),
+                                             out.data_ptr(), ws.data_ptr(), ws.numel(), 0, _stream_ptr(dev)))
+    return out if on_device else out.cpu().numpy()
+
+
 def density_overlap_window(rho0, rho1, dr, z_lo=0, z_hi=None, alpha0=1.0, alpha1=1.0, out=None, device=None,
-                           flags=0, tip_support=None):
+                           flags=0, tip_support=None, tip_points=None):
     """dV * sum_r rho0[r]^alpha0 * rho1[(r-R) mod N]^alpha1 for R on planes z_lo..z_hi-1.
 
     Fuses what dbspm:329-330 / :348-349 do in three passes (`**ALPHA`, get_density_overlap,
@@ -108,7 +208,24 @@ def density_overlap_window(rho0, rho1, dr, z_lo=0, z_hi=None, alpha0=1.0, alpha1
 
     tip_support: None -> full-length transform; "auto" -> find the z-support of rho1 (tip_zsupport)
     and take the z-pruned path when it pays; (s_lo, s_len) -> the caller's claim that rho1 is exactly
-    zero outside those planes (e.g. found once for a tip that is used for many samples)."""
+    zero outside those planes (e.g. found once for a tip that is used for many samples).
+
+    tip_points: None -> spectral path; "auto" -> compact the nonzero entries of rho1 (tip_support_points) and take the direct
+    real-space sum when that is cheaper for this shape (direct_is_faster); (pts, values) -> the caller's list (found once
+    per tip), same choice.  The path is picked per grid shape and support size."""
+    if tip_points is not None:
+        found = tip_support_points(rho1, device=device) if isinstance(tip_points, str) else tip_points
+        if isinstance(tip_points, str) and tip_points != "auto":
+            raise ValueError("tip_points must be None, 'auto' or (pts, values)")
+        shape0 = tuple(int(v) for v in rho0.shape)
+        zh = shape0[2] if z_hi is None else int(z_hi)
+        if found is not None and direct_is_faster(shape0, z_lo, zh, found[0]):
+            pts, vals = found
+            with np.errstate(invalid="ignore"):
+                w = vals if float(alpha1) == 1.0 else np.power(vals, float(alpha1))       # numpy's `**`, as the reference
+            return density_overlap_direct(rho0, pts, w, dr, z_lo, zh, alpha0, out=out, device=device)
+        if found is not None and tip_support is None and shape0[2] % 2 == 0:
+            tip_support = points_zsupport(found[0], shape0[2])                            # spectral, but z-pruned: the list says where
     on_device = isinstance(rho0, torch.Tensor) and rho0.is_cuda
     dev = rho0.device if on_device else _device(device)
     a = _to_dev(rho0, dev)

@@ -62,8 +62,9 @@ extern "C" {
 #define DBSPM_CORR_SKIP_Z     (1 << 10)
 #define DBSPM_CORR_SKIP_YINV  (1 << 11)
 #define DBSPM_CORR_SKIP_XINV  (1 << 12)
-#define DBSPM_CORR_Z_RADIX8   (1 << 13)  /* fused z kernel: plan with radices <= 8 and the kernel built without the radix-16
-                                            butterfly (fewer registers, one more shared-memory stage; A/B timing) */
+#define DBSPM_CORR_Z_RADIX8   (1 << 13)  /* fused z kernel: plan with radices <= 8 and the kernel instantiated without the radix-16
+                                            butterfly (120 instead of 166 registers, one more shared-memory stage; A/B timing:
+                                            2.67 against 2.75 ms at nz = 256 on B200 -- the kernel is not occupancy-bound) */
 
 /* library / build identification: "dbspm_b200 <version> sm_100a" */
 const char *dbspm_version(void);
@@ -94,6 +95,26 @@ int dbspm_corr3d_pruned_f64(const double *A, const double *B, double alphaA, dou
                             int nx, int ny, int nz, int z_lo, int z_hi, int s_lo, int s_len, double *E_win,
                             void *workspace, size_t workspace_bytes, int flags, void *stream);
 int dbspm_zsupport_f64(const double *B, int nx, int ny, int nz, int *plane_nonzero, void *stream);
+
+/* ---- sr / es as a direct real-space sum for a tip with a few hundred support points ---------------------------------
+ * E_win[x,y,z-z_lo] = dV * sum_k w_k * A[(R + s_k) mod N]^alphaA: the same quantity as dbspm_corr3d_f64 when B is nonzero
+ * only at the npts points s_k = (sx,sy,sz)[k] (indices into B) with w_k = B[s_k]^alphaB.  N_w * K fused multiply-adds
+ * instead of five passes over both grids: cheaper than the spectral path for small K (the crossover is measured in
+ * profiles/; dbspm_corr3d_direct_cost returns the multiply-adds per output point for the caller's choice, 0 when the
+ * support's bounding box does not fit a shared-memory tile).  One kernel builds A^alphaA on the planes the window can see
+ * with a periodic halo; the main kernel stages one sample box per output tile with a single tensor-map load
+ * (cp.async.bulk.tensor.3d) and keeps a sliding window of the box in registers.  sx, sy, sz, w are HOST arrays;
+ * dbspm_support_points_f64 compacts the nonzero entries of a device array (count_dev: device int, entries beyond
+ * max_points are counted but not stored).  Replaces pydbspm/interactions.py:18-22 + dbspm:329-330 / :348-349.            */
+int dbspm_support_points_f64(const double *B, int nx, int ny, int nz, int max_points, int *count_dev,
+                             long long *idx_dev, double *val_dev, void *stream);
+size_t dbspm_corr3d_direct_workspace_bytes(int nx, int ny, int nz, int z_lo, int z_hi, int npts,
+                                           const int *sx, const int *sy, const int *sz);
+long long dbspm_corr3d_direct_cost(int nx, int ny, int nz, int z_lo, int z_hi, int npts,
+                                   const int *sx, const int *sy, const int *sz);
+int dbspm_corr3d_direct_f64(const double *A, double alphaA, double dV, int nx, int ny, int nz, int z_lo, int z_hi,
+                            int npts, const int *sx, const int *sy, const int *sz, const double *w,
+                            double *E_win, void *workspace, size_t workspace_bytes, int flags, void *stream);
 
 /* ---- sr / es distributed over the G ranks of a group (x-slab decomposition) ------------------
  * Replaces the same reference lines as dbspm_corr3d_f64 (the reference computes sr / es on rank 0 only,

@@ -158,7 +158,52 @@ def next_row_cases():
     return {"interp_shape": list(out.data.shape), "rpivot": 0.3, "new_origin_z_index": 4}
 
 
+def spmgrid_cases():
+    """SPMGrid.interpolate_data (SPMGrid.py:311-342) run through the reference's own method on attribute containers (the
+    class itself needs matplotlib / ase to be constructed; the method only reads attributes).  Own file."""
+    import copy
+    import types
+    sys.path.insert(0, os.path.join(HERE, "refshim"))
+    import pydbspm.SPMGrid as RS
+    fake = types.ModuleType("tricubic")
+    fake.tricubic = O.Tricubic
+    sys.modules["tricubic"] = fake
+    rng = np.random.default_rng(20260103)
+
+    class Box(types.SimpleNamespace):
+        def copy(self):
+            return copy.deepcopy(self)
+
+    def make(shape, dr, z0, data, tip=None):
+        xs, ys = np.arange(shape[0]) * dr[0], np.arange(shape[1]) * dr[1]
+        x, y = np.meshgrid(xs, ys, indexing="ij")
+        b = Box(data=data, x=x, y=y, z=z0 + np.arange(shape[2]) * dr[2], dr=np.asarray(dr), shape=data.shape)
+        b.x_ = np.linalg.norm([x[:, 0], y[:, 0]], axis=0)
+        b.y_ = np.linalg.norm([x[0, :], y[0, :]], axis=0)
+        if tip is not None:
+            b.tip = tip
+        return b
+    dr = (0.15, 0.15, 0.1)
+    gx, gy, gz = np.meshgrid(np.arange(24), np.arange(20), np.arange(30), indexing="ij")
+    stm = np.exp(-((gx - 11.5) ** 2 + (gy - 9.0) ** 2) / 40.0 - gz / 8.0) + 0.05 * np.cos(2 * np.pi * gx / 24) * np.sin(2 * np.pi * gy / 20)
+    data_grid = make((24, 20, 30), dr, 3.0, stm)
+    tip = rng.normal(0.0, 0.05, (24, 20, 6, 3))
+    tip[..., 2] = -3.02 + 0.02 * rng.standard_normal((24, 20, 6)) + 3.02       # set_tip adds rpivot to z
+    tip_grid = make((24, 20, 6), dr, 3.4, np.zeros((24, 20, 6)), tip)
+    out = RS.SPMGrid.interpolate_data(tip_grid, data_grid)
+    np.savez_compressed(os.path.join(OUT, "spmgrid_reference.npz"), stm=stm, tip=tip, dr=np.asarray(dr), interp=out.data)
+    return {"data_shape": [24, 20, 30], "tip_shape": [24, 20, 6], "data_z0": 3.0, "tip_z0": 3.4}
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["spmgrid"]:
+        with open(os.path.join(OUT, "manifest.json")) as fh:
+            manifest = json.load(fh)
+        manifest["spmgrid"] = spmgrid_cases()
+        with open(os.path.join(OUT, "manifest.json"), "w") as fh:
+            json.dump(manifest, fh, indent=1, sort_keys=True)
+        print("wrote spmgrid_reference.npz")
+        raise SystemExit(0)
     if sys.argv[1:] == ["noortho"]:          # round 2: add the skew-cell relax fixture without regenerating the others
         with open(os.path.join(OUT, "manifest.json")) as fh:
             manifest = json.load(fh)
@@ -170,7 +215,7 @@ if __name__ == "__main__":
     manifest = {
         "generator": "oracle/make_golden.py", "reference": "/root/reference (SPMTH/DBSPM, unmodified)",
         "numpy": np.__version__, "scipy": scipy.__version__,
-        "overlap": overlap_cases(), "relax": relax_cases(), "relax_noortho": relax_noortho_cases(), "geometry": geometry_cases(),
+        "overlap": overlap_cases(), "relax": relax_cases(), "relax_noortho": relax_noortho_cases(), "spmgrid": spmgrid_cases(), "geometry": geometry_cases(),
         "nextrow": next_row_cases(),
     }
     with open(os.path.join(OUT, "manifest.json"), "w") as fh:

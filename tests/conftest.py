@@ -165,6 +165,23 @@ class Emu:
             raise RuntimeError(f"emu_relax_powell_slab_f64 -> {rc}")
         return etp, cart, nfev
 
+    def corr3d_direct(self, a, pts, w, dr, z_lo, z_hi, alpha0=1.0):
+        """direct real-space correlation with a tip given as support points `pts` (K,3 indices) and weights w (= B^alphaB)"""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        nx, ny, nz = a.shape
+        pts = np.ascontiguousarray(pts, dtype=np.int32)
+        sx, sy, sz = (np.ascontiguousarray(pts[:, q]) for q in range(3))
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        out = np.empty((nx, ny, z_hi - z_lo))
+        f = self.L.emu_corr3d_direct_f64
+        f.restype = C.c_longlong
+        f.argtypes = [_dp, C.c_double, C.c_double] + [C.c_int] * 6 + [_ip, _ip, _ip, _dp, _dp]
+        rc = f(self._p(a), alpha0, float(np.prod(dr)), nx, ny, nz, z_lo, z_hi, len(w), sx.ctypes.data_as(_ip), sy.ctypes.data_as(_ip),
+               sz.ctypes.data_as(_ip), self._p(w), self._p(out))
+        if rc < 0:
+            raise RuntimeError(f"emu_corr3d_direct_f64 -> {rc}")
+        return out, int(rc)
+
     def tricubic(self, g, x, y, z):
         g = np.ascontiguousarray(g, dtype=np.float64)
         return self.L.emu_tricubic(self._p(g), *g.shape, x, y, z)

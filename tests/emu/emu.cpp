@@ -11,6 +11,7 @@
 #include <vector>
 #include "../../dbspm_b200/csrc/corr_body.h"
 #include "../../dbspm_b200/csrc/relax_body.h"
+#include "../../dbspm_b200/csrc/direct_plan.h"
 #include "../../dbspm_b200/csrc/plan.h"
 
 double (*dbspm_emu_interp_hook)(double, double, double) = nullptr;
@@ -500,4 +501,31 @@ extern "C" long long emu_check_div_by(long long n, unsigned long long seed)
         if (memcmp(&got, &want, sizeof got) != 0 && !(got == 0.0 && want == 0.0)) ++bad;
     }
     return bad;
+}
+
+
+// what dbspm_corr3d_direct_f64 does: plan on the host, the pad kernel body, then every tile (tensor-map load emulated by a
+// plain copy with zero fill, all DIRECT_THREADS "threads" one after the other).  Returns the multiply-adds per output (> 0), < 0 on error
+extern "C" long long emu_corr3d_direct_f64(const double *A, double alphaA, double dV, int nx, int ny, int nz, int z_lo, int z_hi,
+                                           int npts, const int *sx, const int *sy, const int *sz, const double *w, double *E_win)
+{
+    const DirectPlan D = direct_make_plan(nx, ny, nz, z_lo, z_hi, npts, sx, sy, sz, w, dV);
+    if (!D.ok) return -2;
+    std::vector<double> P((size_t)D.PX * D.PY * D.PZ);
+    DirectPadParams Qp;
+    Qp.A = A; Qp.P = P.data(); Qp.nx = nx; Qp.ny = ny; Qp.nz = nz; Qp.PX = D.PX; Qp.PY = D.PY; Qp.PZ = D.PZ;
+    Qp.x0 = D.start[0]; Qp.y0 = D.start[1]; Qp.z0 = (z_lo + D.start[2]) % nz; Qp.alpha = alphaA;
+    direct_pad_body(Qp, 0, 1);
+    DirectParams Q;
+    Q.P = P.data(); Q.PX = D.PX; Q.PY = D.PY; Q.PZ = D.PZ; Q.E = E_win; Q.nx = nx; Q.ny = ny; Q.nzw = z_hi - z_lo;
+    Q.Tx = D.Tx; Q.Ty = D.Ty; Q.Tz = D.Tz; Q.BX = D.BX; Q.BY = D.BY; Q.BZ = D.BZ;
+    Q.tiles_y = D.tiles_y; Q.tiles_z = D.tiles_z; Q.nchunks = (int)D.chunk_off.size();
+    Q.chunk_off = D.chunk_off.data(); Q.chunk_w = D.chunk_w.data();
+    std::vector<double> box((size_t)D.BX * D.BY * D.BZ);
+    const long long ntiles = (long long)D.tiles_x * D.tiles_y * D.tiles_z;
+    for (long long t = 0; t < ntiles; ++t) {
+        direct_tile_stage_host(Q, box.data(), t);
+        for (int tid = 0; tid < DIRECT_THREADS; ++tid) direct_tile_compute(Q, box.data(), t, tid);
+    }
+    return D.fma_per_output;
 }

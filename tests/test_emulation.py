@@ -442,3 +442,39 @@ def test_corr3d_pruned_equals_full_correlation(emu, shape, window, support):
     # a support claim wider than the real one is harmless
     got2, _ = emu.corr3d_pruned(a, b, dr, window[0], window[1], s_lo - 2, s_len + 3, alpha0=1.08)
     assert np.abs(got2 - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("shape,window,center,radius", [
+    ((12, 10, 16), (3, 11), (0, 0, 0), 2.2),          # ball around the origin: wraps on all three axes
+    ((9, 14, 20), (0, 20), (4, 7, 10), 1.5),          # off-centre support, whole z range
+    ((16, 16, 24), (20, 24), (15, 1, 23), 2.9),       # window at the top, support straddling the corner
+    ((7, 5, 8), (2, 3), (0, 0, 0), 0.0),              # a single point (delta tip)
+    ((40, 36, 32), (5, 27), (0, 0, 0), 3.4),          # several tiles in x and y
+])
+def test_direct_real_space_correlation(emu, shape, window, center, radius):
+    """Direct path (tip = a few hundred support points): plan (circular bounding box, chunks), pad kernel with periodic halo,
+    tile kernel with the emulated tensor-map load -- against the reference's FFT expression and the explicit periodic sum."""
+    rng = np.random.default_rng(sum(shape) + window[0])
+    a = rng.random(shape) + 0.05
+    b = np.zeros(shape)
+    g = np.stack(np.meshgrid(*[np.arange(n) for n in shape], indexing="ij"), axis=-1)
+    d = g - np.array(center)
+    d = np.minimum(np.abs(d), np.array(shape) - np.abs(d))                       # periodic distance
+    mask = (d ** 2).sum(axis=-1) <= radius ** 2 + 1e-9
+    b[mask] = rng.random(int(mask.sum())) - 0.3
+    b[tuple(center)] = 0.7
+    if radius > 2:
+        b[tuple((np.array(center) + [1, 0, 1]) % shape)] = 0.0                   # a hole inside a chunk
+    pts = np.argwhere(b != 0.0)
+    dr = np.array([0.1, 0.2, 0.3])
+    for alpha in (1.0, 1.08):
+        w = np.abs(b[b != 0.0]) ** alpha if alpha != 1.0 else b[b != 0.0]
+        bb = np.zeros(shape); bb[b != 0.0] = w
+        ref = O.density_overlap_fft(a ** alpha, bb, dr)[:, :, window[0]:window[1]]
+        got, cost = emu.corr3d_direct(a, pts, w, dr, window[0], window[1], alpha0=alpha)
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, alpha)
+        assert cost >= len(w)
+    if np.prod(shape) <= 4000:
+        direct = O.corr_direct(a, b, dr, window[0], window[1])
+        got, _ = emu.corr3d_direct(a, pts, b[b != 0.0], dr, window[0], window[1])
+        assert np.abs(got - direct).max() <= 1e-13 * np.abs(direct).max()

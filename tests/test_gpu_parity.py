@@ -697,6 +697,74 @@ def test_cli_sr_es_relax_end_to_end(tmp_path, ops):
                 assert abs(br["data"][i, j, k] - want_b[i, j, k]) <= 1e-11 * np.abs(sp).max(), (i, j, k)
 
 
+def _oracle_relax_rows(args):
+    static, i_lo, i_hi, ny, nz, kappa, rp, dr, twin = args
+    return O.relax_tile(static, i_lo, i_hi, 0, ny, nz, kappa, rp, dr, twin=twin)
+
+
+def test_cli_full_pyridine_example_at_size(tmp_path, ops):
+    """BASELINE configs[0] through the CLI at its real size: `dbspm sr es relax -i input.in` with the reference's
+    example/input.in parameters on synthetic 196x196x240 sample.npz / tip.npz (the committed ones are LFS pointers), against
+    the oracle pipeline -- numpy overlap -> static -> C Powell on all host cores: sr/es <= 1e-9, E <= 1e-6, tip positions
+    within 1e-6 * rpivot up to a bounded fraction of Powell branch flips, and bit for bit against the oracle's kernel twin run
+    on the very static the CLI assembled.  The per-step time table the CLI prints is kept in gpurun_out/."""
+    import multiprocessing as mp
+    from dbspm_b200 import synth
+    from dbspm_b200.grid import Grid, get_grid_from_params
+    from dbspm_b200.input_parser import parse_params
+    cfg = synth.CONFIGS["pyridine"]
+    dev = torch.device("cuda", 0)
+    rhoS, potS, atoms = synth.make_sample(cfg, dev)
+    rhoT, nrhoT = synth.make_tip(cfg, dev, "noisy")
+    rhoS, potS, rhoT, nrhoT = (t.cpu().numpy() for t in (rhoS, potS, rhoT, nrhoT))
+    cell = np.diag(cfg.cell)
+    pos = np.array([[a[1], a[2], a[3]] for a in atoms]); num = np.array([a[0] for a in atoms])
+    (tmp_path / "sample").mkdir(); (tmp_path / "tip").mkdir()
+    np.savez(tmp_path / "sample" / "sample.npz", rhoS=rhoS, potS=potS, cell=cell, positions=pos, numbers=num)
+    np.savez(tmp_path / "tip" / "tip.npz", rhoT=rhoT, nrhoT=nrhoT, cell=cell,
+             positions=np.array([[0, 0, 0.0], [0, 0, 1.153425]]), numbers=np.array([8, 6]))
+    (tmp_path / "input.in").write_text("# Example input\nLABEL   = pyridine\nZ0      = 2.7\nZF      = 4.5\nZREF   = 3.0\n"
+                                       "ALPHA   = 1.08\nV       = 42.9071\nOPT = False\n")
+    p = parse_params(str(tmp_path / "input.in"))
+    gS = Grid(cfg.shape, cell=cell, positions=pos, numbers=num)
+    win, nidx = get_grid_from_params(p, gS, nidx=True, rpivot=p.RPIVOT, zpad=p.ZPAD, numbers=num, positions=pos)
+    z_lo, z_hi = nidx[2].start, nidx[2].stop
+    assert (z_lo, z_hi) == (76, 130) and tuple(int(v) for v in win.shape) == (196, 196, 54)     # SURVEY 8: window of config 1
+    vdw = synth.make_vdw_window(cfg, atoms, (196, 196, 54), float(win.origin[2])).numpy()
+    win.set_density("vdw", vdw)
+    win.save_density("vdw", filename=str(tmp_path / "pyridine_vdw.npz"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "dbspm"), "sr", "es", "relax", "-i", "input.in"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "cli_pyridine_steps.txt"), "w") as fh:
+        fh.write(r.stdout[r.stdout.index("Steps"):] if "Steps" in r.stdout else r.stdout)
+    sr = np.load(tmp_path / "pyridine_sr_a1.08.npz")["sr"]
+    es = np.load(tmp_path / "pyridine_es.npz")["es"]
+    rl = np.load(tmp_path / "relax_pyridine_k0.2000_a1.08_V42.91.npz")
+    dr = gS.dr
+    ref_sr = O.density_overlap_fft(rhoS ** 1.08, rhoT ** 1.08, dr)[:, :, z_lo:z_hi]
+    ref_es = O.density_overlap_fft(potS, nrhoT, dr)[:, :, z_lo:z_hi]
+    assert _rel(sr, ref_sr) <= 1e-9 and _rel(es, ref_es) <= 1e-9
+    assert rl["E"].shape == (196, 196, 24)
+    # the oracle pipeline end to end (its own sr / es / static), reference-faithful mode
+    static_ref = np.zeros(ref_sr.shape); static_ref += ref_sr * 42.9071; static_ref += ref_es; static_ref += vdw
+    static_cli = np.zeros(sr.shape); static_cli += sr * 42.9071; static_cli += es; static_cli += vdw     # dbspm:479-486 order
+    O.lib()
+    rows = [(i, min(i + 7, 196)) for i in range(0, 196, 7)]
+    with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+        ref = np.concatenate(pool.map(_oracle_relax_rows, [(static_ref, a, b, 196, 24, 0.2, 3.02, dr, False) for a, b in rows]))
+        twin = np.concatenate(pool.map(_oracle_relax_rows, [(static_cli, a, b, 196, 24, 0.2, 3.02, dr, True) for a, b in rows]))
+    assert _rel(rl["E"], ref[..., 0]) <= 1e-6
+    want = np.stack(O.sph2cart(ref[..., 1], ref[..., 2], 3.02))
+    got = np.stack([rl["tip_x"], rl["tip_y"], rl["tip_z"]])
+    dev_pos = np.abs(got - want).max(axis=0) / 3.02
+    assert (dev_pos > 1e-6).mean() <= 2e-3 and dev_pos.max() <= 1e-3, ((dev_pos > 1e-6).mean(), dev_pos.max())
+    # ... and against the kernel twin on the CLI's own static: identical bits for all 921 984 positions
+    assert np.array_equal(rl["E"], twin[..., 0])
+    assert np.array_equal(got, O.sph2cart_twin(twin[..., 1], twin[..., 2], 3.02))
+
+
 # ------------------------------------------------------------------------------------ next rows (SURVEY 8f)
 def test_delta_f_matches_reference_get_fs(ops):
     from dbspm_b200 import tools
@@ -733,6 +801,29 @@ def test_interpolate_data_matches_reference(ops, manifest):
     out = interpolate_data(new_grid, data_grid, "sp", rpivot=manifest["nextrow"]["rpivot"])
     assert list(out.data.shape) == manifest["nextrow"]["interp_shape"]
     assert np.abs(out.data - g["interp"]).max() <= 1e-12 * np.abs(g["interp"]).max()
+
+
+def test_spmgrid_interpolate_data_matches_reference(ops, manifest):
+    """SPMGrid.interpolate_data (SPMGrid.py:311-342): the fixture is the output of the reference's own method."""
+    from dbspm_b200.spmgrid import SPMGridLite, interpolate_data
+    g = np.load(os.path.join(ROOT, "tests", "golden", "spmgrid_reference.npz"))
+    m = manifest["spmgrid"]
+    dr = g["dr"]
+
+    def mesh(shape):
+        return np.meshgrid(np.arange(shape[0]) * dr[0], np.arange(shape[1]) * dr[1], indexing="ij")
+    x, y = mesh(m["data_shape"])
+    data = SPMGridLite(g["stm"], x, y, m["data_z0"] + np.arange(m["data_shape"][2]) * dr[2], dr)
+    x, y = mesh(m["tip_shape"])
+    tip = SPMGridLite(np.zeros(m["tip_shape"]), x, y, m["tip_z0"] + np.arange(m["tip_shape"][2]) * dr[2], dr, tip=g["tip"])
+    out = interpolate_data(tip, data)
+    assert out.data.shape == g["interp"].shape and out is not tip
+    assert np.abs(out.data - g["interp"]).max() <= 1e-12 * np.abs(g["interp"]).max()
+    # set_tip semantics (axis 0, rpivot added to z)
+    t2 = SPMGridLite(np.zeros(m["tip_shape"]), x, y, tip.z, dr)
+    raw = np.moveaxis(g["tip"], -1, 0).copy(); raw[2] -= 3.02
+    t2.set_tip(raw, rpivot=3.02, axis=0)
+    assert np.allclose(t2.tip, g["tip"], rtol=0, atol=1e-15)
 
 
 def test_interpolate_density_matches_reference(ops):
@@ -808,6 +899,51 @@ def test_compact_tip_takes_pruned_path_and_matches_full(ops, name):
     if name == "pyridine":
         ref = O.density_overlap_fft(potS.cpu().numpy(), nrhoT.cpu().numpy(), dr)[:, :, z_lo:z_hi]
         assert _rel(auto.cpu().numpy(), ref) <= 1e-9
+
+
+def _ball_tip(shape, radius, rng, center=(0, 0, 0)):
+    g = np.stack(np.meshgrid(*[np.arange(n) for n in shape], indexing="ij"), axis=-1)
+    d = np.abs(g - np.array(center))
+    d = np.minimum(d, np.array(shape) - d)
+    b = np.zeros(shape)
+    mask = (d ** 2).sum(axis=-1) <= radius ** 2 + 1e-9
+    b[mask] = rng.random(int(mask.sum())) + 0.05
+    return b
+
+
+@pytest.mark.parametrize("shape,window,radius,center", [
+    ((12, 10, 16), (3, 11), 2.2, (0, 0, 0)), ((40, 36, 32), (5, 27), 3.4, (0, 0, 0)), ((64, 48, 40), (0, 40), 2.0, (31, 7, 39)),
+    ((196, 196, 240), (76, 130), 4.3, (0, 0, 0)), ((33, 9, 62), (7, 30), 1.0, (0, 0, 0)), ((7, 5, 8), (2, 3), 0.0, (0, 0, 0)),
+])
+def test_direct_real_space_correlation(ops, shape, window, radius, center):
+    """The TMA-staged direct sum for a tip with a few hundred support points (north_star's alternative to the FFT):
+    support compaction on the device, path choice, and agreement with the numpy oracle and with the spectral path for
+    sr (alpha on both arrays) and es-like signed weights."""
+    rng = np.random.default_rng(sum(shape) + window[0])
+    a = rng.random(shape) + 0.05
+    b = _ball_tip(shape, radius, rng, center)
+    dr = np.array([0.1, 0.2, 0.3])
+    found = ops.tip_support_points(b)
+    assert found is not None
+    pts, vals = found
+    want_pts = np.argwhere(b != 0.0)
+    assert np.array_equal(pts, want_pts) and np.array_equal(vals, b[b != 0.0])
+    assert ops.direct_cost(shape, window[0], window[1], pts) >= len(vals)
+    for alpha, signed in ((1.08, False), (1.0, True)):
+        bb = b - 0.4 * (b != 0) if signed else b
+        w = bb[b != 0.0] if alpha == 1.0 else bb[b != 0.0] ** alpha
+        got = ops.density_overlap_direct(a, pts, w, dr, window[0], window[1], alpha)
+        spectral = ops.density_overlap_window(a, bb, dr, window[0], window[1], alpha, alpha)
+        assert _rel(got, spectral) <= 1e-12, (shape, alpha)
+        if np.prod(shape) < 3e6:
+            ref = O.density_overlap_fft(a ** alpha, bb ** alpha if alpha != 1.0 else bb, dr)[:, :, window[0]:window[1]]
+            assert _rel(got, ref) <= 1e-9
+        # the public operator picks the path itself ("auto"): whatever it picks, same answer
+        auto = ops.density_overlap_window(a, bb, dr, window[0], window[1], alpha, alpha, tip_points="auto")
+        assert _rel(auto, spectral) <= 1e-12
+    assert ops.tip_support_points(rng.random((8, 8, 8)), max_points=100) is None          # a dense tip: spectral path
+    # a support whose bounding box cannot be staged in shared memory is refused by the plan (the caller stays spectral)
+    assert ops.direct_cost((1024, 8, 8), 0, 8, np.array([[0, 0, 0], [512, 0, 0]])) == 0
 
 
 def test_pruned_entry_argument_checks(ops):
