@@ -236,11 +236,118 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+SWEEP_SETS = [(a, v, 0.20 if i < 8 else 0.24)
+              for i, (a, v) in enumerate((a, v) for a in (1.00, 1.04, 1.08, 1.12) for v in (35.0, 42.9071, 50.0, 60.0))]
+
+
+def run_sweep_arm(args):
+    """BASELINE.json configs[3]: 16 (alpha, V0, k) sets over the pyridine grid -- es once, one sr per distinct alpha (4), 16
+    relax runs.  N = 1: the sweep captured in CUDA graphs (dbspm_b200.sweep.SweepGraph) and replayed; the eager form is timed
+    beside it.  N > 1: the sets dealt over the ranks (sweep._sweep_sharded: es broadcast, gather of the relax results)."""
+    import torch
+    import torch.distributed as dist
+
+    from dbspm_b200 import interactions as ops
+    from dbspm_b200 import parallel, synth, sweep
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    rank, world, dev = parallel.init_from_env()
+    cfg = synth.CONFIGS["pyridine"]
+    nx, ny, nz = cfg.shape
+    N, z_lo, z_hi, nz_relax = nx * ny * nz, 76, 130, 24
+    dr = np.array(cfg.cell) / np.array(cfg.shape)
+    rhoS, potS, atoms = synth.make_sample(cfg, dev)
+    rhoT, nrhoT = synth.make_tip(cfg, dev, "noisy")
+    vdw = synth.make_vdw_window(cfg, atoms, (nx, ny, z_hi - z_lo), 2.7, dev)
+    npos = nx * ny * nz_relax * len(SWEEP_SETS)
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True); e.record(); return e
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def eager():
+        return sweep.fdbm_sweep(rhoS, potS, rhoT, nrhoT, dr, (z_lo, z_hi), nz_relax, SWEEP_SETS, cfg.rpivot, vdw=vdw)
+
+    for _ in range(max(args.warmup, 1)):
+        eager()
+    barrier()
+    ts = []
+    for _ in range(args.steps):
+        a = ev(); out = eager(); b = ev(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    t = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_eager = float(t.item())
+    line = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    if world == 1:
+        plan = sweep.SweepGraph(rhoS, potS, rhoT, nrhoT, dr, (z_lo, z_hi), nz_relax, SWEEP_SETS, cfg.rpivot, vdw=vdw)
+        for _ in range(max(args.warmup, 3)):
+            plan.run()
+        torch.cuda.synchronize()
+        # same bits as the eager sweep
+        same = all(torch.equal(plan.relax[i]["E"], out["relax"][i]["E"]) for i in range(len(SWEEP_SETS))) and torch.equal(plan.es, out["es"])
+        tc, tr = [], []
+        with ClockSampler(dev.index) as clk:
+            for _ in range(args.steps):
+                a = ev(); plan.run_corr(); b = ev(); plan.run_relax(); c = ev(); torch.cuda.synchronize()
+                tc.append(a.elapsed_time(b)); tr.append(b.elapsed_time(c))
+        t_corr, t_relax = float(np.mean(tc)), float(np.mean(tr))
+        # end to end: pinned host inputs in, every set's E and tip positions out, inside the timed region
+        hosts = [torch.empty(x.shape, dtype=torch.float64).pin_memory().copy_(x) for x in (rhoS, potS, rhoT, nrhoT)]
+        outs_h = torch.empty((len(SWEEP_SETS), 4, nx, ny, nz_relax), dtype=torch.float64).pin_memory()
+        te = []
+        for it in range(args.steps + 1):
+            a = ev()
+            for d, h in zip(plan.inputs, hosts):
+                d.copy_(h, non_blocking=True)
+            plan.run()
+            for i, r in enumerate(plan.relax):
+                for q, key in enumerate(("E", "tip_x", "tip_y", "tip_z")):
+                    outs_h[i, q].copy_(r[key], non_blocking=True)
+            b = ev(); torch.cuda.synchronize()
+            if it:
+                te.append(a.elapsed_time(b))
+        peak, peak_src = measured_peak()
+        balg = 8 * (2 * N + nx * ny * (z_hi - z_lo))
+        line.update(value=5 * N / (t_corr * 1e-3), ms_per_step=t_corr + t_relax,
+                    relax={"value": npos / (t_relax * 1e-3), "unit": "tip positions/s", "ms": t_relax, "sets": len(SWEEP_SETS)},
+                    sweep={"ms_correlations_es_plus_4_sr": t_corr, "ms_16_relax": t_relax, "ms_eager_whole_sweep": t_eager,
+                           "graph_equals_eager_bit_for_bit": bool(same),
+                           "note": "two CUDA graphs (5 correlations = 25 launches | 16 x (3 accumulate, re-layout, relax, sph2cart) = 96 "
+                                   "launches on 4 forked streams), replayed; eager = the same calls issued from Python"},
+                    roofline={"bound": "hbm", "achieved": 5 * balg / (t_corr * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": 5 * balg / (t_corr * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                              "note": "five pyridine-sized correlations (164 MB algorithmic each) are launch-latency sized: 25 launches of ~0.1 ms"},
+                    e2e={"value": 5 * N / (float(np.mean(te)) * 1e-3), "unit": UNIT, "ms_whole_sweep": float(np.mean(te)),
+                         "h2d_bytes_per_step": 4 * 8 * N, "d2h_bytes_per_step": int(outs_h.numel()) * 8},
+                    gpu_launches=(25 + 96) * args.steps, clocks=clk.summary(),
+                    config={"workload": "fdbmfit-style batch sweep (BASELINE.json configs[3]): 16 (alpha, V0, k) sets over the synthetic "
+                                        "pyridine grid 196x196x240, window 54 planes, relax 196x196x24 per set", "sets": SWEEP_SETS})
+    else:
+        line.update(value=None, ms_per_step=t_eager,
+                    relax={"value": npos / (t_eager * 1e-3), "unit": "tip positions/s (whole sweep time, correlations included)"},
+                    sweep={"ms_eager_whole_sweep": t_eager, "assignment": parallel.sweep_assignment(SWEEP_SETS, world),
+                           "note": "sets dealt over the ranks by alpha (a rank computes the sr grids of its own alphas), es on rank 0 + "
+                                   "broadcast, one gather of the stacked relax results"},
+                    gpu_launches=None,
+                    config={"workload": "fdbmfit-style batch sweep (BASELINE.json configs[3]), sharded over %d ranks" % world})
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 WORKLOAD_DESC = {
     "large_slab": "synthetic large slab 1024x1024x256 (BASELINE.json configs[4]), window 54 planes, relax 1024x1024x24",
     "tma_cu111": "synthetic 384x384x160 (BASELINE.json configs[2]), window 54 planes, relax 384x384x24",
     "pyridine": "synthetic pyridine-sized 196x196x240 (BASELINE.json configs[0] shape), window 54, relax 196x196x24",
     "triangulene": "synthetic triangulene-sized 240x320x240 (BASELINE.json configs[1] shape)",
+    "sweep16": "fdbmfit-style batch sweep: 16 (alpha, V0, k) sets over the pyridine grid (BASELINE.json configs[3])",
 }
 SKIP = {"x_fwd": 1 << 8, "y_fwd": 1 << 9, "z_fused": 1 << 10, "y_inv": 1 << 11, "x_inv": 1 << 12}
 
@@ -776,7 +883,11 @@ def main():
     ap.add_argument("--no-cufft", action="store_true", help="skip the cuFFT (torch.fft) comparator")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload == "sweep16":
+            args.workload = "pyridine"
         return run_reference_arm(args)
+    if args.workload == "sweep16":
+        return run_sweep_arm(args)
     return run_gpu_arm(args)
 
 

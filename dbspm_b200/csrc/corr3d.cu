@@ -356,9 +356,10 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     P.use_pow = use_pow; P.narrays = narrays;
     P.n = n; P.inner = inner; P.outer = outer;
     // path picked per shape: the TMA-fed persistent kernel wins where a ring of three 8-line tiles fits
-    // (256 <= n <= 576: measured 27 % faster at n = 384); the register-staged kernel wins at n = 1024
-    // (4-line tiles, FP64/shared-memory bound) and ties below 256
-    const bool tma_auto = n >= 256 && axis3_config(n, inner) == 3;
+    // (192 <= n <= 576; measured on B200 after its tile accesses became real LDS/STS: es 0.346 against 0.374 ms at
+    // 196x196x240, x pass 0.155 against 0.189 ms at n = 240, 0.186 against 0.228 ms at n = 384); the register-staged
+    // kernel wins at n = 1024 (4-line tiles: 2.50 against 3.31 ms)
+    const bool tma_auto = n >= 192 && axis3_config(n, inner) == 3;
     P.gather = 0;
     P.in_map = P.out_map = nullptr;
     P.in_ostride = P.out_ostride = (long long)n * inner;

@@ -12,31 +12,67 @@ from . import interactions as ops
 from . import parallel
 
 
-def fdbm_sweep(rhoS, potS, rhoT, nrhoT, dr, z_window, nz_relax, param_sets, rpivot, vdw=None, dR=None,
-               keep_static=False, streams=4):
-    """param_sets: iterable of (alpha, V0, kappa).  Inputs: CUDA tensors (or numpy, uploaded once).
-    Returns {"es": window, "sr": {alpha: window}, "relax": [dict per set]} with CUDA tensors.
-    streams: how many CUDA streams the independent relax runs are spread over (1 = serial).
+class SweepGraph:
+    """The whole sweep captured in two CUDA graphs (correlations | static + relax of every set) and replayed.
 
-    Under torchrun (torch.distributed initialised, one process per GPU) the sets are dealt over the
-    ranks (parallel.sweep_assignment); es is computed on rank 0 and broadcast, every rank computes the
-    sr grids of its own alphas, and rank 0 returns all relax results in the order of `param_sets`
-    (the other ranks return only their own sets, `None` elsewhere)."""
-    dev = rhoS.device if isinstance(rhoS, torch.Tensor) and rhoS.is_cuda else ops._device()
-    A, P, T, NT = (ops._to_dev(a, dev) for a in (rhoS, potS, rhoT, nrhoT))
+    One pyridine-sized correlation is five launches of ~0.1 ms and a relax of 38 416 columns fills a third of the GPU: the
+    sweep is launch- and host-bound (about 120 kernel launches through ctypes + torch allocations per sweep).  Capturing it
+    once removes the host from the loop; the relax runs of the sets keep their fork/join over `streams` side streams inside
+    the graph, so independent sets still overlap.  Inputs are read from the tensors given here (refresh them in place with
+    .copy_() between replays); parameters (alpha, V0, kappa) are baked into the captured launches.
+
+        plan = SweepGraph(rhoS, potS, rhoT, nrhoT, dr, (76, 130), 24, sets, 3.02, vdw=vdw)
+        out = plan.run()          # {"es", "sr", "relax"}: the same tensors every replay
+    """
+
+    def __init__(self, rhoS, potS, rhoT, nrhoT, dr, z_window, nz_relax, param_sets, rpivot, vdw=None, dR=None, streams=4):
+        self.args = dict(dr=dr, z_window=z_window, nz_relax=nz_relax, param_sets=list(param_sets), rpivot=rpivot, dR=dR, streams=streams)
+        dev = rhoS.device
+        self.inputs = tuple(ops._to_dev(a, dev) for a in (rhoS, potS, rhoT, nrhoT))
+        self.vdw = ops._to_dev(vdw, dev) if vdw is not None else None
+        self.dev = dev
+        # eager warm-up on a side stream: FFT plans, function attributes and the allocator's pools exist before the capture
+        warm = torch.cuda.Stream(device=dev)
+        warm.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(warm):
+            _corr_part(*self.inputs, dr, z_window, self.args["param_sets"])
+            fdbm_sweep(*self.inputs, vdw=self.vdw, keep_static=False, _sync=False, **self.args)
+        torch.cuda.current_stream(dev).wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        before = set(ops._WS_CACHE)
+        self.g_corr, self.g_relax = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_corr):
+            self.es, self.sr = _corr_part(*self.inputs, dr, z_window, self.args["param_sets"])
+        with torch.cuda.graph(self.g_relax, pool=self.g_corr.pool()):
+            self.relax = _relax_part(self.es, self.sr, self.vdw, dr, nz_relax, self.args["param_sets"], rpivot, dR, streams, False, dev)
+        # workspaces allocated during capture live in the graphs' pool: keep them here, out of the eager cache
+        self._ws = [ops._WS_CACHE.pop(k) for k in list(ops._WS_CACHE) if k not in before]
+
+    def run_corr(self):
+        self.g_corr.replay()
+
+    def run_relax(self):
+        self.g_relax.replay()
+
+    def run(self):
+        self.g_corr.replay()
+        self.g_relax.replay()
+        return {"es": self.es, "sr": self.sr, "relax": self.relax}
+
+
+def _corr_part(A, P, T, NT, dr, z_window, param_sets):
     z_lo, z_hi = z_window
-    param_sets = list(param_sets)
-    rank, world = parallel._world()
-    if world > 1:
-        return _sweep_sharded(A, P, T, NT, dr, z_lo, z_hi, nz_relax, param_sets, rpivot, vdw, dR, dev, rank, world)
     es = ops.density_overlap_window(P, NT, dr, z_lo, z_hi)
-    vd = ops._to_dev(vdw, dev) if vdw is not None else None
     sr = {}
     for alpha, _, _ in param_sets:
         a = float(alpha)
         if a not in sr:
             sr[a] = ops.density_overlap_window(A, T, dr, z_lo, z_hi, a, a)
-    # The relax of a small scan grid does not fill the GPU (pyridine: 300 blocks for 592 resident slots)
+    return es, sr
+
+
+def _relax_part(es, sr, vd, dr, nz_relax, param_sets, rpivot, dR, streams, keep_static, dev):
+    # The relax of a small scan grid does not fill the GPU (pyridine: 1200 one-warp blocks for 2368 resident slots)
     # and the sets are independent: run them on a few streams so that their kernels overlap.
     main = torch.cuda.current_stream(dev)
     nstreams = max(1, min(int(streams), len(param_sets)))
@@ -56,7 +92,30 @@ def fdbm_sweep(rhoS, potS, rhoT, nrhoT, dr, z_window, nz_relax, param_sets, rpiv
         out.append(r)
     for st in side:
         main.wait_stream(st)
-    if nstreams > 1:
+    return out
+
+
+def fdbm_sweep(rhoS, potS, rhoT, nrhoT, dr, z_window, nz_relax, param_sets, rpivot, vdw=None, dR=None,
+               keep_static=False, streams=4, _sync=True):
+    """param_sets: iterable of (alpha, V0, kappa).  Inputs: CUDA tensors (or numpy, uploaded once).
+    Returns {"es": window, "sr": {alpha: window}, "relax": [dict per set]} with CUDA tensors.
+    streams: how many CUDA streams the independent relax runs are spread over (1 = serial).
+
+    Under torchrun (torch.distributed initialised, one process per GPU) the sets are dealt over the
+    ranks (parallel.sweep_assignment); es is computed on rank 0 and broadcast, every rank computes the
+    sr grids of its own alphas, and rank 0 returns all relax results in the order of `param_sets`
+    (the other ranks return only their own sets, `None` elsewhere)."""
+    dev = rhoS.device if isinstance(rhoS, torch.Tensor) and rhoS.is_cuda else ops._device()
+    A, P, T, NT = (ops._to_dev(a, dev) for a in (rhoS, potS, rhoT, nrhoT))
+    z_lo, z_hi = z_window
+    param_sets = list(param_sets)
+    rank, world = parallel._world()
+    if world > 1:
+        return _sweep_sharded(A, P, T, NT, dr, z_lo, z_hi, nz_relax, param_sets, rpivot, vdw, dR, dev, rank, world)
+    es, sr = _corr_part(A, P, T, NT, dr, (z_lo, z_hi), param_sets)
+    vd = ops._to_dev(vdw, dev) if vdw is not None else None
+    out = _relax_part(es, sr, vd, dr, nz_relax, param_sets, rpivot, dR, streams, keep_static, dev)
+    if _sync and min(int(streams), len(param_sets)) > 1:
         torch.cuda.synchronize(dev)     # results were allocated on side streams: make them safe for any consumer
     return {"es": es, "sr": sr, "relax": out}
 
@@ -70,14 +129,19 @@ def _sweep_sharded(A, P, T, NT, dr, z_lo, z_hi, nz_relax, param_sets, rpivot, vd
     parallel.broadcast_(es)
     vd = ops._to_dev(vdw, dev) if vdw is not None else None
     assignment = parallel.sweep_assignment(param_sets, world)
-    sr, mine = {}, []
-    for i in assignment[rank]:
-        alpha, V0, kappa = param_sets[i]
+    my_sets = [param_sets[i] for i in assignment[rank]]
+    sr = {}
+    for alpha, _, _ in my_sets:
         a = float(alpha)
         if a not in sr:
             sr[a] = ops.density_overlap_window(A, T, dr, z_lo, z_hi, a, a)
-        comps = [(sr[a], float(V0)), (es, 1.0)] + ([(vd, 1.0)] if vd is not None else [])
-        mine.append(ops.relax_grid(ops.build_static(comps), float(kappa), rpivot, dr, nz_relax, dR=dR))
+    # the rank's own sets overlap on side streams like the single-GPU sweep (a pyridine-sized relax fills half a GPU)
+    mine = _relax_part(es, sr, vd, dr, nz_relax, my_sets, rpivot, dR, 4, False, dev) if my_sets else []
+    if len(my_sets) > 1:
+        torch.cuda.synchronize(dev)
+    for r in mine:
+        for key in ("alpha", "V", "kappa"):
+            r.pop(key, None)
     gathered = parallel.gather_sweep(mine, assignment)
     if rank == 0:
         for i, r in enumerate(gathered):

@@ -50,7 +50,7 @@ extern "C" {
 #define DBSPM_CORR_USE_TMA    (1 << 2)   /* force the TMA-fed persistent axis pass (tensor-map load, digit-reversing
                                             tensor-map store, two consumer groups + producer warp) */
 #define DBSPM_CORR_NO_TMA     (1 << 3)   /* force the register-staged axis pass.  Default: picked per axis length --
-                                            TMA for 256 <= n <= 576 (27 % faster at n = 384 on B200), register-staged
+                                            TMA for 192 <= n <= 576 (8-20 % faster on B200), register-staged
                                             otherwise (n = 1024 is FP64/shared-memory bound with 4-line tiles) */
 #define DBSPM_CORR_PEER_NARROW (1 << 4)  /* fused exchange: keep the 4-line tiles of the local pass (64-byte remote stores; A/B timing) */
 #define DBSPM_CORR_NO_PREFETCH (1 << 5)  /* no L2 prefetch of the next tile / pair group (A/B timing) */

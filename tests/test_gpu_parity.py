@@ -872,6 +872,35 @@ def test_batched_parameter_sweep(ops):
         assert (dev_pos > 1e-6).mean() < 2e-2, (dev_pos > 1e-6).mean()
 
 
+def test_sweep_cuda_graph_equals_eager(ops):
+    """configs[3] captured in CUDA graphs (sweep.SweepGraph): replays give the bits of the eager sweep, also after the
+    inputs were refreshed in place."""
+    from dbspm_b200 import synth
+    from dbspm_b200.sweep import SweepGraph, fdbm_sweep
+    cfg = synth.CONFIGS["tiny"]
+    dev = torch.device("cuda", 0)
+    rhoS, potS, atoms = synth.make_sample(cfg, dev)
+    rhoT, nrhoT = synth.make_tip(cfg, dev, "noisy")
+    dr = np.array(cfg.cell) / np.array(cfg.shape)
+    sets = [(1.0, 0.4, 0.2), (1.08, 0.4, 0.2), (1.08, 0.6, 0.24), (1.0, 0.6, 0.24), (1.12, 0.5, 0.2)]
+    eager = fdbm_sweep(rhoS, potS, rhoT, nrhoT, dr, (24, 32), 6, sets, cfg.rpivot)
+    plan = SweepGraph(rhoS.clone(), potS.clone(), rhoT.clone(), nrhoT.clone(), dr, (24, 32), 6, sets, cfg.rpivot)
+    for rep in range(3):
+        out = plan.run()
+        torch.cuda.synchronize()
+        assert torch.equal(out["es"], eager["es"]) and sorted(out["sr"]) == sorted(eager["sr"])
+        for a in eager["sr"]:
+            assert torch.equal(out["sr"][a], eager["sr"][a])
+        for r, e in zip(out["relax"], eager["relax"]):
+            assert torch.equal(r["E"], e["E"]) and torch.equal(r["tip_z"], e["tip_z"])
+    # new sample in place -> replay -> equals the eager sweep of the new sample
+    plan.inputs[0].mul_(1.1)
+    out = plan.run()
+    torch.cuda.synchronize()
+    eager2 = fdbm_sweep(rhoS * 1.1, potS, rhoT, nrhoT, dr, (24, 32), 6, sets, cfg.rpivot)
+    assert torch.equal(out["relax"][1]["E"], eager2["relax"][1]["E"]) and not torch.equal(out["relax"][1]["E"], eager["relax"][1]["E"])
+
+
 # ------------------------------------------------------------------------------------ compact tip
 @pytest.mark.parametrize("name", ["pyridine", "tma_cu111"])
 def test_compact_tip_takes_pruned_path_and_matches_full(ops, name):
