@@ -18,6 +18,9 @@
 #ifndef AXIS2_MIN_BLOCKS
 #define AXIS2_MIN_BLOCKS 2
 #endif
+#ifndef AXIS_PLAN_MAXR
+#define AXIS_PLAN_MAXR 16   /* power-of-two radix cap of the axis-pass plans (experiment: 8 with three resident CTAs) */
+#endif
 
 template <int D>
 __global__ void __launch_bounds__(DBSPM_THREADS) axis_pass_kernel(const __grid_constant__ AxisParams P)
@@ -40,6 +43,21 @@ __global__ void __launch_bounds__(512, 1) axis_pass2w_kernel(const __grid_consta
 {
     extern __shared__ __align__(16) unsigned char smem[];
     axis_pass_body_v2<D>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
+}
+
+// persistent, software-pipelined variants (axis_pass_body_v2s): blockIdx.x walks the tiles with stride gridDim.x
+template <int D>
+__global__ void __launch_bounds__(AXIS2_THREADS, AXIS2_MIN_BLOCKS) axis_pass2s_kernel(const __grid_constant__ AxisParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    axis_pass_body_v2s<D>(P, smem, (long long)blockIdx.x, (long long)gridDim.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
+}
+
+template <int D>
+__global__ void __launch_bounds__(512, 1) axis_pass2sw_kernel(const __grid_constant__ AxisParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    axis_pass_body_v2s<D>(P, smem, (long long)blockIdx.x, (long long)gridDim.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
 }
 
 // row-mapped variant (distributed correlation): rows of the transform axis are read / written through a table
@@ -348,7 +366,7 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
                        cudaStream_t st, int flags, const GatherSpec *g = nullptr, const AxisMap *mp = nullptr)
 {
     DevPlan *pl = nullptr;
-    int rc = get_plan(n, st, &pl);
+    int rc = get_plan(n, st, &pl, AXIS_PLAN_MAXR);
     if (rc) return rc;
     AxisParams P;
     P.in[0] = in0; P.in[1] = in1; P.out[0] = out0; P.out[1] = out1;
@@ -393,6 +411,9 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     P.tw_smem = 0;
     size_t smem;
     bool wide = false;
+    // persistent software-pipelined blocks (opt-in, DBSPM_CORR_PIPE: measured slower, see the header) for the plain passes
+    // with more tiles than resident CTAs
+    const bool pipe_off = !(flags & DBSPM_CORR_PIPE) || g || mp || !axis2s_ok(pl->host.dev);
     if (P.v2) {
         axis2_config(n, inner, P.plan.nstages, &P.tshift, &P.tw_smem);
         smem = axis2_smem_bytes(n, P.tshift, P.plan.nstages, P.tw_smem);
@@ -405,6 +426,7 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
         // 4.21 ms (2 x 256) against 4.87 ms (1 x 512).
         else if (!mp && outer == 1 && P.tshift == 2 && inner >= 65536 && P.plan.nstages > 1 &&
                  (!(use_pow && (alpha0 != 1.0 || alpha1 != 1.0)) || (flags & DBSPM_CORR_POW_WIDE)) &&
+                 (pipe_off || (flags & DBSPM_CORR_PIPE_WIDE)) &&
                  axis2_smem_bytes(n, 3, P.plan.nstages, 0) <= 200 * 1024) {
             wide = true;
             P.tshift = 3; P.tw_smem = 0;
@@ -453,6 +475,16 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     } else if (P.v2 && mp) {
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2m_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         axis_pass2m_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), AXIS2_THREADS, smem, st>>>(P);
+    } else if (P.v2 && !pipe_off && nblocks * narrays >= 4LL * 148 * (wide ? 1 : AXIS2_MIN_BLOCKS)) {
+        const int per_sm = wide ? 1 : AXIS2_MIN_BLOCKS;
+        const unsigned gx = (unsigned)((148 * per_sm + narrays - 1) / narrays);
+        if (wide) {
+            DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2sw_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            axis_pass2sw_kernel<D><<<dim3(gx, (unsigned)narrays), 512, smem, st>>>(P);
+        } else {
+            DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2s_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            axis_pass2s_kernel<D><<<dim3(gx, (unsigned)narrays), AXIS2_THREADS, smem, st>>>(P);
+        }
     } else if (P.v2 && wide) {
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2w_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         axis_pass2w_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), 512, smem, st>>>(P);

@@ -14,6 +14,9 @@
 #include <string.h>
 #include "fft_core.h"
 
+#ifndef AXIS2_SWITCH_MAXR
+#define AXIS2_SWITCH_MAXR 16   /* largest radix instantiated in the one-shot axis pass (experiment builds: 8) */
+#endif
 #ifndef AXIS2_TILE_BUDGET
 #define AXIS2_TILE_BUDGET (220 * 1024 / 3)   /* shared-memory bytes per CTA the axis-pass tile may use */
 #endif
@@ -521,7 +524,7 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
     // one slab per x of the rank's x-slab)
     const size_t gbase = P.gather ? (size_t)o * n * (size_t)P.g_src_inner : 0;
 #define CALL_(R) axis2_first<D, R, MAP>(P, s, tw, gin, gout, tcount, do_pow, alpha, ptab, which, i0, gbase, tid, nthr)
-    DBSPM_FAST_RADIX_SWITCH(pl.radix[0], CALL_)
+    DBSPM_RADIX_SWITCH_MAX(pl.radix[0], CALL_, AXIS2_SWITCH_MAXR)
 #undef CALL_
     if (pl.nstages == 1) return;
     BLOCK_SYNC();
@@ -529,14 +532,166 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
     for (int st = 1; st + 1 < pl.nstages; ++st) {
         const int r = pl.radix[st];
 #define CALL_(R) fft_stage<R, D>(s, T, P.tshift, n, m, tw, tid, nthr)
-        DBSPM_FAST_RADIX_SWITCH(r, CALL_)
+        DBSPM_RADIX_SWITCH_MAX(r, CALL_, AXIS2_SWITCH_MAXR)
 #undef CALL_
         m /= r;
         BLOCK_SYNC();
     }
 #define CALL_(R) axis2_last<D, R, MAP>(P, s, gout, tcount, which, tid, nthr)
-    DBSPM_FAST_RADIX_SWITCH(pl.radix[pl.nstages - 1], CALL_)
+    DBSPM_RADIX_SWITCH_MAX(pl.radix[pl.nstages - 1], CALL_, AXIS2_SWITCH_MAXR)
 #undef CALL_
+}
+
+// ------------------------------------------------------------------------------------------
+// v2s: the register-first / register-last pass as a PERSISTENT, software-pipelined block.  A block walks over the tiles
+// b0, b0 + bstride, ...; as soon as the first stage of tile i has left the registers for shared memory, the rows of
+// tile i + 1 are requested (the same R independent 128-bit streaming loads per thread) and stay in flight while the
+// middle stages and the storing last stage of tile i run.  The one-shot body above exposes the whole HBM latency of a
+// tile at the start of every block (two resident CTAs per SM cannot hide it: ncu showed 45-55 % of DRAM peak with the
+// issue slots 30 % busy); here a CTA always has its next 64 KB on the way.  Same arithmetic in the same order as
+// axis_pass_body_v2 (bit-identical results).  Plain passes only (no row map, no z-range gather).
+// The register array has the largest radix; every index is a compile-time constant after unrolling.
+// ------------------------------------------------------------------------------------------
+HD void axis2s_tile(const AxisParams &P, long long b, int which, const cplx **gin, cplx **gout, int *tcount)
+{
+    const int T = 1 << P.tshift;
+    const long long o = b / P.tiles, tile = b - o * P.tiles, i0 = tile << P.tshift;
+    *tcount = (int)((P.inner - i0) < T ? (P.inner - i0) : T);
+    *gin = P.in[which] + (size_t)o * P.n * P.inner + i0;
+    *gout = P.out[which] + (size_t)o * P.n * P.inner + i0;
+}
+
+HD void axis2s_load(const cplx *src, size_t rstride, int R, bool have, cplx *v)
+{
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (k < R) v[k] = have ? ld_stream(src + (size_t)k * rstride) : cmake(0.0, 0.0);
+}
+
+// first stage of one item (t, j) whose R rows are already in v: power, butterfly, twiddles, store to the tile
+template <int D, int R>
+HD void axis2s_stage1(const AxisParams &P, cplx *s, const cplx *tw, cplx *v, bool have, bool do_pow, double alpha,
+                      const double *ptab, int which, int q, int j, int t, int tid)
+{
+    if (do_pow && have) {
+        if (ptab) {
+            const double plo = P.pow_lo[which], phi = P.pow_hi[which];
+#if defined(__CUDA_ARCH__)
+            const int pstride = POW_TAB_COPIES, pcopy = tid & (POW_TAB_COPIES - 1);
+#else
+            const int pstride = 1, pcopy = 0;
+#endif
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                v[k].x = (v[k].x >= plo && v[k].x <= phi) ? pow_fast_core(v[k].x, alpha, ptab, pstride, pcopy) : pow_cold(v[k].x, alpha);
+                v[k].y = (v[k].y >= plo && v[k].y <= phi) ? pow_fast_core(v[k].y, alpha, ptab, pstride, pcopy) : pow_cold(v[k].y, alpha);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) { v[k].x = pow_cold(v[k].x, alpha); v[k].y = pow_cold(v[k].y, alpha); }
+        }
+    }
+    bfly<R, D>(v);
+#pragma unroll
+    for (int k = 1; k < R; ++k) {
+        const cplx w = tw[j * k];
+        v[k] = D < 0 ? cmul(v[k], w) : cmulc(v[k], w);
+    }
+    cplx *dst = s + ((j << P.tshift) + t);
+#pragma unroll
+    for (int k = 0; k < R; ++k) dst[(k * q) << P.tshift] = v[k];
+}
+
+// The rows in flight occupy 4*R0 registers during the later stages, so those are instantiated for small radices only
+// (ptxas allocates for the largest butterfly instantiated, taken or not; with radix 16 in the last stage the in-flight
+// rows were spilled, i.e. waited for, at once).  1024 = 16*8*8, 512 = 16*8*4, 2048 = 16*16*8 (not eligible), ...
+#ifndef AXIS2S_MAXR_REST
+#define AXIS2S_MAXR_REST 8
+#endif
+HD bool axis2s_ok(const FftPlanDev &pl)
+{
+    if (!axis_v2_ok(pl) || pl.nstages < 2) return false;
+    for (int i = 1; i < pl.nstages; ++i)
+        if (pl.radix[i] > AXIS2S_MAXR_REST) return false;
+    return true;
+}
+
+template <int D>
+HD void axis_pass_body_v2s(const AxisParams &P, unsigned char *smem_raw, long long b0, long long bstride, int which, int tid, int nthr)
+{
+    const int n = P.n, T = 1 << P.tshift, tmask = T - 1;
+    const FftPlanDev &pl = P.plan;
+    cplx *twbuf = (cplx *)smem_raw;
+    cplx *s = P.tw_smem ? twbuf + n : twbuf;
+    const cplx *tw = P.tw_smem ? (const cplx *)twbuf : P.tw;
+    const double alpha = P.alpha[which];
+    const bool do_pow = P.use_pow && alpha != 1.0;
+    const long long nblk = P.outer * P.tiles;
+    const int R0 = pl.radix[0], q = n / R0, total = q << P.tshift;
+    const size_t rstride = (size_t)q * (size_t)P.inner;        // rows k*q of the first butterfly
+
+    const double *ptab = nullptr;
+    if (do_pow && P.pow_tab_off >= 0) {
+#if defined(__CUDA_ARCH__)
+        double *pt = (double *)(smem_raw + P.pow_tab_off);
+        for (int e = tid; e < DBSPM_POW_TABLE_LEN * POW_TAB_COPIES; e += nthr) pt[e] = dbspm_pow_table_d[e / POW_TAB_COPIES];
+        ptab = pt;
+#else
+        ptab = dbspm_pow_table_h;
+#endif
+    }
+    if (P.tw_smem)
+        for (int e = tid; e < n; e += nthr) twbuf[e] = ldg_c(P.tw + e);
+    BLOCK_SYNC();
+
+    // the item of the first stage this thread keeps in flight across tiles
+    const bool mine = tid < total;
+    const int t0 = tid & tmask, j0 = tid >> P.tshift;
+    cplx v[16];
+    const cplx *gin; cplx *gout; int tcount;
+    // (v is assigned unconditionally -- zeros when there is nothing to load -- so that it is dead between the first stage
+    // and the next request; a conditional assignment keeps 64 registers live through the whole loop and ptxas spills them)
+    {
+        const long long bb = b0 < nblk ? b0 : 0;
+        axis2s_tile(P, bb, which, &gin, &gout, &tcount);
+        axis2s_load(gin + (size_t)j0 * P.inner + t0, rstride, R0, b0 < nblk && mine && t0 < tcount, v);
+    }
+    for (long long b = b0; b < nblk; b += bstride) {
+        axis2s_tile(P, b, which, &gin, &gout, &tcount);
+        if (mine) {
+#define CALL_(R) axis2s_stage1<D, R>(P, s, tw, v, t0 < tcount, do_pow, alpha, ptab, which, q, j0, t0, tid)
+            DBSPM_FAST_RADIX_SWITCH(R0, CALL_)
+#undef CALL_
+        }
+        for (int idx = tid + nthr; idx < total; idx += nthr) {          // tiles with more items than threads
+            const int t = idx & tmask, j = idx >> P.tshift;
+            cplx u[16];
+            axis2s_load(gin + (size_t)j * P.inner + t, rstride, R0, t < tcount, u);
+#define CALL_(R) axis2s_stage1<D, R>(P, s, tw, u, t < tcount, do_pow, alpha, ptab, which, q, j, t, tid)
+            DBSPM_FAST_RADIX_SWITCH(R0, CALL_)
+#undef CALL_
+        }
+        BLOCK_SYNC();
+        {   // next tile's rows: in flight during the remaining stages of this one
+            const long long bn = b + bstride;
+            const cplx *gin2; cplx *gout2; int tc2;
+            axis2s_tile(P, bn < nblk ? bn : b, which, &gin2, &gout2, &tc2);
+            axis2s_load(gin2 + (size_t)j0 * P.inner + t0, rstride, R0, bn < nblk && mine && t0 < tc2, v);
+        }
+        int m = n / R0;
+        for (int st = 1; st + 1 < pl.nstages; ++st) {
+            const int r = pl.radix[st];
+#define CALL_(R) fft_stage<R, D>(s, T, P.tshift, n, m, tw, tid, nthr)
+            DBSPM_RADIX_SWITCH_MAX(r, CALL_, AXIS2S_MAXR_REST)
+#undef CALL_
+            m /= r;
+            BLOCK_SYNC();
+        }
+#define CALL_(R) axis2_last<D, R, 0>(P, s, gout, tcount, which, tid, nthr)
+        DBSPM_RADIX_SWITCH_MAX(pl.radix[pl.nstages - 1], CALL_, AXIS2S_MAXR_REST)
+#undef CALL_
+        BLOCK_SYNC();                       // the tile is overwritten by the next first stage
+    }
 }
 
 // ------------------------------------------------------------------------------------------

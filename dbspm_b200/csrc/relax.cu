@@ -25,10 +25,24 @@ __global__ void __launch_bounds__(256) relax_cart_kernel(const double *etp, doub
                     (long long)gridDim.x * blockDim.x);
 }
 
+#ifndef RELAX_FOOT_X_DEFAULT
+#define RELAX_FOOT_X_DEFAULT 8
+#endif
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(RELAX_THREADS, RELAX_MIN_BLOCKS) relax_kernel(const __grid_constant__ RelaxParams P, long long ncol)
 {
-    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (P.foot_x > 1) {
+        // warp w relaxes the foot_x x (32 / foot_x) patch of columns number w (patches in row-major order over the tile);
+        // lanes beyond a ragged edge of the tile idle
+        const int fy = 32 / P.foot_x, nj = P.j_hi - P.j_lo, ni = P.i_hi - P.i_lo;
+        const long long w = col >> 5;
+        const int lane = (int)(col & 31), pj = (nj + fy - 1) / fy;
+        const long long s = w / pj;
+        const int ci = (int)s * P.foot_x + lane / fy, cj = (int)(w - s * pj) * fy + lane % fy;
+        col = (ci < ni && cj < nj) ? (long long)ci * nj + cj : ncol;
+    }
     __shared__ double powell_sm[(RELAX_SMEM_STATE == 0 ? PS_COUNT : (RELAX_SMEM_STATE == 1 ? PS_P_0 : PS_TOTAL)) * RELAX_THREADS];       // Powell-level state, one column per thread
     relax_column_body<LAYOUT, RELAX_THREADS>(P, col, ncol, powell_sm, threadIdx.x);      // lanes past the end idle inside (warp barrier)
 }
@@ -240,7 +254,22 @@ static int relax_launch(const double *static_win, int nx, int ny, int nzc, int x
     P.out_etp = out_E_theta_phi; P.out_cart = out_cart; P.out_nfev = out_nfev;
     const long long ncol = (long long)(i_hi - i_lo) * (j_hi - j_lo);
     if (ncol == 0 || nz_relax == 0) return DBSPM_OK;
-    const long long blocks = (ncol + RELAX_THREADS - 1) / RELAX_THREADS;
+    // columns of a warp: 32 consecutive y (foot_x = 1) or a foot_x x (32 / foot_x) patch (relax_kernel)
+    // Measured on B200 with the y-quad layout (1024 x 1024 x 24 positions): 1 x 32 columns per warp 71.9 ms, 2 x 16 68.9, 4 x 8 66.9,
+    // 8 x 4 65.7, 16 x 2 70.0, 32 x 1 81.1 -- x-neighbours reuse each other's sectors in L1, but every x plane of a load is
+    // another 128-byte line, so the patch must stay wide enough in y to fill its lines.  The other layouts keep 1 x 32.
+    P.foot_x = 1;
+    if (workspace && workspace_bytes >= dbspm_relax_workspace_bytes_layout(nxs, ny, nzc, 2) && dbspm_relax_workspace_bytes_layout(nxs, ny, nzc, 2)) {
+        P.foot_x = RELAX_FOOT_X_DEFAULT;
+        while (P.foot_x > 1 && (P.foot_x > i_hi - i_lo || 32 / P.foot_x > j_hi - j_lo)) P.foot_x >>= 1;   // narrow tiles
+    }
+    if (const char *e = getenv("DBSPM_RELAX_FOOT_X")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) P.foot_x = v; }
+    long long blocks = (ncol + RELAX_THREADS - 1) / RELAX_THREADS;
+    if (P.foot_x > 1) {
+        const long long fy = 32 / P.foot_x;
+        const long long warps = (((long long)(i_hi - i_lo) + P.foot_x - 1) / P.foot_x) * (((long long)(j_hi - j_lo) + fy - 1) / fy);
+        blocks = (warps * 32 + RELAX_THREADS - 1) / RELAX_THREADS;
+    }
     DBSPM_REQUIRE(blocks < 2147483647LL, DBSPM_EUNSUPPORTED, "tile too large");
     // Heights per launch (default: the whole sweep in one launch).  A launch can also continue a sweep: it finds its warm
     // start in out_etp.  One launch per height keeps every resident warp on the same few z rows (L2-resident working set

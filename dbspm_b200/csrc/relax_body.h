@@ -31,6 +31,8 @@ struct RelaxParams {
                               // x-tile plus a halo of the lever length on both sides); x_base = 0, nx_local = nx: the whole window
     int nyp;                  // LAYOUT 1: row length ny + 3 (periodic halo: stored index t holds y = t - 1)
     int i_lo, i_hi, j_lo, j_hi;
+    int foot_x;               // lanes of a warp along x (1, 2, 4, 8, 16 or 32; the other 32/foot_x along y): which 32 columns a warp relaxes.
+                              // x-neighbouring lanes share 12 of their 16 stencil sectors in the y-quad layout (L1 hits / hit-on-miss)
     int nz_relax;
     int k_hi, k_lo;           // this launch sweeps the heights k_hi, k_hi - 1, ..., k_lo (whole sweep: nz_relax - 1 ... 0); the start
                               // point of height k_hi < nz_relax - 1 is the relaxed (theta, phi) of height k_hi + 1 in out_etp

@@ -66,6 +66,12 @@ extern "C" {
                                             butterfly (120 instead of 166 registers, one more shared-memory stage; A/B timing:
                                             2.67 against 2.75 ms at nz = 256 on B200 -- the kernel is not occupancy-bound) */
 
+#define DBSPM_CORR_PIPE       (1 << 14)  /* register-staged axis pass as persistent, software-pipelined blocks (next tile's rows requested
+                                            before the remaining stages of the current one).  A/B: measured SLOWER on B200 (x 3.84 against
+                                            2.68 ms, y 3.26 against 2.38 ms at n = 1024): within 128 registers ptxas spills the rows in flight,
+                                            i.e. waits for them at once; kept for the record, off by default */
+#define DBSPM_CORR_PIPE_WIDE  (1 << 15)  /* with DBSPM_CORR_PIPE: 8-line tiles / one CTA of 512 threads where the one-shot pass would pick them */
+
 /* library / build identification: "dbspm_b200 <version> sm_100a" */
 const char *dbspm_version(void);
 const char *dbspm_last_error(void);

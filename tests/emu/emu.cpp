@@ -68,6 +68,13 @@ static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, in
         P.g_src_inner = inner / P.g_dst_nzh * P.g_src_nzh;
         for (int w = 0; w < 2; ++w) { P.g_zp0[w] = g->z0[w] / 2; P.g_valid[w] = g->valid[w] / 2; }
     }
+    // 300 = persistent software-pipelined body (axis_pass_body_v2s), auto tile width; 301.. = forced tshift.  Falls back to the
+    // one-shot body where the launcher does (plan not eligible, row maps, z-range gather)
+    bool pipelined = false;
+    if (force_tshift >= 300 && force_tshift < 1000) {
+        pipelined = axis2s_ok(hp.dev) && !g && !mp;
+        force_tshift = force_tshift > 300 ? force_tshift - 301 : -1;
+    }
     if (force_tshift >= 200 && (!axis_v2_ok(hp.dev) || hp.dev.nstages > 3)) force_tshift = -1;   // launcher falls back too
     if (force_tshift >= 200) {
         // TMA-fed persistent body (axis_tma_body) with the two TMA operations emulated by copies;
@@ -103,6 +110,14 @@ static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, in
     P.tiles = (inner + (1LL << P.tshift) - 1) >> P.tshift;
     std::vector<unsigned char> smem(bytes + 64);
     unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
+    if (pipelined && P.v2) {
+        // three "persistent blocks" walk the tiles with stride 3; one thread each, so a tile has more items than
+        // threads and both the carried first item and the directly loaded ones are exercised.  In-place passes: a real
+        // block requests tile i + 1 before it stores tile i, and tiles are disjoint, so the serial order is faithful
+        for (int w = 0; w < narrays; ++w)
+            for (long long b = 0; b < 3; ++b) axis_pass_body_v2s<D>(P, sm, b, 3, w, 0, 1);
+        return 0;
+    }
     for (int w = 0; w < narrays; ++w)
         for (long long b = 0; b < outer * P.tiles; ++b) {
             if (P.v2 && mp && mp->npeers > 0) axis_pass_body_v2<D, 2>(P, sm, b, w, 0, 1);

@@ -66,10 +66,26 @@ def test_corr3d_edge_shapes_all_tile_widths(emu, shape, window):
     dr = np.array([0.1, 0.2, 0.3])
     ref = O.density_overlap_fft(a, b, dr)[:, :, window[0]:window[1]]
     # -1/0/1/2: register-first/last body with auto/forced tile width; 100+: the all-in-smem body;
-    # 200+: the TMA-fed persistent body (loads/stores emulated by copies)
-    for tshift in (-1, 0, 1, 2, 100, 101, 103, 200, 201, 203):
+    # 200+: the TMA-fed persistent body (loads/stores emulated by copies); 300+: the persistent software-pipelined body
+    for tshift in (-1, 0, 1, 2, 100, 101, 103, 200, 201, 203, 300, 301, 303):
         got = emu.corr3d(a, b, dr, *window, tshift=tshift)
         assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, window, tshift)
+
+
+@pytest.mark.parametrize("shape,window", [((64, 28, 8), (2, 7)), ((128, 32, 6), (0, 6)), ((20, 96, 10), (3, 4)), ((256, 6, 4), (1, 3))])
+def test_pipelined_axis_pass_is_bit_identical_to_the_one_shot_pass(emu, shape, window):
+    """axis_pass_body_v2s (persistent blocks, next tile's rows requested before the remaining stages of the current
+    one) does the arithmetic of axis_pass_body_v2 in the same order: same bits, with and without the fused power."""
+    rng = np.random.default_rng(sum(shape))
+    a, b = rng.random(shape) + 0.01, rng.random(shape) + 0.02
+    dr = np.array([0.1, 0.2, 0.3])
+    for alpha in (1.0, 1.08):
+        ref = O.density_overlap_fft(a ** alpha, b ** alpha, dr)[:, :, window[0]:window[1]]
+        for one_shot, piped in ((-1, 300), (0, 301), (2, 303)):
+            x = emu.corr3d(a, b, dr, *window, alpha0=alpha, alpha1=alpha, tshift=one_shot)
+            y = emu.corr3d(a, b, dr, *window, alpha0=alpha, alpha1=alpha, tshift=piped)
+            assert np.array_equal(x, y), (shape, alpha, piped)
+            assert np.abs(y - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
 @pytest.mark.parametrize("shape,window,G", [
