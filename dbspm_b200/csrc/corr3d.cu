@@ -45,19 +45,33 @@ __global__ void __launch_bounds__(512, 1) axis_pass2w_kernel(const __grid_consta
     axis_pass_body_v2<D>(P, smem, (long long)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
 }
 
-// persistent, software-pipelined variants (axis_pass_body_v2s): blockIdx.x walks the tiles with stride gridDim.x
-template <int D>
+// persistent, software-pipelined variants (axis_pass_body_v2s, one instantiation per plan shape): blockIdx.x walks the tiles
+// with stride gridDim.x
+template <int D, int R0, int RM, int RL, bool POW>
 __global__ void __launch_bounds__(AXIS2_THREADS, AXIS2_MIN_BLOCKS) axis_pass2s_kernel(const __grid_constant__ AxisParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    axis_pass_body_v2s<D>(P, smem, (long long)blockIdx.x, (long long)gridDim.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
+    axis_pass_body_v2s<D, R0, RM, RL, POW>(P, smem, (long long)blockIdx.x, (long long)gridDim.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
 }
 
-template <int D>
+template <int D, int R0, int RM, int RL, bool POW>
 __global__ void __launch_bounds__(512, 1) axis_pass2sw_kernel(const __grid_constant__ AxisParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    axis_pass_body_v2s<D>(P, smem, (long long)blockIdx.x, (long long)gridDim.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
+    axis_pass_body_v2s<D, R0, RM, RL, POW>(P, smem, (long long)blockIdx.x, (long long)gridDim.x, (int)blockIdx.y, (int)threadIdx.x, (int)blockDim.x);
+}
+
+template <int D, int R0, int RM, int RL, bool POW>
+static int launch_axis_pipelined(const AxisParams &P, unsigned gx, int narrays, bool wide, size_t smem, cudaStream_t st)
+{
+    if (wide) {
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2sw_kernel<D, R0, RM, RL, POW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        axis_pass2sw_kernel<D, R0, RM, RL, POW><<<dim3(gx, (unsigned)narrays), 512, smem, st>>>(P);
+    } else {
+        DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2s_kernel<D, R0, RM, RL, POW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        axis_pass2s_kernel<D, R0, RM, RL, POW><<<dim3(gx, (unsigned)narrays), AXIS2_THREADS, smem, st>>>(P);
+    }
+    return DBSPM_OK;
 }
 
 // row-mapped variant (distributed correlation): rows of the transform axis are read / written through a table
@@ -411,9 +425,10 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     P.tw_smem = 0;
     size_t smem;
     bool wide = false;
-    // persistent software-pipelined blocks (opt-in, DBSPM_CORR_PIPE: measured slower, see the header) for the plain passes
-    // with more tiles than resident CTAs
-    const bool pipe_off = !(flags & DBSPM_CORR_PIPE) || g || mp || !axis2s_ok(pl->host.dev);
+    // persistent software-pipelined blocks (axis_pass_body_v2s) for the plain passes; not with the power fused into the
+    // load (the pass is FP64-issue bound and measured slower pipelined), see DBSPM_CORR_NO_PIPE in the header
+    const bool powered = use_pow && (alpha0 != 1.0 || alpha1 != 1.0);
+    const bool pipe_off = (flags & DBSPM_CORR_NO_PIPE) || g || mp || powered || !axis2s_ok(pl->host.dev);
     if (P.v2) {
         axis2_config(n, inner, P.plan.nstages, &P.tshift, &P.tw_smem);
         smem = axis2_smem_bytes(n, P.tshift, P.plan.nstages, P.tw_smem);
@@ -426,7 +441,6 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
         // 4.21 ms (2 x 256) against 4.87 ms (1 x 512).
         else if (!mp && outer == 1 && P.tshift == 2 && inner >= 65536 && P.plan.nstages > 1 &&
                  (!(use_pow && (alpha0 != 1.0 || alpha1 != 1.0)) || (flags & DBSPM_CORR_POW_WIDE)) &&
-                 (pipe_off || (flags & DBSPM_CORR_PIPE_WIDE)) &&
                  axis2_smem_bytes(n, 3, P.plan.nstages, 0) <= 200 * 1024) {
             wide = true;
             P.tshift = 3; P.tw_smem = 0;
@@ -475,16 +489,17 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     } else if (P.v2 && mp) {
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2m_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         axis_pass2m_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), AXIS2_THREADS, smem, st>>>(P);
-    } else if (P.v2 && !pipe_off && nblocks * narrays >= 4LL * 148 * (wide ? 1 : AXIS2_MIN_BLOCKS)) {
+    } else if (P.v2 && !pipe_off && (outer > 1 || wide) && nblocks * narrays >= 4LL * 148 * (wide ? 1 : AXIS2_MIN_BLOCKS) &&
+               ((long long)(n / P.plan.radix[0]) << P.tshift) == (wide ? 512 : AXIS2_THREADS)) {
+        // exactly one first-stage item per thread: its rows travel to the next tile's first stage through cp.async slots + registers
         const int per_sm = wide ? 1 : AXIS2_MIN_BLOCKS;
+        P.stage_off = (int)align_up(smem, 16);
+        smem = (size_t)P.stage_off + 8 * (size_t)(wide ? 512 : AXIS2_THREADS) * sizeof(cplx);
         const unsigned gx = (unsigned)((148 * per_sm + narrays - 1) / narrays);
-        if (wide) {
-            DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2sw_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            axis_pass2sw_kernel<D><<<dim3(gx, (unsigned)narrays), 512, smem, st>>>(P);
-        } else {
-            DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2s_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            axis_pass2s_kernel<D><<<dim3(gx, (unsigned)narrays), AXIS2_THREADS, smem, st>>>(P);
-        }
+        // (the instantiation with the power exists in the CPU emulation only: on the device the powered pass stays one-shot)
+        if (axis2s_plan_is<16, 8, 8>(P.plan)) rc = launch_axis_pipelined<D, 16, 8, 8, false>(P, gx, narrays, wide, smem, st);
+        else rc = launch_axis_pipelined<D, 16, 8, 4, false>(P, gx, narrays, wide, smem, st);
+        if (rc) return rc;
     } else if (P.v2 && wide) {
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2w_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         axis_pass2w_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), 512, smem, st>>>(P);

@@ -72,6 +72,9 @@ struct AxisParams {
     // >= 0: byte offset in dynamic shared memory of the staged pow_fast table (powered first pass); < 0: pow_nonneg
     int pow_tab_off;
     double pow_lo[2], pow_hi[2];   // pow_fast_bounds(alpha[w])
+    // pipelined body (axis_pass_body_v2s): byte offset of the per-thread staging slots (8 x nthr x 16 bytes) of the rows that
+    // travel to the next first stage through cp.async instead of registers
+    int stage_off;
 };
 
 // ---- distributed correlation: slot order of a transform axis --------------------------------------
@@ -545,8 +548,8 @@ HD void axis_pass_body_v2(const AxisParams &P, unsigned char *smem_raw, long lon
 // ------------------------------------------------------------------------------------------
 // v2s: the register-first / register-last pass as a PERSISTENT, software-pipelined block.  A block walks over the tiles
 // b0, b0 + bstride, ...; as soon as the first stage of tile i has left the registers for shared memory, the rows of
-// tile i + 1 are requested (the same R independent 128-bit streaming loads per thread) and stay in flight while the
-// middle stages and the storing last stage of tile i run.  The one-shot body above exposes the whole HBM latency of a
+// tile i + 1 are requested (half of a thread's R rows as cp.async copies into its own shared-memory slots, half as 128-bit
+// streaming loads into registers) and stay in flight while the middle stages and the storing last stage of tile i run.  The one-shot body above exposes the whole HBM latency of a
 // tile at the start of every block (two resident CTAs per SM cannot hide it: ncu showed 45-55 % of DRAM peak with the
 // issue slots 30 % busy); here a CTA always has its next 64 KB on the way.  Same arithmetic in the same order as
 // axis_pass_body_v2 (bit-identical results).  Plain passes only (no row map, no z-range gather).
@@ -566,6 +569,49 @@ HD void axis2s_load(const cplx *src, size_t rstride, int R, bool have, cplx *v)
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         if (k < R) v[k] = have ? ld_stream(src + (size_t)k * rstride) : cmake(0.0, 0.0);
+}
+
+// Request of the carried item of the NEXT tile.  Rows 0..7 of the butterfly go through cp.async (16 bytes each, L2 ->
+// shared memory, no register) into the thread's own staging slots stg[k * nthr + tid]; rows 8..15 into the registers hi[].
+// 64 registers of rows in flight did not survive the later stages (ptxas spilled them, i.e. waited for them at once);
+// 32 do.  A thread only ever reads the slots it filled itself, so cp.async.wait_group is all the synchronisation needed.
+HD void axis2s_request(const cplx *src, size_t rstride, int R, bool have, cplx *stg, int tid, int nthr, cplx *hi)
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k < R) {
+            cplx *dst = stg + (k * nthr + tid);
+#if defined(__CUDA_ARCH__)
+            if (have) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (size_t)k * rstride) : "memory");
+            } else {
+                *dst = cmake(0.0, 0.0);
+            }
+#else
+            *dst = have ? src[(size_t)k * rstride] : cmake(0.0, 0.0);
+#endif
+        }
+    }
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (8 + k < R) hi[k] = have ? ld_stream(src + (size_t)(8 + k) * rstride) : cmake(0.0, 0.0);
+}
+
+HD void axis2s_collect(const cplx *stg, int R, int tid, int nthr, const cplx *hi, cplx *v)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < R) v[k] = stg[k * nthr + tid];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (8 + k < R) v[8 + k] = hi[k];
 }
 
 // first stage of one item (t, j) whose R rows are already in v: power, butterfly, twiddles, store to the tile
@@ -602,21 +648,21 @@ HD void axis2s_stage1(const AxisParams &P, cplx *s, const cplx *tw, cplx *v, boo
     for (int k = 0; k < R; ++k) dst[(k * q) << P.tshift] = v[k];
 }
 
-// The rows in flight occupy 4*R0 registers during the later stages, so those are instantiated for small radices only
-// (ptxas allocates for the largest butterfly instantiated, taken or not; with radix 16 in the last stage the in-flight
-// rows were spilled, i.e. waited for, at once).  1024 = 16*8*8, 512 = 16*8*4, 2048 = 16*16*8 (not eligible), ...
-#ifndef AXIS2S_MAXR_REST
-#define AXIS2S_MAXR_REST 8
-#endif
-HD bool axis2s_ok(const FftPlanDev &pl)
+// The body is compiled for ONE plan shape at a time -- first radix R0, middle stages of radix RM, last radix RL, power or
+// not -- because only a lean instruction stream keeps the rows in flight in registers: with the run-time radix
+// switches of the one-shot body around them ptxas spilled them right behind the loads.
+//   <16, 8, 8>: n = 128 (16*8), 1024 (16*8*8);  <16, 8, 4>: n = 64 (16*4), 512 (16*8*4)
+template <int R0, int RM, int RL>
+HD bool axis2s_plan_is(const FftPlanDev &pl)
 {
-    if (!axis_v2_ok(pl) || pl.nstages < 2) return false;
-    for (int i = 1; i < pl.nstages; ++i)
-        if (pl.radix[i] > AXIS2S_MAXR_REST) return false;
+    if (pl.nstages < 2 || pl.radix[0] != R0 || pl.radix[pl.nstages - 1] != RL) return false;
+    for (int i = 1; i + 1 < pl.nstages; ++i)
+        if (pl.radix[i] != RM) return false;
     return true;
 }
+HD bool axis2s_ok(const FftPlanDev &pl) { return axis2s_plan_is<16, 8, 8>(pl) || axis2s_plan_is<16, 8, 4>(pl); }
 
-template <int D>
+template <int D, int R0, int RM, int RL, bool POW>
 HD void axis_pass_body_v2s(const AxisParams &P, unsigned char *smem_raw, long long b0, long long bstride, int which, int tid, int nthr)
 {
     const int n = P.n, T = 1 << P.tshift, tmask = T - 1;
@@ -625,9 +671,9 @@ HD void axis_pass_body_v2s(const AxisParams &P, unsigned char *smem_raw, long lo
     cplx *s = P.tw_smem ? twbuf + n : twbuf;
     const cplx *tw = P.tw_smem ? (const cplx *)twbuf : P.tw;
     const double alpha = P.alpha[which];
-    const bool do_pow = P.use_pow && alpha != 1.0;
+    const bool do_pow = POW && P.use_pow && alpha != 1.0;
     const long long nblk = P.outer * P.tiles;
-    const int R0 = pl.radix[0], q = n / R0, total = q << P.tshift;
+    const int q = n / R0, total = q << P.tshift;
     const size_t rstride = (size_t)q * (size_t)P.inner;        // rows k*q of the first butterfly
 
     const double *ptab = nullptr;
@@ -647,49 +693,47 @@ HD void axis_pass_body_v2s(const AxisParams &P, unsigned char *smem_raw, long lo
     // the item of the first stage this thread keeps in flight across tiles
     const bool mine = tid < total;
     const int t0 = tid & tmask, j0 = tid >> P.tshift;
-    cplx v[16];
+    cplx *stg = (cplx *)(smem_raw + P.stage_off);
+    cplx hi[8];
     const cplx *gin; cplx *gout; int tcount;
-    // (v is assigned unconditionally -- zeros when there is nothing to load -- so that it is dead between the first stage
-    // and the next request; a conditional assignment keeps 64 registers live through the whole loop and ptxas spills them)
+    // (hi is assigned unconditionally -- zeros when there is nothing to load -- so that it is dead between the first stage
+    // and the next request; a conditional assignment keeps its registers live through the whole loop)
     {
         const long long bb = b0 < nblk ? b0 : 0;
         axis2s_tile(P, bb, which, &gin, &gout, &tcount);
-        axis2s_load(gin + (size_t)j0 * P.inner + t0, rstride, R0, b0 < nblk && mine && t0 < tcount, v);
+        axis2s_request(gin + (size_t)j0 * P.inner + t0, rstride, R0, b0 < nblk && mine && t0 < tcount, stg, tid, nthr, hi);
     }
     for (long long b = b0; b < nblk; b += bstride) {
         axis2s_tile(P, b, which, &gin, &gout, &tcount);
         if (mine) {
-#define CALL_(R) axis2s_stage1<D, R>(P, s, tw, v, t0 < tcount, do_pow, alpha, ptab, which, q, j0, t0, tid)
-            DBSPM_FAST_RADIX_SWITCH(R0, CALL_)
-#undef CALL_
+            cplx v[16];
+            axis2s_collect(stg, R0, tid, nthr, hi, v);
+            axis2s_stage1<D, R0>(P, s, tw, v, t0 < tcount, do_pow, alpha, ptab, which, q, j0, t0, tid);
         }
-        for (int idx = tid + nthr; idx < total; idx += nthr) {          // tiles with more items than threads
+#if !defined(__CUDA_ARCH__)
+        // CPU emulation only (one "thread" per block): the remaining items of the tile, loaded directly.  On the device the
+        // launcher guarantees one item per thread (total <= nthr)
+        for (int idx = tid + nthr; idx < total; idx += nthr) {
             const int t = idx & tmask, j = idx >> P.tshift;
             cplx u[16];
             axis2s_load(gin + (size_t)j * P.inner + t, rstride, R0, t < tcount, u);
-#define CALL_(R) axis2s_stage1<D, R>(P, s, tw, u, t < tcount, do_pow, alpha, ptab, which, q, j, t, tid)
-            DBSPM_FAST_RADIX_SWITCH(R0, CALL_)
-#undef CALL_
+            axis2s_stage1<D, R0>(P, s, tw, u, t < tcount, do_pow, alpha, ptab, which, q, j, t, tid);
         }
+#endif
         BLOCK_SYNC();
         {   // next tile's rows: in flight during the remaining stages of this one
             const long long bn = b + bstride;
             const cplx *gin2; cplx *gout2; int tc2;
             axis2s_tile(P, bn < nblk ? bn : b, which, &gin2, &gout2, &tc2);
-            axis2s_load(gin2 + (size_t)j0 * P.inner + t0, rstride, R0, bn < nblk && mine && t0 < tc2, v);
+            axis2s_request(gin2 + (size_t)j0 * P.inner + t0, rstride, R0, bn < nblk && mine && t0 < tc2, stg, tid, nthr, hi);
         }
         int m = n / R0;
         for (int st = 1; st + 1 < pl.nstages; ++st) {
-            const int r = pl.radix[st];
-#define CALL_(R) fft_stage<R, D>(s, T, P.tshift, n, m, tw, tid, nthr)
-            DBSPM_RADIX_SWITCH_MAX(r, CALL_, AXIS2S_MAXR_REST)
-#undef CALL_
-            m /= r;
+            fft_stage<RM, D>(s, T, P.tshift, n, m, tw, tid, nthr);
+            m /= RM;
             BLOCK_SYNC();
         }
-#define CALL_(R) axis2_last<D, R, 0>(P, s, gout, tcount, which, tid, nthr)
-        DBSPM_RADIX_SWITCH_MAX(pl.radix[pl.nstages - 1], CALL_, AXIS2S_MAXR_REST)
-#undef CALL_
+        axis2_last<D, RL, 0>(P, s, gout, tcount, which, tid, nthr);
         BLOCK_SYNC();                       // the tile is overwritten by the next first stage
     }
 }

@@ -32,17 +32,7 @@ __global__ void __launch_bounds__(256) relax_cart_kernel(const double *etp, doub
 template <int LAYOUT>
 __global__ void __launch_bounds__(RELAX_THREADS, RELAX_MIN_BLOCKS) relax_kernel(const __grid_constant__ RelaxParams P, long long ncol)
 {
-    long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (P.foot_x > 1) {
-        // warp w relaxes the foot_x x (32 / foot_x) patch of columns number w (patches in row-major order over the tile);
-        // lanes beyond a ragged edge of the tile idle
-        const int fy = 32 / P.foot_x, nj = P.j_hi - P.j_lo, ni = P.i_hi - P.i_lo;
-        const long long w = col >> 5;
-        const int lane = (int)(col & 31), pj = (nj + fy - 1) / fy;
-        const long long s = w / pj;
-        const int ci = (int)s * P.foot_x + lane / fy, cj = (int)(w - s * pj) * fy + lane % fy;
-        col = (ci < ni && cj < nj) ? (long long)ci * nj + cj : ncol;
-    }
+    const long long col = relax_patch_column(P, (long long)blockIdx.x * blockDim.x + threadIdx.x, ncol);
     __shared__ double powell_sm[(RELAX_SMEM_STATE == 0 ? PS_COUNT : (RELAX_SMEM_STATE == 1 ? PS_P_0 : PS_TOTAL)) * RELAX_THREADS];       // Powell-level state, one column per thread
     relax_column_body<LAYOUT, RELAX_THREADS>(P, col, ncol, powell_sm, threadIdx.x);      // lanes past the end idle inside (warp barrier)
 }
@@ -264,12 +254,7 @@ static int relax_launch(const double *static_win, int nx, int ny, int nzc, int x
         while (P.foot_x > 1 && (P.foot_x > i_hi - i_lo || 32 / P.foot_x > j_hi - j_lo)) P.foot_x >>= 1;   // narrow tiles
     }
     if (const char *e = getenv("DBSPM_RELAX_FOOT_X")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) P.foot_x = v; }
-    long long blocks = (ncol + RELAX_THREADS - 1) / RELAX_THREADS;
-    if (P.foot_x > 1) {
-        const long long fy = 32 / P.foot_x;
-        const long long warps = (((long long)(i_hi - i_lo) + P.foot_x - 1) / P.foot_x) * (((long long)(j_hi - j_lo) + fy - 1) / fy);
-        blocks = (warps * 32 + RELAX_THREADS - 1) / RELAX_THREADS;
-    }
+    const long long blocks = (relax_patch_threads(i_hi - i_lo, j_hi - j_lo, P.foot_x) + RELAX_THREADS - 1) / RELAX_THREADS;
     DBSPM_REQUIRE(blocks < 2147483647LL, DBSPM_EUNSUPPORTED, "tile too large");
     // Heights per launch (default: the whole sweep in one launch).  A launch can also continue a sweep: it finds its warm
     // start in out_etp.  One launch per height keeps every resident warp on the same few z rows (L2-resident working set

@@ -447,6 +447,30 @@ struct PowellRegs {
 #define RELAX_DRIFT 0
 #endif
 
+// ---- which column a thread relaxes ------------------------------------------------------------
+// foot_x = 1: thread g takes column g (a warp = 32 consecutive y).  foot_x > 1: warp w relaxes the foot_x x (32 / foot_x)
+// patch of columns number w (patches in row-major order over the tile), lane = dx * fy + dy; lanes beyond a ragged edge
+// of the tile idle (return ncol).  Column index = (i - i_lo) * nj + (j - j_lo), the row order of the outputs.
+HD long long relax_patch_column(const RelaxParams &P, long long g, long long ncol)
+{
+    if (P.foot_x <= 1) return g;
+    const int fy = 32 / P.foot_x, nj = P.j_hi - P.j_lo, ni = P.i_hi - P.i_lo;
+    const long long w = g >> 5;
+    const int lane = (int)(g & 31), pj = (nj + fy - 1) / fy;
+    const long long s = w / pj;
+    const long long ci = s * P.foot_x + lane / fy;
+    const int cj = (int)(w - s * pj) * fy + lane % fy;
+    return (ci < ni && cj < nj) ? ci * nj + cj : ncol;
+}
+
+// number of threads the patch order needs for a tile (a multiple of 32)
+HD long long relax_patch_threads(int ni, int nj, int foot_x)
+{
+    if (foot_x <= 1) return (long long)ni * nj;
+    const long long fy = 32 / foot_x;
+    return (((long long)ni + foot_x - 1) / foot_x) * (((long long)nj + fy - 1) / fy) * 32;
+}
+
 // ---- one lateral column: sweep z from the top with warm start ------------------------------
 // NTHR = threads per block (the stride of the shared-memory columns); sm = PS_TOTAL*NTHR doubles.
 template <int LAYOUT, int NTHR>

@@ -373,10 +373,20 @@ def relax_sharded(compute_tile, nx, device):
     if world == 1:
         return mine
     out = {}
+    sizes = [b - a for a, b in tiles]
     for key in sorted(mine):
-        parts = _gather_padded(mine[key].contiguous(), [b - a for a, b in tiles])
-        if rank == 0:
-            out[key] = torch.cat(parts, dim=0)
+        local = mine[key].contiguous()
+        if len(set(sizes)) == 1:
+            # equal tiles: rank 0 receives every tile straight into its rows of the result (no padded copies, no concatenation)
+            gl = None
+            if rank == 0:
+                out[key] = torch.empty((nx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+                gl = [out[key][a:b] for a, b in tiles]
+            dist.gather(local, gl, dst=0)
+        else:
+            parts = _gather_padded(local, sizes)
+            if rank == 0:
+                out[key] = torch.cat(parts, dim=0)
     return out if rank == 0 else None
 
 

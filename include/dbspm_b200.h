@@ -66,11 +66,12 @@ extern "C" {
                                             butterfly (120 instead of 166 registers, one more shared-memory stage; A/B timing:
                                             2.67 against 2.75 ms at nz = 256 on B200 -- the kernel is not occupancy-bound) */
 
-#define DBSPM_CORR_PIPE       (1 << 14)  /* register-staged axis pass as persistent, software-pipelined blocks (next tile's rows requested
-                                            before the remaining stages of the current one).  A/B: measured SLOWER on B200 (x 3.84 against
-                                            2.68 ms, y 3.26 against 2.38 ms at n = 1024): within 128 registers ptxas spills the rows in flight,
-                                            i.e. waits for them at once; kept for the record, off by default */
-#define DBSPM_CORR_PIPE_WIDE  (1 << 15)  /* with DBSPM_CORR_PIPE: 8-line tiles / one CTA of 512 threads where the one-shot pass would pick them */
+#define DBSPM_CORR_NO_PIPE    (1 << 14)  /* plain axis passes as one-shot blocks only.  Default: where the plan is 16*8*8 or 16*8*4 (n = 1024, 512,
+                                            128, 64) and the pass has many more tiles than resident CTAs, persistent blocks request the next
+                                            tile's rows (8 per thread through cp.async into the thread's own shared-memory slots, 8 into
+                                            registers) before the remaining stages of the current tile.  B200, n = 1024: y pass 2.39 -> 2.30 ms,
+                                            x pass on 8-line tiles 2.68 -> 2.42 ms; slower with 4-line tiles on the slowest axis (3.23 ms) and
+                                            with the power fused (4.28 against 3.90 ms), where the one-shot blocks stay */
 
 /* library / build identification: "dbspm_b200 <version> sm_100a" */
 const char *dbspm_version(void);

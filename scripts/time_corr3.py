@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from dbspm_b200 import interactions as ops, synth, _lib
 SKIP = {"xfwd": 1 << 8, "yfwd": 1 << 9, "z": 1 << 10, "yinv": 1 << 11, "xinv": 1 << 12}; ALL = sum(SKIP.values())
-PIPE, PIPE_WIDE = 1 << 14, 1 << 15
+NO_PIPE = 1 << 14
 def timeit(fn, reps=5, warm=2):
     for _ in range(warm): fn()
     torch.cuda.synchronize(); ts = []
@@ -21,7 +21,7 @@ for name in (sys.argv[1:] or ["large_slab"]):
     dr = np.array(cfg.cell) / np.array(cfg.shape)
     outs = {}
     for alpha in (1.0, 1.08):
-        for label, fl in (("nopipe", 0), ("pipe", PIPE), ("pipewide", PIPE | PIPE_WIDE)):
+        for label, fl in (("default", 0), ("nopipe", NO_PIPE)):
             out = torch.empty((nx, ny, 54), dtype=torch.float64, device=dev)
             f = lambda extra=0: ops.density_overlap_window(A, B, dr, 76, 130, alpha, alpha, out=out, flags=fl | extra)
             t = timeit(f)
@@ -31,5 +31,5 @@ for name in (sys.argv[1:] or ["large_slab"]):
                 line += f" {k} {timeit(lambda: f(ALL & ~bit)):.3f}"
             f()
             print(line, flush=True)
-        same = bool(torch.equal(outs[(alpha, "pipe")], outs[(alpha, "nopipe")]))
-        print(f"CORR3 {name} alpha={alpha} pipe == nopipe bitwise: {same}; pipewide == nopipe: {bool(torch.equal(outs[(alpha, 'pipewide')], outs[(alpha, 'nopipe')]))}", flush=True)
+        same = bool(torch.equal(outs[(alpha, "default")], outs[(alpha, "nopipe")]))
+        print(f"CORR3 {name} alpha={alpha} default == nopipe bitwise: {same}", flush=True)

@@ -182,6 +182,16 @@ class Emu:
             raise RuntimeError(f"emu_corr3d_direct_f64 -> {rc}")
         return out, int(rc)
 
+    def relax_patch_columns(self, ni, nj, foot_x):
+        f = self.L.emu_relax_patch_columns
+        f.restype = C.c_longlong
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_longlong]
+        cap = (ni + 32) * (nj + 32) * 2 + 64
+        cols = np.empty(cap, dtype=np.int64)
+        n = f(ni, nj, foot_x, cols.ctypes.data_as(C.POINTER(C.c_longlong)), cap)
+        assert n <= cap
+        return cols[:n]
+
     def tricubic(self, g, x, y, z):
         g = np.ascontiguousarray(g, dtype=np.float64)
         return self.L.emu_tricubic(self._p(g), *g.shape, x, y, z)

@@ -111,11 +111,17 @@ static int run_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1, in
     std::vector<unsigned char> smem(bytes + 64);
     unsigned char *sm = (unsigned char *)align_up((size_t)smem.data(), 16);
     if (pipelined && P.v2) {
+        P.stage_off = (int)align_up(bytes, 16);
+        std::vector<unsigned char> smem2(P.stage_off + 8 * sizeof(cplx) + 64);
+        sm = (unsigned char *)align_up((size_t)smem2.data(), 16);
         // three "persistent blocks" walk the tiles with stride 3; one thread each, so a tile has more items than
         // threads and both the carried first item and the directly loaded ones are exercised.  In-place passes: a real
         // block requests tile i + 1 before it stores tile i, and tiles are disjoint, so the serial order is faithful
         for (int w = 0; w < narrays; ++w)
-            for (long long b = 0; b < 3; ++b) axis_pass_body_v2s<D>(P, sm, b, 3, w, 0, 1);
+            for (long long b = 0; b < 3; ++b) {
+                if (axis2s_plan_is<16, 8, 8>(P.plan)) axis_pass_body_v2s<D, 16, 8, 8, true>(P, sm, b, 3, w, 0, 1);
+                else axis_pass_body_v2s<D, 16, 8, 4, true>(P, sm, b, 3, w, 0, 1);
+            }
         return 0;
     }
     for (int w = 0; w < narrays; ++w)
@@ -501,6 +507,16 @@ extern "C" double emu_tricubic(const double *g, int nx, int ny, int nz, double x
 {
     const double inv_n[3] = {1.0 / nx, 1.0 / ny, 1.0 / nz}, nd[3] = {(double)nx, (double)ny, (double)nz};
     return tricubic_eval<0>(g, nx, ny, nz, 0, nd, inv_n, x, y, z);
+}
+
+// the column each thread of the relax launch takes (relax_patch_column); returns the number of threads launched
+extern "C" long long emu_relax_patch_columns(int ni, int nj, int foot_x, long long *cols, long long cap)
+{
+    RelaxParams P;
+    P.i_lo = 0; P.i_hi = ni; P.j_lo = 0; P.j_hi = nj; P.foot_x = foot_x;
+    const long long ncol = (long long)ni * nj, nthr = relax_patch_threads(ni, nj, foot_x);
+    for (long long g = 0; g < nthr && g < cap; ++g) cols[g] = relax_patch_column(P, g, ncol);
+    return nthr;
 }
 
 // div_by(x, d, RN(1/d)) against x / d on random operands: returns the number of mismatching bit patterns

@@ -72,7 +72,7 @@ def test_corr3d_edge_shapes_all_tile_widths(emu, shape, window):
         assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, window, tshift)
 
 
-@pytest.mark.parametrize("shape,window", [((64, 28, 8), (2, 7)), ((128, 32, 6), (0, 6)), ((20, 96, 10), (3, 4)), ((256, 6, 4), (1, 3))])
+@pytest.mark.parametrize("shape,window", [((64, 128, 8), (2, 7)), ((128, 64, 6), (0, 6)), ((512, 3, 4), (1, 3)), ((1024, 2, 4), (0, 2)), ((20, 96, 10), (3, 4))])
 def test_pipelined_axis_pass_is_bit_identical_to_the_one_shot_pass(emu, shape, window):
     """axis_pass_body_v2s (persistent blocks, next tile's rows requested before the remaining stages of the current
     one) does the arithmetic of axis_pass_body_v2 in the same order: same bits, with and without the fused power."""
@@ -239,6 +239,28 @@ def test_odd_nz_takes_the_complex_path(emu, shape, window):
     for ts in (-1, 101, 200):
         got = emu.corr3d(a, b, dr, window[0], window[1], alpha0=1.08, tshift=ts)
         assert np.abs(got - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-300), (shape, ts)
+
+
+@pytest.mark.parametrize("ni,nj", [(1, 1), (8, 4), (70, 45), (3, 45), (70, 2), (33, 31), (128, 1024)])
+def test_relax_patch_order_covers_every_column_once(emu, ni, nj):
+    """relax_patch_column: whatever patch a warp relaxes (foot_x x 32/foot_x), every column of the tile is taken by exactly
+    one thread, idle lanes return ncol, a warp's columns lie in one patch, and foot_x = 1 is the identity."""
+    ncol = ni * nj
+    for fx in (1, 2, 4, 8, 16, 32):
+        cols = emu.relax_patch_columns(ni, nj, fx)
+        assert cols.size % 32 == 0 or fx == 1
+        taken = cols[cols < ncol]
+        assert taken.size == ncol and np.array_equal(np.sort(taken), np.arange(ncol)), (ni, nj, fx)
+        assert np.all(cols[cols >= ncol] == ncol)
+        if fx == 1:
+            assert np.array_equal(cols, np.arange(ncol))
+            continue
+        fy = 32 // fx
+        for w in range(0, cols.size, 32):
+            c = cols[w:w + 32]; c = c[c < ncol]
+            if c.size:
+                ci, cj = c // nj, c % nj
+                assert ci.max() - ci.min() < fx and cj.max() - cj.min() < fy and ci.min() % fx == 0 and cj.min() % fy == 0
 
 
 def test_tricubic_stencil_equals_oracle(emu, relax_golden):

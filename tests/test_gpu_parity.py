@@ -267,6 +267,30 @@ def test_relax_x_slab_mode_matches_whole_window(ops, relax_golden):
         ops.relax_grid(static[:60].contiguous(), 0.2, 3.02, dr, 24, tile=(10, 50, 0, ny), x_slab=(0, nx))
 
 
+def test_relax_warp_footprint_does_not_change_the_bits(ops, monkeypatch):
+    """Which 32 columns a warp relaxes (32 consecutive y, or an 8 x 4 / 32 x 1 / ... patch: DBSPM_RELAX_FOOT_X) only moves
+    work between lanes: every output is bit-identical, also on tiles whose edges cut through patches and on tiles
+    narrower than a patch (the launcher shrinks the patch)."""
+    from dbspm_b200 import synth
+    dev = torch.device("cuda", 0)
+    nx, ny, nzc = 70, 45, 54
+    static = synth.make_static_like((nx, ny, nzc), 5, dev)
+    dr = np.array([0.0765306, 0.0765306, 0.075])
+    keys = ("E", "theta", "phi", "tip_x", "tip_y", "tip_z", "nfev")
+    for tile in ((0, nx, 0, ny), (3, 64, 2, 41), (10, 13, 0, ny), (0, nx, 7, 9)):
+        monkeypatch.setenv("DBSPM_RELAX_FOOT_X", "1")
+        ref = ops.relax_grid(static, 0.2, 3.02, dr, 12, tile=tile, want_nfev=True, layout=2)
+        for fx in ("2", "4", "8", "16", "32"):
+            monkeypatch.setenv("DBSPM_RELAX_FOOT_X", fx)
+            got = ops.relax_grid(static, 0.2, 3.02, dr, 12, tile=tile, want_nfev=True, layout=2)
+            for key in keys:
+                assert torch.equal(got[key], ref[key]), (tile, fx, key)
+        monkeypatch.delenv("DBSPM_RELAX_FOOT_X")
+        got = ops.relax_grid(static, 0.2, 3.02, dr, 12, tile=tile, want_nfev=True, layout=2)      # the default patch
+        for key in keys:
+            assert torch.equal(got[key], ref[key]), (tile, "default", key)
+
+
 _CLI_WORKER_INPUT = "LABEL = two  # blanks before the comment stay in the label, as in the reference\nZ0 = {z0}\nZF = {zf}\nZREF = {zref}\nRPIVOT = {rp}\nZPAD = {zpad}\nALPHA = {alpha}\nV = 0.5\nK = 0.2\n"
 
 
@@ -333,6 +357,21 @@ def test_overlap_kernel_variants_agree(ops, overlap_golden, manifest, flags):
         ref = O.density_overlap_fft(a, b, np.ones(3))
         got = ops.density_overlap_window(a, b, np.ones(3), flags=flags)
         assert _rel(got, ref) <= 1e-9, (shape, flags)
+
+
+def test_overlap_pipelined_axis_pass_same_bits_as_one_shot(ops):
+    """Persistent software-pipelined y pass (n = 1024 = 16*8*8, enough tiles: the default there) against the one-shot blocks
+    (DBSPM_CORR_NO_PIPE): same bits; and both against the oracle."""
+    shape, (z_lo, z_hi) = (80, 1024, 64), (20, 41)
+    rng = np.random.default_rng(11)
+    a, b = rng.random(shape), rng.random(shape) - 0.3
+    dr = np.array([0.1, 0.09, 0.11])
+    A, B = torch.as_tensor(a, device="cuda"), torch.as_tensor(b, device="cuda")
+    x = ops.density_overlap_window(A, B, dr, z_lo, z_hi)
+    y = ops.density_overlap_window(A, B, dr, z_lo, z_hi, flags=1 << 14)
+    assert torch.equal(x, y)
+    ref = O.density_overlap_fft(a, b, dr)[:, :, z_lo:z_hi]
+    assert np.abs(x.cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
 def test_overlap_tiny_config_sr_es(ops, overlap_golden):

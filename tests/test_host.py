@@ -255,6 +255,12 @@ tiles = {{k: torch.from_numpy(rng.random((5, 4, 3))) for k in ("E", "tip_x")}}
 def tile(i_lo, i_hi):
     return {{k: v[i_lo:i_hi].contiguous() for k, v in tiles.items()}}
 res = parallel.relax_sharded(tile, 5, device)
+# equal tiles are received straight into place (no padded copies, no concatenation)
+tiles6 = {{k: torch.from_numpy(rng.random((6, 4, 3))) for k in ("E", "tip_x")}}
+res6 = parallel.relax_sharded(lambda a, b: {{k: v[a:b] for k, v in tiles6.items()}}, 6, device)
+assert (res6 is None) == (rank != 0)
+if rank == 0:
+    assert all(torch.equal(res6[k], tiles6[k]) for k in tiles6), "x-tile gather in place"
 # sr on rank 0, es on rank 1 (interaction-parallel plan), one gather assembles both windows
 plan = parallel.interaction_plan(2, 10, 17)
 assert plan == [[(0, 10, 17)], [(1, 10, 17)]]
