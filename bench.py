@@ -6,11 +6,14 @@
 One step = one pass of the hot path over the workload: sr (alpha-powered overlap), es,
 static = V*sr + es + vdw, relax of every tip position.  Default workload = BASELINE.json
 configs[4], the 1024x1024x256 slab (it fits one GPU, so N = 1, 2, 4, 8 all run it: strong
-scaling).  N = 2: one rank per interaction.  N >= 4: an sr group and an es group; inside a group
-the transform itself is distributed over x-slabs (parallel.sr_es_distributed: both exchanges
-fused into the passes as peer stores over NVLink, gather of the finished slabs to rank 0; the
-assembled es window is checked against the single-GPU path once per run).  relax shards by
-lateral x-tile; NCCL gathers.
+scaling).  N >= 2: ONE group of all ranks computes sr, then es, with the transform itself
+distributed over x-slabs (parallel.sr_es_distributed: both exchanges fused into the passes as
+peer stores over NVLink); every rank keeps its x-slab of both windows, assembles its static
+tile, fetches a halo of the lever length from its two neighbours and relaxes its x-tile
+(relax kernel in x-slab mode); the windows and the relax tiles go to rank 0 for the .npz, the
+window gathers beside the relax kernel.  Once per run the assembled es window is checked
+against the single-GPU path and the relaxed tile against the whole-window relax (same bits).
+--legacy-groups: the round-1 plan (an sr and an es group, windows gathered and broadcast back).
 Timed with CUDA events on the launching stream (torch's current stream), max over ranks.
 The arrays (2.1 GB each) are far larger than the 126 MB L2, so no explicit flush is needed.
 
