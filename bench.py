@@ -331,13 +331,35 @@ def run_sweep_arm(args):
                     config={"workload": "fdbmfit-style batch sweep (BASELINE.json configs[3]): 16 (alpha, V0, k) sets over the synthetic "
                                         "pyridine grid 196x196x240, window 54 planes, relax 196x196x24 per set", "sets": SWEEP_SETS})
     else:
-        line.update(value=None, ms_per_step=t_eager,
-                    relax={"value": npos / (t_eager * 1e-3), "unit": "tip positions/s (whole sweep time, correlations included)"},
-                    sweep={"ms_eager_whole_sweep": t_eager, "assignment": parallel.sweep_assignment(SWEEP_SETS, world),
-                           "note": "sets dealt over the ranks by alpha (a rank computes the sr grids of its own alphas), es on rank 0 + "
-                                   "broadcast, one gather of the stacked relax results"},
-                    gpu_launches=None,
-                    config={"workload": "fdbmfit-style batch sweep (BASELINE.json configs[3]), sharded over %d ranks" % world})
+        # every rank replays the CUDA graph of its own sets, then one gather of the stacked results to rank 0
+        plan = sweep.ShardedSweepGraph(rhoS, potS, rhoT, nrhoT, dr, (z_lo, z_hi), nz_relax, SWEEP_SETS, cfg.rpivot, vdw=vdw)
+        for _ in range(max(args.warmup, 3)):
+            res = plan.run()
+        barrier()
+        same = None
+        if rank == 0:      # same bits as the eager sharded sweep (whose results rank 0 holds in `out`)
+            same = all(torch.equal(res[i]["E"], out["relax"][i]["E"]) and torch.equal(res[i]["tip_z"], out["relax"][i]["tip_z"])
+                       for i in range(len(SWEEP_SETS)))
+        tg = []
+        with ClockSampler(dev.index) as clk:
+            for _ in range(args.steps):
+                barrier(); a = ev(); plan.run(); b = ev(); torch.cuda.synchronize(); tg.append(a.elapsed_time(b))
+        t = torch.tensor([float(np.mean(tg))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_graph = float(t.item())
+        n_mine = len(plan.assignment[rank])
+        n_alpha = len({SWEEP_SETS[i][0] for i in plan.assignment[rank]})
+        line.update(value=None, ms_per_step=t_graph,
+                    relax={"value": npos / (t_graph * 1e-3), "unit": "tip positions/s (whole sweep time, correlations and gather included)"},
+                    sweep={"ms_graph_whole_sweep": t_graph, "ms_eager_whole_sweep": t_eager, "graph_equals_eager_bit_for_bit": same,
+                           "assignment": plan.assignment,
+                           "note": "sets dealt over the ranks by alpha; every rank replays the CUDA graphs of its own sets (its own es, the "
+                                   "sr grids of its alphas, its relax runs on 4 forked streams, copies into one stacked buffer), then ONE "
+                                   "gather of the stacked results to rank 0; eager = sweep.fdbm_sweep issued from Python (es on rank 0 + "
+                                   "broadcast, pickled shape exchange, padded gather)"},
+                    gpu_launches=((1 + n_alpha) * 5 + 6 * n_mine + 4 * n_mine) * args.steps, clocks=clk.summary(),
+                    config={"workload": "fdbmfit-style batch sweep (BASELINE.json configs[3]): 16 (alpha, V0, k) sets over the synthetic "
+                                        "pyridine grid 196x196x240, sharded over %d ranks" % world, "sets": SWEEP_SETS})
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -25,11 +25,13 @@
 #define WARP_SYNC() __syncwarp()
 #define WARP_ALL(p) __all_sync(0xffffffffu, (p))
 #define LDG(p) __ldg(p)
+#define LD_CG(p) __ldcg(p)          /* L2-coherent load: data another SM may have written during this kernel */
 #else
 #define BLOCK_SYNC() ((void)0)
 #define WARP_SYNC() ((void)0)
 #define WARP_ALL(p) (p)
 #define LDG(p) (*(p))
+#define LD_CG(p) (*(p))
 #endif
 
 struct __attribute__((aligned(16))) cplx {

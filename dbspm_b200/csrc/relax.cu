@@ -34,7 +34,47 @@ __global__ void __launch_bounds__(RELAX_THREADS, RELAX_MIN_BLOCKS) relax_kernel(
 {
     const long long col = relax_patch_column(P, (long long)blockIdx.x * blockDim.x + threadIdx.x, ncol);
     __shared__ double powell_sm[(RELAX_SMEM_STATE == 0 ? PS_COUNT : (RELAX_SMEM_STATE == 1 ? PS_P_0 : PS_TOTAL)) * RELAX_THREADS];       // Powell-level state, one column per thread
-    relax_column_body<LAYOUT, RELAX_THREADS>(P, col, ncol, powell_sm, threadIdx.x);      // lanes past the end idle inside (warp barrier)
+    relax_column_body<LAYOUT, RELAX_THREADS>(P, col, ncol, powell_sm, threadIdx.x, P.k_hi, P.k_lo);      // lanes past the end idle inside (warp barrier)
+}
+
+// Dynamic schedule: a persistent grid (one wave: SMs x resident warps) whose warps pull tasks from a global counter.  A task =
+// (patch of 32 columns, chunk of `hpc` heights), issued chunk-major: all patches' top chunk first.  A static launch gives every
+// warp one patch with all its heights -- with 4096 patches for 2368 resident warps (one rank of 8 on the 1024 x 1024 grid) the
+// second wave runs at 73 % occupancy and the slowest patches (over the molecule) finish alone; tasks of a quarter of the length
+// fill the tail.  The chunk c of a patch needs chunk c - 1 (warm start): `progress[patch]` counts finished chunks; the task
+// that needs it was issued a whole round of patches later, so the wait is almost never taken, and it cannot deadlock: a task
+// only waits for tasks issued BEFORE it, which run on resident warps.  Each height starts a fresh Powell minimisation from the
+// previous height's angles (as the reference), so chunking does not change a single bit.
+template <int LAYOUT>
+__global__ void __launch_bounds__(RELAX_THREADS, RELAX_MIN_BLOCKS) relax_dyn_kernel(const __grid_constant__ RelaxParams P, long long ncol,
+                                                                                    int npatch, int nchunks, int hpc, int *ctrl)
+{
+    __shared__ double powell_sm[(RELAX_SMEM_STATE == 0 ? PS_COUNT : (RELAX_SMEM_STATE == 1 ? PS_P_0 : PS_TOTAL)) * RELAX_THREADS];
+    const int lane = threadIdx.x & 31;
+    int *progress = ctrl + 1;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(ctrl, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= npatch * nchunks) break;
+        const int c = t / npatch, p = t - c * npatch;
+        if (c > 0) {
+            if (lane == 0) {
+                int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(progress + p) : "memory");
+                    if (seen < c) __nanosleep(256);
+                } while (seen < c);
+            }
+            __syncwarp();
+        }
+        const int k_hi = P.nz_relax - 1 - c * hpc, k_lo = (k_hi - hpc + 1) > 0 ? (k_hi - hpc + 1) : 0;
+        const long long col = relax_patch_column(P, (long long)p * 32 + lane, ncol);
+        relax_column_body<LAYOUT, RELAX_THREADS>(P, col, ncol, powell_sm, threadIdx.x, k_hi, k_lo);
+        __threadfence();                      // every lane's rows of out_etp before the flag
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress + p), "r"(c + 1) : "memory");
+    }
 }
 
 // (nx,ny,nz) -> (nx,nz,ny+3) so that the lanes of a warp (adjacent y columns) read adjacent addresses
@@ -138,12 +178,27 @@ extern "C" int dbspm_static_accumulate_f64(double *acc, const double *comp, doub
 }
 
 // layout 1: y-fastest copy with a 3-plane periodic halo; layout 2: y-quads (four times the window)
-extern "C" size_t dbspm_relax_workspace_bytes_layout(int nx, int ny, int nzc, int layout)
+// control block of the dynamic schedule (task counter + one progress word per patch of 32 columns), behind the re-laid potential
+static size_t relax_ctrl_bytes(int nx, int ny)
+{
+    const size_t words = (size_t)nx * ny / 32 + (size_t)nx + ny + 8;          // >= patches of any patch shape, + counter
+    return (words * sizeof(int) + 255) / 256 * 256;
+}
+
+// bytes of the re-laid potential alone (a multiple of 256, so the control block behind it is aligned)
+static size_t relax_layout_bytes(int nx, int ny, int nzc, int layout)
 {
     if (nx < 1 || ny < 1 || nzc < 1) return 0;
-    if (layout == 1) return (size_t)nx * (ny + 3) * nzc * sizeof(double);
-    if (layout == 2) return (long long)nx * ny * nzc * 4 < 2147483647LL ? (size_t)nx * ny * nzc * 4 * sizeof(double) : 0;
-    return 0;
+    size_t b = 0;
+    if (layout == 1) b = (size_t)nx * (ny + 3) * nzc * sizeof(double);
+    if (layout == 2) b = (long long)nx * ny * nzc * 4 < 2147483647LL ? (size_t)nx * ny * nzc * 4 * sizeof(double) : 0;
+    return (b + 255) / 256 * 256;
+}
+
+extern "C" size_t dbspm_relax_workspace_bytes_layout(int nx, int ny, int nzc, int layout)
+{
+    const size_t b = relax_layout_bytes(nx, ny, nzc, layout);
+    return b ? b + relax_ctrl_bytes(nx, ny) : 0;
 }
 
 // the preferred workspace: the quad layout where its 32-bit element offsets allow, else the y-fastest copy
@@ -270,11 +325,36 @@ static int relax_launch(const double *static_win, int nx, int ny, int nzc, int x
                       need1, need2, workspace_bytes);
         DBSPM_REQUIRE(nxs <= 65535, DBSPM_EUNSUPPORTED, "nx too large for the transpose grid");
         P.grid = (const double *)workspace;
-        if (need2 && workspace_bytes >= need2) {
+        const bool quads = need2 && workspace_bytes >= need2;
+        // dynamic schedule (relax_dyn_kernel): chunks of `hpc` heights pulled by one wave of persistent warps; the control
+        // block sits behind the re-laid potential.  DBSPM_RELAX_CHUNK=0 keeps the static launches (A/B; with
+        // DBSPM_RELAX_HEIGHTS_PER_LAUNCH), any other value sets the chunk length
+        int hpc = 4;     // B200, 1024 x 1024 x 24: chunks of 2 ... 8 heights 63.9-64.1 ms, 12: 64.6, static launch 65.7
+        if (const char *e = getenv("DBSPM_RELAX_CHUNK")) hpc = atoi(e);
+        int *ctrl = (int *)((char *)workspace + relax_layout_bytes(nxs, ny, nzc, quads ? 2 : 1));
+        const long long npatch = relax_patch_threads(i_hi - i_lo, j_hi - j_lo, P.foot_x) / 32 + (P.foot_x <= 1 && ncol % 32 ? 1 : 0);
+        const int nchunks = hpc > 0 ? (nz_relax + hpc - 1) / hpc : 0;
+        bool dynamic = hpc > 0 && getenv("DBSPM_RELAX_HEIGHTS_PER_LAUNCH") == nullptr && npatch * nchunks < 2147483647LL &&
+                             (size_t)(npatch + 1) * sizeof(int) <= relax_ctrl_bytes(nxs, ny);
+        int resident = 0;
+        if (dynamic) {
+            int dev = 0, sms = 0;
+            DBSPM_CUDA_TRY(cudaGetDevice(&dev));
+            DBSPM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            const long long warps = (long long)sms * RELAX_MIN_BLOCKS * (RELAX_THREADS / 32);
+            // Only with more patches than resident warps.  Otherwise every patch has its own warp from the start, a static
+            // launch IS the best schedule, and the chunk-major order would make early finishers wait for the patch whose
+            // next chunk they drew (16-set pyridine sweep on four streams, 1225 patches per launch: 41.8 -> 44.4 ms).
+            dynamic = npatch > warps || getenv("DBSPM_RELAX_CHUNK") != nullptr;
+            resident = (int)((npatch < warps ? npatch : warps) + (RELAX_THREADS / 32) - 1) / (RELAX_THREADS / 32);
+            if (dynamic) DBSPM_CUDA_TRY(cudaMemsetAsync(ctrl, 0, (size_t)(npatch + 1) * sizeof(int), (cudaStream_t)stream));
+        }
+        if (quads) {
             dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 31) / 32), (unsigned)nxs);
             quad_yz_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_win, (double *)workspace, ny, nzc);
             DBSPM_CUDA_TRY(cudaGetLastError());
-            for (int kh = nz_relax - 1; kh >= 0; kh -= hpl) {
+            if (dynamic) relax_dyn_kernel<2><<<(unsigned)resident, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol, (int)npatch, nchunks, hpc, ctrl);
+            else for (int kh = nz_relax - 1; kh >= 0; kh -= hpl) {
                 P.k_hi = kh; P.k_lo = kh - hpl + 1 > 0 ? kh - hpl + 1 : 0;
                 relax_kernel<2><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
             }
@@ -282,7 +362,8 @@ static int relax_launch(const double *static_win, int nx, int ny, int nzc, int x
             dim3 tg((unsigned)((nzc + 31) / 32), (unsigned)((ny + 3 + 31) / 32), (unsigned)nxs);
             transpose_yz_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(static_win, (double *)workspace, ny, nzc);
             DBSPM_CUDA_TRY(cudaGetLastError());
-            for (int kh = nz_relax - 1; kh >= 0; kh -= hpl) {
+            if (dynamic) relax_dyn_kernel<1><<<(unsigned)resident, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol, (int)npatch, nchunks, hpc, ctrl);
+            else for (int kh = nz_relax - 1; kh >= 0; kh -= hpl) {
                 P.k_hi = kh; P.k_lo = kh - hpl + 1 > 0 ? kh - hpl + 1 : 0;
                 relax_kernel<1><<<(unsigned)blocks, RELAX_THREADS, 0, (cudaStream_t)stream>>>(P, ncol);
             }

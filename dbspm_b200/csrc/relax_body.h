@@ -473,8 +473,11 @@ HD long long relax_patch_threads(int ni, int nj, int foot_x)
 
 // ---- one lateral column: sweep z from the top with warm start ------------------------------
 // NTHR = threads per block (the stride of the shared-memory columns); sm = PS_TOTAL*NTHR doubles.
+// k_hi, k_lo: the heights this call sweeps (k_hi, k_hi - 1, ..., k_lo); the start point of a height k_hi < nz_relax - 1 is the
+// relaxed (theta, phi) of height k_hi + 1 in out_etp -- written by an earlier launch or, under the dynamic schedule of
+// relax_dyn_kernel, by another warp (hence the L2-coherent load)
 template <int LAYOUT, int NTHR>
-HDN inline void relax_column_body(const RelaxParams &P, long long col, long long ncol, double *sm, int tid)
+HDN inline void relax_column_body(const RelaxParams &P, long long col, long long ncol, double *sm, int tid, int k_hi, int k_lo)
 {
 #define PS(f) sm[(f) * NTHR + tid]
     const double _gold = 1.618034, _verysmall_num = 1e-21, grow_limit = 110.0;
@@ -487,7 +490,7 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
     const long long c = done ? 0 : col;
     const int ci = (int)(c / nj), cj = (int)(c - (long long)ci * nj);
     const int oi = P.i_lo + ci, oj = P.j_lo + cj;
-    int k = P.k_hi;
+    int k = k_hi;
     int ok = (int)((double)k + P.npivot);                    // int64 store truncates
     PowellRegs R;
     // start of a minimisation at the current point (scipy: x = asarray(x0); fval = func(x)); the
@@ -496,7 +499,7 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
     double th0 = M_PI, az0 = 0.0;
     if (!done && k < P.nz_relax - 1) {
         const size_t o = (size_t)col * P.nz_relax + (k + 1);
-        th0 = P.out_etp[3 * o + 1]; az0 = P.out_etp[3 * o + 2];
+        th0 = LD_CG(P.out_etp + 3 * o + 1); az0 = LD_CG(P.out_etp + 3 * o + 2);
     }
     PS(PS_X_0) = th0; PS(PS_X_1) = az0;
     PS(PS_D0_0) = 1.0; PS(PS_D0_1) = 0.0; PS(PS_D1_0) = 0.0; PS(PS_D1_1) = 1.0;
@@ -743,7 +746,7 @@ HDN inline void relax_column_body(const RelaxParams &P, long long col, long long
                 P.out_etp[3 * o + 1] = x0;
                 P.out_etp[3 * o + 2] = x1;
                 if (P.out_nfev) P.out_nfev[o] = R.nfev;
-                if (--k < P.k_lo) {
+                if (--k < k_lo) {
                     done = true; pc = PC_IDLE;
                 } else {
                     ok = (int)((double)k + P.npivot);

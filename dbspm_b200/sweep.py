@@ -36,7 +36,7 @@ class SweepGraph:
         warm.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(warm):
             _corr_part(*self.inputs, dr, z_window, self.args["param_sets"])
-            fdbm_sweep(*self.inputs, vdw=self.vdw, keep_static=False, _sync=False, **self.args)
+            fdbm_sweep(*self.inputs, vdw=self.vdw, keep_static=False, _sync=False, _local=True, **self.args)
         torch.cuda.current_stream(dev).wait_stream(warm)
         torch.cuda.synchronize(dev)
         before = set(ops._WS_CACHE)
@@ -58,6 +58,65 @@ class SweepGraph:
         self.g_corr.replay()
         self.g_relax.replay()
         return {"es": self.es, "sr": self.sr, "relax": self.relax}
+
+
+class ShardedSweepGraph:
+    """The sweep under torchrun (one process per GPU) with the host out of the loop: the sets are dealt over the ranks
+    (parallel.sweep_assignment: contiguous blocks after sorting by alpha), every rank captures ITS sets as a SweepGraph (its own
+    es -- 0.35 ms, cheaper than a broadcast inside the step -- the sr grids of its alphas, its relax runs on forked streams)
+    plus the copies of the requested results into one stacked buffer, and a replay is followed by ONE gather of the stacked
+    buffers to rank 0 (received straight into place when the ranks hold equally many sets).  Same bits as the single-GPU
+    sweep (every kernel is deterministic).
+
+        plan = ShardedSweepGraph(rhoS, potS, rhoT, nrhoT, dr, (76, 130), 24, sets, 3.02, vdw=vdw)
+        res = plan.run()      # rank 0: list of dicts in the order of `sets` (views into one buffer, refreshed by every run)
+    """
+
+    def __init__(self, rhoS, potS, rhoT, nrhoT, dr, z_window, nz_relax, param_sets, rpivot, vdw=None, dR=None, streams=4,
+                 keys=("E", "tip_x", "tip_y", "tip_z"), dst=0):
+        import torch.distributed as dist
+        self.rank, self.world = parallel._world()
+        self.keys, self.dst = tuple(keys), int(dst)
+        self.param_sets = [tuple(float(v) for v in p) for p in param_sets]
+        self.assignment = parallel.sweep_assignment(self.param_sets, self.world)
+        mine = [self.param_sets[i] for i in self.assignment[self.rank]]
+        dev = rhoS.device
+        nx, ny = int(rhoS.shape[0]), int(rhoS.shape[1])
+        self.counts = [len(a) for a in self.assignment]
+        big = max(self.counts)
+        # (sets, keys, nx, ny, nz): padded to the largest share so that one plain gather moves everything
+        self.stack = torch.zeros((big, len(self.keys), nx, ny, int(nz_relax)), dtype=torch.float64, device=dev)
+        self.plan = None
+        if mine:
+            self.plan = SweepGraph(rhoS, potS, rhoT, nrhoT, dr, z_window, nz_relax, mine, rpivot, vdw=vdw, dR=dR, streams=streams)
+            self.g_stack = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_stack, pool=self.plan.g_corr.pool()):
+                for j, r in enumerate(self.plan.relax):
+                    for q, k in enumerate(self.keys):
+                        self.stack[j, q].copy_(r[k])
+        self.recv = None
+        if self.world > 1 and self.rank == self.dst:
+            self.recv = torch.empty((self.world,) + tuple(self.stack.shape), dtype=torch.float64, device=dev)
+        self._dist = dist
+
+    def run(self):
+        if self.plan is not None:
+            self.plan.run()
+            self.g_stack.replay()
+        if self.world == 1:
+            parts = [self.stack]
+        else:
+            self._dist.gather(self.stack, list(self.recv.unbind(0)) if self.recv is not None else None, dst=self.dst)
+            if self.rank != self.dst:
+                return None
+            parts = list(self.recv.unbind(0))
+        out = [None] * len(self.param_sets)
+        for a, part in zip(self.assignment, parts):
+            for j, i in enumerate(a):
+                d = {k: part[j, q] for q, k in enumerate(self.keys)}
+                d.update(alpha=self.param_sets[i][0], V=self.param_sets[i][1], kappa=self.param_sets[i][2])
+                out[i] = d
+        return out
 
 
 def _corr_part(A, P, T, NT, dr, z_window, param_sets):
@@ -96,7 +155,7 @@ def _relax_part(es, sr, vd, dr, nz_relax, param_sets, rpivot, dR, streams, keep_
 
 
 def fdbm_sweep(rhoS, potS, rhoT, nrhoT, dr, z_window, nz_relax, param_sets, rpivot, vdw=None, dR=None,
-               keep_static=False, streams=4, _sync=True):
+               keep_static=False, streams=4, _sync=True, _local=False):
     """param_sets: iterable of (alpha, V0, kappa).  Inputs: CUDA tensors (or numpy, uploaded once).
     Returns {"es": window, "sr": {alpha: window}, "relax": [dict per set]} with CUDA tensors.
     streams: how many CUDA streams the independent relax runs are spread over (1 = serial).
@@ -110,7 +169,7 @@ def fdbm_sweep(rhoS, potS, rhoT, nrhoT, dr, z_window, nz_relax, param_sets, rpiv
     z_lo, z_hi = z_window
     param_sets = list(param_sets)
     rank, world = parallel._world()
-    if world > 1:
+    if world > 1 and not _local:      # (_local: this rank's own list, no collectives -- the warm-up of a captured sweep)
         return _sweep_sharded(A, P, T, NT, dr, z_lo, z_hi, nz_relax, param_sets, rpivot, vdw, dR, dev, rank, world)
     es, sr = _corr_part(A, P, T, NT, dr, (z_lo, z_hi), param_sets)
     vd = ops._to_dev(vdw, dev) if vdw is not None else None

@@ -459,7 +459,7 @@ static int emu_relax_impl(const double *static_win, int nx_global, int ny, int n
         // one "launch" per height, as the library does for large tiles: the warm start travels through out_etp
         for (int kh = nz_relax - 1; kh >= 0; --kh) {
             P.k_hi = P.k_lo = kh;
-            for (long long c = 0; c < ncol; ++c) relax_column_body<2, 1>(P, c, ncol, powell_sm, 0);
+            for (long long c = 0; c < ncol; ++c) relax_column_body<2, 1>(P, c, ncol, powell_sm, 0, P.k_hi, P.k_lo);
         }
     } else if (transposed) {
         // what transpose_yz_kernel does, block by block: the body has one block barrier, so it is run
@@ -489,10 +489,10 @@ static int emu_relax_impl(const double *static_win, int nx_global, int ny, int n
         // launches of five heights
         for (int kh = nz_relax - 1; kh >= 0; kh -= 5) {
             P.k_hi = kh; P.k_lo = kh - 4 > 0 ? kh - 4 : 0;
-            for (long long c = 0; c < ncol; ++c) relax_column_body<1, 1>(P, c, ncol, powell_sm, 0);
+            for (long long c = 0; c < ncol; ++c) relax_column_body<1, 1>(P, c, ncol, powell_sm, 0, P.k_hi, P.k_lo);
         }
     } else {
-        for (long long c = 0; c < ncol; ++c) relax_column_body<0, 1>(P, c, ncol, powell_sm, 0);
+        for (long long c = 0; c < ncol; ++c) relax_column_body<0, 1>(P, c, ncol, powell_sm, 0, P.k_hi, P.k_lo);
     }
     if (out_cart) relax_cart_body(out_etp, out_cart, ncol * nz_relax, rpivot, 0, 1);
     return 0;

@@ -291,6 +291,30 @@ def test_relax_warp_footprint_does_not_change_the_bits(ops, monkeypatch):
             assert torch.equal(got[key], ref[key]), (tile, "default", key)
 
 
+def test_relax_dynamic_schedule_does_not_change_the_bits(ops, monkeypatch):
+    """relax_dyn_kernel (persistent warps pulling (patch, chunk of heights) tasks from a counter; a patch's next chunk starts
+    from the angles the previous chunk stored) against the static launch (DBSPM_RELAX_CHUNK=0): identical bits for every chunk
+    length, patch shape and layout, with more tasks than resident warps and with fewer."""
+    from dbspm_b200 import synth
+    dev = torch.device("cuda", 0)
+    dr = np.array([0.0765306, 0.0765306, 0.075])
+    keys = ("E", "theta", "phi", "tip_x", "tip_y", "tip_z", "nfev")
+    for (nx, ny), tile, nz in (((70, 45), None, 12), ((70, 45), (3, 64, 2, 41), 7), ((400, 260), None, 5)):
+        static = synth.make_static_like((nx, ny, 54), 9, dev)
+        for layout in (2, 1):
+            monkeypatch.setenv("DBSPM_RELAX_CHUNK", "0")
+            ref = ops.relax_grid(static, 0.2, 3.02, dr, nz, tile=tile, want_nfev=True, layout=layout)
+            for chunk in ("1", "2", "5", "6", "100"):
+                monkeypatch.setenv("DBSPM_RELAX_CHUNK", chunk)
+                got = ops.relax_grid(static, 0.2, 3.02, dr, nz, tile=tile, want_nfev=True, layout=layout)
+                for key in keys:
+                    assert torch.equal(got[key], ref[key]), ((nx, ny), tile, layout, chunk, key)
+            monkeypatch.delenv("DBSPM_RELAX_CHUNK")
+            got = ops.relax_grid(static, 0.2, 3.02, dr, nz, tile=tile, want_nfev=True, layout=layout)      # the default
+            for key in keys:
+                assert torch.equal(got[key], ref[key]), ((nx, ny), tile, layout, "default", key)
+
+
 _CLI_WORKER_INPUT = "LABEL = two  # blanks before the comment stay in the label, as in the reference\nZ0 = {z0}\nZF = {zf}\nZREF = {zref}\nRPIVOT = {rp}\nZPAD = {zpad}\nALPHA = {alpha}\nV = 0.5\nK = 0.2\n"
 
 
@@ -909,6 +933,27 @@ def test_batched_parameter_sweep(ops):
         assert (dE > 1e-6).mean() < 1e-2, (dE > 1e-6).mean()
         dev_pos = _dev_positions(r, ref, cfg.rpivot)
         assert (dev_pos > 1e-6).mean() < 2e-2, (dev_pos > 1e-6).mean()
+
+
+def test_sharded_sweep_graph_on_one_rank_equals_the_sweep(ops):
+    """ShardedSweepGraph without a process group (one rank holds every set): the stacked buffer it would gather holds the
+    bits of the plain sweep, in the caller's order (the assignment sorts by alpha)."""
+    from dbspm_b200 import sweep, synth
+    dev = torch.device("cuda", 0)
+    cfg = synth.CONFIGS["tiny"]
+    rhoS, potS, atoms = synth.make_sample(cfg, dev)
+    rhoT, nrhoT = synth.make_tip(cfg, dev, "noisy")
+    dr = np.array(cfg.cell) / np.array(cfg.shape)
+    sets = [(1.08, 0.4, 0.2), (1.0, 0.35, 0.24), (1.08, 0.5, 0.2), (1.12, 0.35, 0.2), (1.0, 0.6, 0.2)]
+    ref = sweep.fdbm_sweep(rhoS, potS, rhoT, nrhoT, dr, (24, 32), 6, sets, cfg.rpivot)
+    plan = sweep.ShardedSweepGraph(rhoS, potS, rhoT, nrhoT, dr, (24, 32), 6, sets, cfg.rpivot)
+    for _ in range(2):
+        got = plan.run()
+    assert plan.assignment == [[1, 4, 0, 2, 3]]
+    for i, p in enumerate(sets):
+        assert (got[i]["alpha"], got[i]["V"], got[i]["kappa"]) == p
+        for key in ("E", "tip_x", "tip_y", "tip_z"):
+            assert torch.equal(got[i][key], ref["relax"][i][key]), (i, key)
 
 
 def test_sweep_cuda_graph_equals_eager(ops):
