@@ -208,7 +208,11 @@ int dbspm_relax_powell_slab_f64(const double *static_slab, int nx, int ny, int n
  * halo.  Layout 2 (4x the window; returns 0 when 32-bit element offsets would overflow): the four y neighbours of every
  * stencil row as one 32-byte sector, one 256-bit load per row.  The kernel takes the largest layout the workspace
  * holds; dbspm_relax_workspace_bytes returns the preferred size (layout 2, else 1).  Without a workspace the kernel
- * reads static_win in place.  Results are bit-identical in all three cases.                                       */
+ * reads static_win in place.  Results are bit-identical in all three cases.
+ * The sizes include a small control block behind the re-laid potential (a task counter and one progress word per patch
+ * of 32 columns): with more patches than resident warps the heights are relaxed in chunks pulled by one wave of
+ * persistent warps (dynamic schedule, same bits; environment: DBSPM_RELAX_CHUNK = heights per chunk, 0 = static
+ * launches; DBSPM_RELAX_FOOT_X = columns of a warp's patch along x, 1 = 32 consecutive y).                          */
 size_t dbspm_relax_workspace_bytes(int nx, int ny, int nzc);
 size_t dbspm_relax_workspace_bytes_layout(int nx, int ny, int nzc, int layout);
 
