@@ -183,10 +183,14 @@ def test_sass_has_the_async_machinery_the_design_claims():
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     sass = out.stdout
-    for mnemonic in ("UTMALDG", "UTMASTG", "UBLKPF.L2", "CCTL.E.PF2", "DFMA"):
+    # round 2: cp.async slots of the pipelined axis pass (LDGSTS + LDGDEPBAR), the 256-bit y-quad loads of the relax stencil,
+    # the task counter / progress words of the dynamic relax schedule (ATOMG, acquire load, release store, NANOSLEEP)
+    for mnemonic in ("UTMALDG", "UTMASTG", "UBLKPF.L2", "CCTL.E.PF2", "DFMA", "LDGSTS.E.BYPASS.128", "LDGDEPBAR", ".256.CONSTANT",
+                     "ATOMG.E.ADD.STRONG.GPU", "LDG.E.STRONG.GPU", "STG.E.STRONG.GPU", "NANOSLEEP"):
         assert mnemonic in sass, mnemonic
     for kernel in ("axis_pass2_kernel", "axis_pass2w_kernel", "axis_pass2m_kernel", "axis_pass2p_kernel", "axis_pass2pw_kernel",
-                   "axis_tma_kernel", "zfused2_kernel", "relax_kernel"):
+                   "axis_pass2s_kernel", "axis_pass2sw_kernel", "axis_tma_kernel", "zfused2_kernel", "relax_kernel", "relax_dyn_kernel",
+                   "direct_kernel"):
         assert kernel in sass, kernel
 
 
