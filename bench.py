@@ -438,6 +438,15 @@ def run_gpu_arm(args):
         my_which, my_h = rank // G, rank % G
         sx0, sx1 = parallel.x_slab(nx, G, my_h)
     halo = ops.relax_slab_halo(cfg.rpivot, dr) if slab_mode else 0
+    asm, asm_side = None, None
+    if slab_mode and not args.no_peer:
+        shapes = {"sr": (nx, ny, nzw), "es": (nx, ny, nzw), "E": (nx, ny, nz_relax), "tip_x": (nx, ny, nz_relax),
+                  "tip_y": (nx, ny, nz_relax), "tip_z": (nx, ny, nz_relax)}
+        asm = {k: parallel.PeerAssembler.get(k, shp, dev) for k, shp in shapes.items()}
+        if any(v is None for v in asm.values()):
+            asm = None
+        else:
+            asm_side = torch.cuda.Stream(device=dev)
     dist_marks = []
     rest_marks = []        # slab mode: events inside "the rest" of a step (static | halo exchange | relax | tile gathers | window gathers)
     tiles = parallel.split_range(0, nx, world)
@@ -491,8 +500,19 @@ def run_gpu_arm(args):
         es_slab = slab_interaction(1, rec, src, sliced=sliced)
         e2 = ev()
         launches["n"] += 10                                        # per interaction: y fwd | x fwd, z, x inv | y inv
-        w_sr, work_sr = parallel.gather_x_slabs(sr_slab, nx, async_op=True)      # only the .npz needs them on rank 0
-        w_es, work_es = parallel.gather_x_slabs(es_slab, nx, async_op=True)
+        # The windows and the relax tiles go to rank 0 only for the .npz.  With symmetric memory every rank copies its rows
+        # straight into rank 0's buffers (parallel.PeerAssembler: copy engines over NVLink, no SM), the windows on a side
+        # stream beside static / halo exchange / relax; otherwise NCCL gathers (the window gathers asynchronously).
+        use_asm = asm is not None
+        if use_asm:
+            cur = torch.cuda.current_stream(dev)
+            asm_side.wait_stream(cur)
+            for key, slab in (("sr", sr_slab), ("es", es_slab)):
+                asm[key].begin(asm_side)
+                asm[key].put(slab, asm_side)
+        else:
+            w_sr, work_sr = parallel.gather_x_slabs(sr_slab, nx, async_op=True)
+            w_es, work_es = parallel.gather_x_slabs(es_slab, nx, async_op=True)
         static_slab = ops.build_static([(sr_slab, cfg.V), (es_slab, 1.0), (vdw[sx0:sx1] if vdw_slab is None else vdw_slab, 1.0)])
         ea = ev()
         static_loc = parallel.exchange_halo(static_slab, halo)
@@ -500,9 +520,19 @@ def run_gpu_arm(args):
         r = ops.relax_grid(static_loc, cfg.kappa, cfg.rpivot, dr, nz_relax, tile=(sx0, sx1, 0, ny), x_slab=((sx0 - halo) % nx, nx))
         ec = ev()
         launches["n"] += 6                                         # 3 x accumulate, y-quad re-layout, relax, sph2cart
-        res = parallel.relax_sharded(lambda il, ih: {k: r[k] for k in ("E", "tip_x", "tip_y", "tip_z")}, nx, dev)
-        ed = ev()
-        work_sr.wait(); work_es.wait()
+        if use_asm:
+            for key in ("E", "tip_x", "tip_y", "tip_z"):
+                asm[key].begin()
+                asm[key].put(r[key])
+            res = {key: asm[key].end() for key in ("E", "tip_x", "tip_y", "tip_z")}
+            res = res if rank == 0 else None
+            ed = ev()
+            cur.wait_stream(asm_side)
+            w_sr, w_es = asm["sr"].end(), asm["es"].end()
+        else:
+            res = parallel.relax_sharded(lambda il, ih: {k: r[k] for k in ("E", "tip_x", "tip_y", "tip_z")}, nx, dev)
+            ed = ev()
+            work_sr.wait(); work_es.wait()
         e3 = ev()
         if timed is not None:
             timed.append((e0, e1, e2, e3))
@@ -562,6 +592,12 @@ def run_gpu_arm(args):
             full_static = ops.build_static([(keep["w_sr"], cfg.V), (keep["w_es"], 1.0), (vdw, 1.0)])
             sub = ops.relax_grid(full_static, cfg.kappa, cfg.rpivot, dr, nz_relax, tile=(sx0, sx0 + 8, 0, ny))
             relax_check = bool(torch.equal(sub["E"], keep["r"]["E"][:8]) and torch.equal(sub["tip_x"], keep["r"]["tip_x"][:8]))
+            # ... and what arrived on rank 0 from the LAST rank's tile (assembled through peer copies or the NCCL gather)
+            sub2 = ops.relax_grid(full_static, cfg.kappa, cfg.rpivot, dr, nz_relax, tile=(nx - 8, nx, 0, ny))
+            relax_check = relax_check and bool(torch.equal(sub2["E"], keep["res"]["E"][nx - 8:])
+                                               and torch.equal(sub2["tip_z"], keep["res"]["tip_z"][nx - 8:])
+                                               and torch.equal(keep["res"]["tip_y"][:8], keep["r"]["tip_y"][:8]))
+            del sub2
             dist_check_sr = float((keep["w_sr"] - sr1).abs().max() / sr1.abs().max())
             dist_check = max(dist_check, dist_check_sr)
             del one, sr1, full_static, sub
