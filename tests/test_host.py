@@ -259,6 +259,8 @@ tiles = {{k: torch.from_numpy(rng.random((5, 4, 3))) for k in ("E", "tip_x")}}
 def tile(i_lo, i_hi):
     return {{k: v[i_lo:i_hi].contiguous() for k, v in tiles.items()}}
 res = parallel.relax_sharded(tile, 5, device)
+# no symmetric memory on the CPU: the peer assembly declines and callers fall back to the gathers below
+assert parallel.PeerAssembler.get("t", (6, 4, 3), device) is None
 # equal tiles are received straight into place (no padded copies, no concatenation)
 tiles6 = {{k: torch.from_numpy(rng.random((6, 4, 3))) for k in ("E", "tip_x")}}
 res6 = parallel.relax_sharded(lambda a, b: {{k: v[a:b] for k, v in tiles6.items()}}, 6, device)
