@@ -447,6 +447,16 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
             smem = axis2_smem_bytes(n, 3, P.plan.nstages, 0);
         }
 #endif
+        // The pipelined pass takes 8-line tiles for the other axes as well: full 128-byte row segments halve the L1
+        // wavefronts per byte (the one-shot y pass sat at 72 % L1/LSU), and the pipelining covers the latency that one
+        // resident CTA exposes (one-shot, the same tiles were slower: 2.36 against 2.20 ms).  B200, n = 1024, inner = 128:
+        // y pass 2.29 -> 2.08 ms.  Not for ragged or short rows (inverse y pass on the window, inner = 27: 0.301 -> 0.313 ms).
+        if (P.v2 && !wide && !pipe_off && !(flags & DBSPM_CORR_PIPE_NARROW_Y) && outer > 1 && P.tshift == 2 && inner >= 64 &&
+            inner % 8 == 0 && P.plan.nstages > 1 && axis2_smem_bytes(n, 3, P.plan.nstages, 0) <= 160 * 1024) {
+            wide = true;
+            P.tshift = 3; P.tw_smem = 0;
+            smem = axis2_smem_bytes(n, 3, P.plan.nstages, 0);
+        }
         // fused exchange: NVLink moves 128-byte segments much better than 64-byte ones, so the peer-store pass takes
         // 8-line tiles whenever they fit (measured in profiles/README.md)
         if (P.v2 && mp && mp->npeers > 0 && !(flags & DBSPM_CORR_PEER_NARROW) && P.tshift < 3 && inner >= 8 && P.plan.nstages > 1 &&

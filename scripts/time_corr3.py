@@ -21,7 +21,7 @@ for name in (sys.argv[1:] or ["large_slab"]):
     dr = np.array(cfg.cell) / np.array(cfg.shape)
     outs = {}
     for alpha in (1.0, 1.08):
-        for label, fl in (("default", 0), ("nopipe", NO_PIPE)):
+        for label, fl in (("default", 0), ("nopipe", NO_PIPE), ("narrowy", 1 << 15)):
             out = torch.empty((nx, ny, 54), dtype=torch.float64, device=dev)
             f = lambda extra=0: ops.density_overlap_window(A, B, dr, 76, 130, alpha, alpha, out=out, flags=fl | extra)
             t = timeit(f)
@@ -32,4 +32,4 @@ for name in (sys.argv[1:] or ["large_slab"]):
             f()
             print(line, flush=True)
         same = bool(torch.equal(outs[(alpha, "default")], outs[(alpha, "nopipe")]))
-        print(f"CORR3 {name} alpha={alpha} default == nopipe bitwise: {same}", flush=True)
+        print(f"CORR3 {name} alpha={alpha} default == nopipe bitwise: {same}; narrowy == nopipe: {bool(torch.equal(outs[(alpha, 'narrowy')], outs[(alpha, 'nopipe')]))}", flush=True)

@@ -383,17 +383,20 @@ def test_overlap_kernel_variants_agree(ops, overlap_golden, manifest, flags):
         assert _rel(got, ref) <= 1e-9, (shape, flags)
 
 
-def test_overlap_pipelined_axis_pass_same_bits_as_one_shot(ops):
-    """Persistent software-pipelined y pass (n = 1024 = 16*8*8, enough tiles: the default there) against the one-shot blocks
-    (DBSPM_CORR_NO_PIPE): same bits; and both against the oracle."""
-    shape, (z_lo, z_hi) = (80, 1024, 64), (20, 41)
+@pytest.mark.parametrize("shape,window", [((80, 1024, 64), (20, 41)), ((40, 1024, 256), (100, 131))])
+def test_overlap_pipelined_axis_pass_same_bits_as_one_shot(ops, shape, window):
+    """Persistent software-pipelined y pass (n = 1024 = 16*8*8, enough tiles: the default there; 4-line tiles for rows of 32
+    elements, 8-line tiles / one CTA of 512 threads for rows of 128) against the one-shot blocks (DBSPM_CORR_NO_PIPE) and
+    against 4-line tiles forced (DBSPM_CORR_PIPE_NARROW_Y): same bits; and against the oracle."""
+    z_lo, z_hi = window
     rng = np.random.default_rng(11)
     a, b = rng.random(shape), rng.random(shape) - 0.3
     dr = np.array([0.1, 0.09, 0.11])
     A, B = torch.as_tensor(a, device="cuda"), torch.as_tensor(b, device="cuda")
     x = ops.density_overlap_window(A, B, dr, z_lo, z_hi)
     y = ops.density_overlap_window(A, B, dr, z_lo, z_hi, flags=1 << 14)
-    assert torch.equal(x, y)
+    z = ops.density_overlap_window(A, B, dr, z_lo, z_hi, flags=1 << 15)
+    assert torch.equal(x, y) and torch.equal(x, z)
     ref = O.density_overlap_fft(a, b, dr)[:, :, z_lo:z_hi]
     assert np.abs(x.cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
 
