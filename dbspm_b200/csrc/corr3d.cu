@@ -428,7 +428,10 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     // persistent software-pipelined blocks (axis_pass_body_v2s) for the plain passes; not with the power fused into the
     // load (the pass is FP64-issue bound and measured slower pipelined), see DBSPM_CORR_NO_PIPE in the header
     const bool powered = use_pow && (alpha0 != 1.0 || alpha1 != 1.0);
-    const bool pipe_off = (flags & DBSPM_CORR_NO_PIPE) || g || mp || powered || !axis2s_ok(pl->host.dev);
+    const bool pipe_off = (flags & DBSPM_CORR_NO_PIPE) || g || mp || !axis2s_ok(pl->host.dev);
+    // powered pass: pipelined on 8-line tiles where those apply (slowest axis of a large grid: 3.91 -> 3.61 ms at n = 1024);
+    // pipelined on 4-line tiles it measured slower than one-shot (4.28 against 3.90 ms), so there it stays one-shot
+    const bool pow_narrow = powered && (flags & DBSPM_CORR_POW_NARROW);
     if (P.v2) {
         axis2_config(n, inner, P.plan.nstages, &P.tshift, &P.tw_smem);
         smem = axis2_smem_bytes(n, P.tshift, P.plan.nstages, P.tw_smem);
@@ -437,10 +440,10 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
         // slowest axis (outer == 1: rows inner*16 bytes apart) and a tile budget that only allows 4-line tiles:
         // measured on B200 at n = 1024, 2 CTAs x 256 threads x T=4 -> 1 CTA x 512 threads x T=8: 2.60 -> 2.32 ms
         // (the same change slows the y pass, whose rows are 2 KB apart, 2.20 -> 2.36 ms)
-        // With the power fused into the load the pass is FP64-issue bound and two CTAs hide it better:
-        // 4.21 ms (2 x 256) against 4.87 ms (1 x 512).
+        // With the power fused into the load the one-shot pass is FP64-issue bound and two CTAs hide it better
+        // (4.21 ms for 2 x 256 against 4.87 ms for 1 x 512); pipelined, the 8-line tiles win (3.61 against 3.91 ms).
         else if (!mp && outer == 1 && P.tshift == 2 && inner >= 65536 && P.plan.nstages > 1 &&
-                 (!(use_pow && (alpha0 != 1.0 || alpha1 != 1.0)) || (flags & DBSPM_CORR_POW_WIDE)) &&
+                 (!powered || (!pipe_off && !pow_narrow) || (flags & DBSPM_CORR_POW_WIDE)) &&
                  axis2_smem_bytes(n, 3, P.plan.nstages, 0) <= 200 * 1024) {
             wide = true;
             P.tshift = 3; P.tw_smem = 0;
@@ -499,15 +502,18 @@ static int launch_axis(const cplx *in0, cplx *out0, const cplx *in1, cplx *out1,
     } else if (P.v2 && mp) {
         DBSPM_CUDA_TRY(cudaFuncSetAttribute(axis_pass2m_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         axis_pass2m_kernel<D><<<dim3((unsigned)nblocks, (unsigned)narrays), AXIS2_THREADS, smem, st>>>(P);
-    } else if (P.v2 && !pipe_off && (outer > 1 || wide) && nblocks * narrays >= 4LL * 148 * (wide ? 1 : AXIS2_MIN_BLOCKS) &&
+    } else if (P.v2 && !pipe_off && (outer > 1 || wide) && (!powered || wide) && nblocks * narrays >= 4LL * 148 * (wide ? 1 : AXIS2_MIN_BLOCKS) &&
                ((long long)(n / P.plan.radix[0]) << P.tshift) == (wide ? 512 : AXIS2_THREADS)) {
         // exactly one first-stage item per thread: its rows travel to the next tile's first stage through cp.async slots + registers
         const int per_sm = wide ? 1 : AXIS2_MIN_BLOCKS;
         P.stage_off = (int)align_up(smem, 16);
         smem = (size_t)P.stage_off + 8 * (size_t)(wide ? 512 : AXIS2_THREADS) * sizeof(cplx);
         const unsigned gx = (unsigned)((148 * per_sm + narrays - 1) / narrays);
-        // (the instantiation with the power exists in the CPU emulation only: on the device the powered pass stays one-shot)
-        if (axis2s_plan_is<16, 8, 8>(P.plan)) rc = launch_axis_pipelined<D, 16, 8, 8, false>(P, gx, narrays, wide, smem, st);
+        // (with the power: the forward instantiation only -- inverse passes have no power)
+        if (powered && D < 0) {
+            if (axis2s_plan_is<16, 8, 8>(P.plan)) rc = launch_axis_pipelined<-1, 16, 8, 8, true>(P, gx, narrays, wide, smem, st);
+            else rc = launch_axis_pipelined<-1, 16, 8, 4, true>(P, gx, narrays, wide, smem, st);
+        } else if (axis2s_plan_is<16, 8, 8>(P.plan)) rc = launch_axis_pipelined<D, 16, 8, 8, false>(P, gx, narrays, wide, smem, st);
         else rc = launch_axis_pipelined<D, 16, 8, 4, false>(P, gx, narrays, wide, smem, st);
         if (rc) return rc;
     } else if (P.v2 && wide) {

@@ -70,12 +70,15 @@ extern "C" {
                                             128, 64) and the pass has many more tiles than resident CTAs, persistent blocks request the next
                                             tile's rows (8 per thread through cp.async into the thread's own shared-memory slots, 8 into
                                             registers) before the remaining stages of the current tile.  B200, n = 1024: y pass 2.39 -> 2.30 ms (2.08 on 8-line tiles),
-                                            x pass on 8-line tiles 2.68 -> 2.42 ms; slower with 4-line tiles on the slowest axis (3.23 ms) and
-                                            with the power fused (4.28 against 3.90 ms), where the one-shot blocks stay */
+                                            x pass on 8-line tiles 2.68 -> 2.42 ms (3.91 -> 3.61 ms with the power fused); slower with 4-line
+                                            tiles on the slowest axis (3.23 ms; 4.28 against 3.90 ms with the power), where the one-shot blocks stay */
 
 #define DBSPM_CORR_PIPE_NARROW_Y (1 << 15) /* A/B: keep 4-line tiles (two CTAs of 256 threads) in the pipelined y-type passes.  Default: 8-line
                                             tiles / one CTA of 512 threads when the rows are at least 64 elements and a multiple of 8
                                             (B200, n = 1024: 2.29 -> 2.08 ms) */
+
+#define DBSPM_CORR_POW_NARROW  (1 << 16)  /* A/B: powered x pass as one-shot blocks on 4-line tiles (the default of round 1) instead of the
+                                            pipelined pass on 8-line tiles (B200, n = 1024: 3.91 against 3.61 ms) */
 
 /* library / build identification: "dbspm_b200 <version> sm_100a" */
 const char *dbspm_version(void);

@@ -21,7 +21,7 @@ for name in (sys.argv[1:] or ["large_slab"]):
     dr = np.array(cfg.cell) / np.array(cfg.shape)
     outs = {}
     for alpha in (1.0, 1.08):
-        for label, fl in (("default", 0), ("nopipe", NO_PIPE), ("narrowy", 1 << 15)):
+        for label, fl in (("default", 0), ("nopipe", NO_PIPE), ("narrowy", 1 << 15), ("pownarrow", 1 << 16)):
             out = torch.empty((nx, ny, 54), dtype=torch.float64, device=dev)
             f = lambda extra=0: ops.density_overlap_window(A, B, dr, 76, 130, alpha, alpha, out=out, flags=fl | extra)
             t = timeit(f)

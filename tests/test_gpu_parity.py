@@ -505,6 +505,11 @@ def test_overlap_large_slab_sampled_direct_sum(ops):
     rhoT, nrhoT = synth.make_tip(cfg, device=dev, variant="noisy")
     sr = ops.density_overlap_window(rhoS, rhoT, dr, z_lo, z_hi, cfg.alpha, cfg.alpha)
     es = ops.density_overlap_window(potS, nrhoT, dr, z_lo, z_hi)
+    # the default passes here are the persistent pipelined ones (8-line tiles, also with the power fused): same bits as the
+    # one-shot passes (DBSPM_CORR_NO_PIPE) and as the one-shot powered pass alone (DBSPM_CORR_POW_NARROW)
+    assert torch.equal(sr, ops.density_overlap_window(rhoS, rhoT, dr, z_lo, z_hi, cfg.alpha, cfg.alpha, flags=1 << 14))
+    assert torch.equal(sr, ops.density_overlap_window(rhoS, rhoT, dr, z_lo, z_hi, cfg.alpha, cfg.alpha, flags=1 << 16))
+    assert torch.equal(es, ops.density_overlap_window(potS, nrhoT, dr, z_lo, z_hi, flags=1 << 14))
     ops.release_workspace()
     rng = np.random.default_rng(20260104)
     pts = np.stack([rng.integers(0, nx, 72), rng.integers(0, ny, 72), rng.integers(z_lo, z_hi, 72)], axis=1)
