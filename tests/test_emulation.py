@@ -72,7 +72,8 @@ def test_corr3d_edge_shapes_all_tile_widths(emu, shape, window):
         assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, window, tshift)
 
 
-@pytest.mark.parametrize("shape,window", [((64, 128, 8), (2, 7)), ((128, 64, 6), (0, 6)), ((512, 3, 4), (1, 3)), ((1024, 2, 4), (0, 2)), ((20, 96, 10), (3, 4))])
+@pytest.mark.parametrize("shape,window", [((64, 128, 8), (2, 7)), ((128, 64, 6), (0, 6)), ((512, 3, 4), (1, 3)), ((1024, 2, 4), (0, 2)), ((20, 96, 10), (3, 4)),
+                                          ((128, 5, 6), (1, 4)), ((64, 7, 10), (0, 9))])       # the last two: ragged last tiles (inner = 15, 35)
 def test_pipelined_axis_pass_is_bit_identical_to_the_one_shot_pass(emu, shape, window):
     """axis_pass_body_v2s (persistent blocks, next tile's rows requested before the remaining stages of the current
     one) does the arithmetic of axis_pass_body_v2 in the same order: same bits, with and without the fused power."""
