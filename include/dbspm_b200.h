@@ -55,7 +55,8 @@ extern "C" {
 #define DBSPM_CORR_PEER_NARROW (1 << 4)  /* fused exchange: keep the 4-line tiles of the local pass (64-byte remote stores; A/B timing) */
 #define DBSPM_CORR_NO_PREFETCH (1 << 5)  /* no L2 prefetch of the next tile / pair group (A/B timing) */
 #define DBSPM_CORR_SLOW_POW   (1 << 6)   /* v^alpha as libdevice exp(alpha*log(v)) instead of the table-driven pow_fast (A/B) */
-#define DBSPM_CORR_POW_WIDE   (1 << 7)   /* powered x pass on 8-line tiles / one CTA of 512 threads as well (A/B timing) */
+#define DBSPM_CORR_POW_WIDE   (1 << 7)   /* with DBSPM_CORR_NO_PIPE: the one-shot powered x pass on 8-line tiles / one CTA of 512 threads (A/B timing;
+                                            pipelined, the powered pass takes 8-line tiles by default, see DBSPM_CORR_POW_NARROW) */
 /* profiling aid: skip stages (results are then meaningless); bench.py times each launch alone */
 #define DBSPM_CORR_SKIP_XFWD  (1 << 8)
 #define DBSPM_CORR_SKIP_YFWD  (1 << 9)
